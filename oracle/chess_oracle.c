@@ -882,6 +882,36 @@ void oc_game_encode(const Game *g, int node_depth, int8_t *planes, int32_t *meta
     meta[6] = cur->halfmove_clock;
 }
 
+/* What the Rust shim hands to the C ABI (include/sc_b200.h, sc_position): the inputs of
+ * `_encode` BEFORE rotation/encoding -- per history slot the python-chess bitboards and the
+ * two repetition flags of `Board::extract` (chess.rs:375-380), plus `encode_meta` of the
+ * current board.  slot layout: [P,N,B,R,Q,K, white occupancy, flags]. */
+void oc_game_pack(const Game *g, int node_depth, u64 *slot /*[8][8]*/, int32_t *meta, int32_t *n_hist_out)
+{
+    memset(slot, 0, sizeof(u64) * 64);
+    int n_hist = node_depth + 1;
+    if (n_hist > 8) n_hist = 8;
+    if (n_hist > g->n + 1) n_hist = g->n + 1;
+    for (int t = 0; t < n_hist; t++) {
+        int ply = g->n - t;
+        const Pos *p = pos_at(g, ply);
+        u64 *s = slot + 8 * t;
+        s[0] = p->pawns; s[1] = p->knights; s[2] = p->bishops;
+        s[3] = p->rooks; s[4] = p->queens; s[5] = p->kings;
+        s[6] = p->occ_co[WHITE];
+        s[7] = (u64)(is_repetition_at(g, ply, 2) ? 1 : 0) | (u64)(is_repetition_at(g, ply, 3) ? 2 : 0);
+    }
+    const Pos *cur = &g->cur;
+    meta[0] = cur->turn;
+    meta[1] = cur->fullmove_number;
+    meta[2] = has_kingside_castling_rights(cur, cur->turn);
+    meta[3] = has_queenside_castling_rights(cur, cur->turn);
+    meta[4] = has_kingside_castling_rights(cur, !cur->turn);
+    meta[5] = has_queenside_castling_rights(cur, !cur->turn);
+    meta[6] = cur->halfmove_clock;
+    *n_hist_out = n_hist;
+}
+
 /* ------------------------------------------------------------------------------------ */
 /* move index (queenmoves.rs / knightmoves.rs / underpromotions.rs)                     */
 /* ------------------------------------------------------------------------------------ */

@@ -46,6 +46,7 @@ def lib():
         L.oc_game_piece_at.argtypes = [C.c_void_p, C.c_int]
         L.oc_game_is_repetition.argtypes = [C.c_void_p, C.c_int]
         L.oc_game_encode.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.oc_game_pack.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oc_game_outcome.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         L.oc_move_index.argtypes = [C.c_int] * 4
         L.oc_perft.restype = C.c_uint64
@@ -157,6 +158,16 @@ class Game:
         meta = np.zeros(7, dtype=np.int32)
         lib().oc_game_encode(self._p, node_depth, planes.ctypes.data, meta.ctypes.data)
         return planes, meta
+
+    def pack(self, node_depth: int | None = None):
+        """The sc_position a Rust shim would build: (slot u64[8,8], meta i32[7], n_hist)."""
+        if node_depth is None:
+            node_depth = self.ply
+        slot = np.zeros((8, 8), dtype=np.uint64)
+        meta = np.zeros(7, dtype=np.int32)
+        nh = C.c_int32(0)
+        lib().oc_game_pack(self._p, node_depth, slot.ctypes.data, meta.ctypes.data, C.byref(nh))
+        return slot, meta, nh.value
 
     def outcome(self, claim_draw: bool = True):
         w = C.c_int(-1)

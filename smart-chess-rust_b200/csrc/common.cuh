@@ -1,0 +1,84 @@
+// Shared declarations for the B200 leaf-evaluation backend (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/sc_b200.h"
+
+namespace scb {
+
+void set_error(const std::string &msg);
+
+#define SCB_CUDA(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            scb::set_error(std::string(#expr) + ": " + cudaGetErrorString(e__));               \
+            return SC_E_CUDA;                                                                  \
+        }                                                                                      \
+    } while (0)
+
+#define SCB_CHECK(expr)                                                                        \
+    do {                                                                                       \
+        int r__ = (expr);                                                                      \
+        if (r__ != SC_OK) return r__;                                                          \
+    } while (0)
+
+constexpr int C_TOWER = 256;     // tower width (py/module.py:120)
+constexpr int C_IN = 112;        // input planes
+constexpr int C_IN_PAD = 128;    // bf16 path: planes padded to two 64-channel K chunks
+constexpr int C_SE = 128;        // SqueezeExcitation(256, 128) (py/module.py:29-33)
+constexpr int C_POLICY = 73;
+constexpr int LD_POLICY = 80;    // row stride of the policy logits buffer [B][64][80]
+constexpr int N_VALUE_HIDDEN = 128;
+constexpr float LN_EPS = 1e-6f;  // timm LayerNorm2d
+
+// ---- encode.cu ---------------------------------------------------------------------------
+// planes: one warp per position. out element (b, s, c), s = rank*8+file, c < ld.
+int launch_encode_i8(const sc_position *d_pos, int n, int8_t *out, int32_t *meta_out, cudaStream_t st);
+int launch_encode_f32(const sc_position *d_pos, int n, float *out /*[n][64][112]*/, float *meta_out /*[n][8]*/,
+                      cudaStream_t st);
+int launch_encode_bf16(const sc_position *d_pos, int n, __nv_bfloat16 *out /*[n][64][128]*/,
+                       float *meta_out /*[n][8]*/, cudaStream_t st);
+// NCHW float planes (sc_forward_only input) -> NHWC
+int launch_nchw_to_nhwc_f32(const float *in, int n, float *out, cudaStream_t st);
+int launch_nchw_to_nhwc_bf16(const float *in, int n, __nv_bfloat16 *out, cudaStream_t st);
+
+// ---- policy.cu ----------------------------------------------------------------------------
+// logits [n][64][LD_POLICY] fp32 (square-major) -> per-leaf log-sum-exp, legal-move gather,
+// exp, sequential renormalisation; optional move index dump / full logp dump.
+int launch_move_index(const sc_position *d_pos, const sc_move *d_moves, const int32_t *d_off, int n,
+                      int32_t *d_index, cudaStream_t st);
+int launch_policy_gather(const float *logits, const sc_position *d_pos, const sc_move *d_moves,
+                         const int32_t *d_off, int n, float *d_priors, cudaStream_t st);
+int launch_policy_logp_full(const float *logits, int n, float *d_logp /*[n][4672]*/, cudaStream_t st);
+
+// ---- tower_f32.cu -------------------------------------------------------------------------
+// C[M][N] = gather_taps(A)[M][TAPS*K] * W[TAPS*K][ldw] + bias ; A is [rows][lda] fp32
+int launch_gemm_f32(int taps, const float *A, int lda, const float *W, int ldw, const float *bias, float *out,
+                    int ldo, int M, int N, int K, cudaStream_t st);
+int launch_ln_f32(float *x, int rows, int C, int ld, const float *gamma, const float *beta, int relu,
+                  cudaStream_t st);
+int launch_se_res_f32(const float *y, const float *x, float *out, int n, const float *w1t, const float *b1,
+                      const float *w2t, const float *b2, cudaStream_t st);
+int launch_value_finish(const float *hidden_pre, int n_split, int n, const float *meta, const float *w_meta,
+                        const float *b1, const float *w2, const float *b2, float *value_out, cudaStream_t st);
+
+// ---- tower_bf16.cu (tcgen05) --------------------------------------------------------------
+struct TcConv;  // opaque per-layer state (tensor maps)
+int tc_conv_create(TcConv **out, const __nv_bfloat16 *w /*[taps][256][cin_pad]*/, int taps, int cin_pad,
+                   const float *bias, const float *gamma, const float *beta);
+void tc_conv_destroy(TcConv *c);
+// out = LN(conv(in) + bias) * gamma + beta, optional ReLU; in/out bf16 NHWC [n_boards][64][C]
+int tc_conv_launch(TcConv *c, const __nv_bfloat16 *in, int n_boards_alloc, int n_boards, __nv_bfloat16 *out,
+                   int relu, int num_sms, cudaStream_t st);
+int launch_se_res_bf16(const __nv_bfloat16 *y, const __nv_bfloat16 *x, __nv_bfloat16 *out, int n,
+                       const float *w1t, const float *b1, const float *w2t, const float *b2, cudaStream_t st);
+int launch_policy_conv2_bf16(const __nv_bfloat16 *p1, int n, const float *w /*[256][80]*/, const float *bias,
+                             const float *gamma, const float *beta, float *logits, cudaStream_t st);
+int launch_value_fc_bf16(const __nv_bfloat16 *v1 /*[n][16384]*/, int n, const __nv_bfloat16 *w /*[16384][128]*/,
+                         float *hidden_pre /*[n_split][n][128]*/, int n_split, cudaStream_t st);
+
+}  // namespace scb

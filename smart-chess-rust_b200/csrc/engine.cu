@@ -1,0 +1,627 @@
+// sc_engine: weight loading / re-layout, device buffers, and the C ABI of include/sc_b200.h.
+//
+// One call of sc_eval() is the reference's `chess_tch_predict` (src/backends/torch.rs:89-146)
+// for n leaves at once: H2D of the packed positions and legal moves, plane encode, the
+// policy/value network, move-index gather + renormalisation, D2H of priors and values.
+// There is no CPU fallback: without an sm_100 device sc_create() fails with SC_E_NOGPU.
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace scb {
+
+static thread_local std::string g_err;
+void set_error(const std::string &msg) { g_err = msg; }
+
+struct Tensor {
+    std::vector<uint32_t> dims;
+    const float *data;
+    size_t numel;
+};
+
+struct Blob {
+    std::vector<char> raw;
+    std::map<std::string, Tensor> t;
+    int n_blocks = 0;
+};
+
+static int read_blob(const char *path, Blob &b)
+{
+    FILE *f = fopen(path, "rb");
+    if (!f) {
+        set_error(std::string("cannot open weight blob: ") + path);
+        return SC_E_IO;
+    }
+    fseek(f, 0, SEEK_END);
+    long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    b.raw.resize((size_t)sz);
+    size_t got = fread(b.raw.data(), 1, (size_t)sz, f);
+    fclose(f);
+    if (got != (size_t)sz || sz < 16 || memcmp(b.raw.data(), "SCB2WTS1", 8) != 0) {
+        set_error("weight blob: bad magic or short read");
+        return SC_E_IO;
+    }
+    const char *p = b.raw.data() + 8, *end = b.raw.data() + sz;
+    auto rd32 = [&](uint32_t &v) { if (p + 4 > end) return false; memcpy(&v, p, 4); p += 4; return true; };
+    auto rd64 = [&](uint64_t &v) { if (p + 8 > end) return false; memcpy(&v, p, 8); p += 8; return true; };
+    uint32_t nb, nt;
+    if (!rd32(nb) || !rd32(nt)) goto bad;
+    b.n_blocks = (int)nb;
+    struct Ent { std::string name; std::vector<uint32_t> dims; uint64_t off, numel; };
+    {
+        std::vector<Ent> ents(nt);
+        for (uint32_t i = 0; i < nt; i++) {
+            uint32_t nl, nd;
+            if (!rd32(nl) || p + nl > end) goto bad;
+            ents[i].name.assign(p, nl);
+            p += nl;
+            if (!rd32(nd) || nd > 8) goto bad;
+            ents[i].dims.resize(nd);
+            for (uint32_t d = 0; d < nd; d++)
+                if (!rd32(ents[i].dims[d])) goto bad;
+            if (!rd64(ents[i].off) || !rd64(ents[i].numel)) goto bad;
+        }
+        uint64_t data_bytes;
+        if (!rd64(data_bytes) || p + data_bytes > end) goto bad;
+        for (auto &e : ents) {
+            if (e.off + e.numel * 4 > data_bytes) goto bad;
+            b.t[e.name] = Tensor{e.dims, reinterpret_cast<const float *>(p + e.off), (size_t)e.numel};
+        }
+    }
+    return SC_OK;
+bad:
+    set_error("weight blob: malformed header");
+    return SC_E_IO;
+}
+
+static uint16_t f2bf(float f)
+{
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+    u += 0x7fffu + ((u >> 16) & 1u);  // round to nearest even
+    return (uint16_t)(u >> 16);
+}
+
+struct ConvW {
+    int taps = 1, cin = 0, cin_pad = 0, cout = 0, ldw = 0;
+    float *w_f32 = nullptr;          // [taps][cin][ldw]        (fp32 mode)
+    __nv_bfloat16 *w_bf16 = nullptr; // [taps][cout][cin_pad]   (bf16 mode, K-major B operand)
+    float *bias = nullptr, *gamma = nullptr, *beta = nullptr;
+    TcConv *tc = nullptr;
+};
+
+struct SeW {
+    float *w1t = nullptr, *b1 = nullptr, *w2t = nullptr, *b2 = nullptr;
+};
+
+}  // namespace scb
+
+using namespace scb;
+
+struct sc_engine {
+    int device = 0, mode = 0, max_batch = 0, n_blocks = 0, num_sms = 148;
+    int alloc_boards = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<void *> allocs;
+    ConvW stem;
+    std::vector<ConvW> conv1, conv2;
+    std::vector<SeW> se;
+    ConvW pol1, pol2, val1;
+    float *pol2_w80 = nullptr;            // bf16 mode: [256][80] fp32 for the CUDA-core policy conv
+    float *vfc_w_f32 = nullptr;           // [16384][128]
+    __nv_bfloat16 *vfc_w_bf16 = nullptr;  // [16384][128]
+    float *v_wmeta = nullptr, *v_b1 = nullptr, *v_w2 = nullptr, *v_b2 = nullptr;
+    // io
+    sc_position *d_pos = nullptr;
+    sc_move *d_moves = nullptr;
+    int32_t *d_off = nullptr;
+    float *d_priors = nullptr, *d_value = nullptr, *d_meta = nullptr;
+    int32_t *d_index = nullptr;
+    int max_moves_total = 0;
+    // activations
+    float *f_planes = nullptr, *f_x = nullptr, *f_t = nullptr, *f_y = nullptr;
+    __nv_bfloat16 *h_planes = nullptr, *h_x = nullptr, *h_t = nullptr, *h_y = nullptr;
+    float *logits = nullptr, *vpre = nullptr;
+    int vsplit = 1;
+    // gates
+    void *d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+    // accounting
+    int64_t launches = 0;
+    int timing = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    float last_tower_ms = 0.f, last_total_ms = 0.f;
+};
+
+namespace scb {
+
+template <typename T> static int dev_alloc(sc_engine *e, T **p, size_t count)
+{
+    void *q = nullptr;
+    SCB_CUDA(cudaMalloc(&q, count * sizeof(T) + 256));
+    SCB_CUDA(cudaMemset(q, 0, count * sizeof(T) + 256));
+    e->allocs.push_back(q);
+    *p = reinterpret_cast<T *>(q);
+    return SC_OK;
+}
+
+template <typename T> static int upload(sc_engine *e, T **p, const std::vector<T> &h)
+{
+    SCB_CHECK(dev_alloc(e, p, h.size()));
+    SCB_CUDA(cudaMemcpy(*p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return SC_OK;
+}
+
+static const Tensor *find(const Blob &b, const std::string &name)
+{
+    auto it = b.t.find(name);
+    if (it == b.t.end()) {
+        set_error("weight blob: missing tensor " + name);
+        return nullptr;
+    }
+    return &it->second;
+}
+
+static int upload_vec(sc_engine *e, const Blob &b, const std::string &name, size_t expect, float **out)
+{
+    const Tensor *t = find(b, name);
+    if (!t) return SC_E_IO;
+    if (t->numel != expect) {
+        set_error("weight blob: wrong size for " + name);
+        return SC_E_IO;
+    }
+    std::vector<float> h(t->data, t->data + t->numel);
+    return upload(e, out, h);
+}
+
+// conv weight [cout][cin][k][k] + bias + LayerNorm gamma/beta -> device layouts
+static int load_conv(sc_engine *e, const Blob &b, const std::string &wname, const std::string &lnname, int taps,
+                     int cin, int cout, ConvW &c)
+{
+    const Tensor *w = find(b, wname + ".weight");
+    if (!w) return SC_E_IO;
+    if (w->numel != (size_t)cout * cin * taps) {
+        set_error("weight blob: wrong size for " + wname);
+        return SC_E_IO;
+    }
+    c.taps = taps;
+    c.cin = cin;
+    c.cout = cout;
+    c.cin_pad = (cin + 63) / 64 * 64;
+    c.ldw = (cout + 127) / 128 * 128;
+    SCB_CHECK(upload_vec(e, b, wname + ".bias", cout, &c.bias));
+    SCB_CHECK(upload_vec(e, b, lnname + ".weight", cout, &c.gamma));
+    SCB_CHECK(upload_vec(e, b, lnname + ".bias", cout, &c.beta));
+    if (e->mode == SC_MODE_FP32) {
+        std::vector<float> h((size_t)taps * cin * c.ldw, 0.f);
+        for (int co = 0; co < cout; co++)
+            for (int ci = 0; ci < cin; ci++)
+                for (int t = 0; t < taps; t++)
+                    h[((size_t)t * cin + ci) * c.ldw + co] = w->data[((size_t)co * cin + ci) * taps + t];
+        SCB_CHECK(upload(e, &c.w_f32, h));
+    } else if (cout == C_TOWER) {
+        std::vector<uint16_t> h((size_t)taps * cout * c.cin_pad, 0);
+        for (int co = 0; co < cout; co++)
+            for (int ci = 0; ci < cin; ci++)
+                for (int t = 0; t < taps; t++)
+                    h[((size_t)t * cout + co) * c.cin_pad + ci] = f2bf(w->data[((size_t)co * cin + ci) * taps + t]);
+        uint16_t *d = nullptr;
+        SCB_CHECK(upload(e, &d, h));
+        c.w_bf16 = reinterpret_cast<__nv_bfloat16 *>(d);
+        SCB_CHECK(tc_conv_create(&c.tc, c.w_bf16, taps, c.cin_pad, c.bias, c.gamma, c.beta));
+    }
+    return SC_OK;
+}
+
+static int load_weights(sc_engine *e, const Blob &b)
+{
+    e->n_blocks = b.n_blocks;
+    SCB_CHECK(load_conv(e, b, "conv_block.0", "conv_block.1", 9, C_IN, C_TOWER, e->stem));
+    e->conv1.resize(b.n_blocks);
+    e->conv2.resize(b.n_blocks);
+    e->se.resize(b.n_blocks);
+    for (int i = 0; i < b.n_blocks; i++) {
+        std::string p = "res_blocks." + std::to_string(i) + ".";
+        SCB_CHECK(load_conv(e, b, p + "conv1", p + "bn1", 9, C_TOWER, C_TOWER, e->conv1[i]));
+        SCB_CHECK(load_conv(e, b, p + "conv2", p + "bn2", 9, C_TOWER, C_TOWER, e->conv2[i]));
+        const Tensor *f1 = find(b, p + "se.fc1.weight"), *f2 = find(b, p + "se.fc2.weight");
+        if (!f1 || !f2) return SC_E_IO;
+        if (f1->numel != (size_t)C_SE * C_TOWER || f2->numel != (size_t)C_SE * C_TOWER) {
+            set_error("weight blob: wrong SE size");
+            return SC_E_IO;
+        }
+        std::vector<float> w1t((size_t)C_TOWER * C_SE), w2t((size_t)C_SE * C_TOWER);
+        for (int j = 0; j < C_SE; j++)
+            for (int c = 0; c < C_TOWER; c++) {
+                w1t[(size_t)c * C_SE + j] = f1->data[(size_t)j * C_TOWER + c];
+                w2t[(size_t)j * C_TOWER + c] = f2->data[(size_t)c * C_SE + j];
+            }
+        SCB_CHECK(upload(e, &e->se[i].w1t, w1t));
+        SCB_CHECK(upload(e, &e->se[i].w2t, w2t));
+        SCB_CHECK(upload_vec(e, b, p + "se.fc1.bias", C_SE, &e->se[i].b1));
+        SCB_CHECK(upload_vec(e, b, p + "se.fc2.bias", C_TOWER, &e->se[i].b2));
+    }
+    SCB_CHECK(load_conv(e, b, "policy_head.model.0", "policy_head.model.1", 1, C_TOWER, C_TOWER, e->pol1));
+    SCB_CHECK(load_conv(e, b, "policy_head.model.2", "policy_head.model.3", 1, C_TOWER, C_POLICY, e->pol2));
+    SCB_CHECK(load_conv(e, b, "value_head.conv.0", "value_head.conv.1", 1, C_TOWER, C_TOWER, e->val1));
+    if (e->mode == SC_MODE_BF16) {
+        const Tensor *w = find(b, "policy_head.model.2.weight");
+        std::vector<float> h((size_t)C_TOWER * LD_POLICY, 0.f);
+        for (int co = 0; co < C_POLICY; co++)
+            for (int ci = 0; ci < C_TOWER; ci++) h[(size_t)ci * LD_POLICY + co] = w->data[(size_t)co * C_TOWER + ci];
+        SCB_CHECK(upload(e, &e->pol2_w80, h));
+    }
+    // value FC: [128][16391], columns c*64+s (NCHW flatten, py/module.py:93) then 7 meta
+    const Tensor *fc = find(b, "value_head.ffn.0.weight");
+    if (!fc) return SC_E_IO;
+    const int KV = 64 * C_TOWER, KT = KV + SC_N_META;
+    if (fc->numel != (size_t)N_VALUE_HIDDEN * KT) {
+        set_error("weight blob: wrong value FC size");
+        return SC_E_IO;
+    }
+    {
+        std::vector<float> wm((size_t)SC_N_META * N_VALUE_HIDDEN);
+        for (int j = 0; j < N_VALUE_HIDDEN; j++)
+            for (int m = 0; m < SC_N_META; m++) wm[(size_t)m * N_VALUE_HIDDEN + j] = fc->data[(size_t)j * KT + KV + m];
+        SCB_CHECK(upload(e, &e->v_wmeta, wm));
+        // re-index K for NHWC activations: k' = s*256 + c  <-  k = c*64 + s
+        if (e->mode == SC_MODE_FP32) {
+            std::vector<float> h((size_t)KV * N_VALUE_HIDDEN);
+            for (int j = 0; j < N_VALUE_HIDDEN; j++)
+                for (int c = 0; c < C_TOWER; c++)
+                    for (int s = 0; s < 64; s++)
+                        h[((size_t)s * C_TOWER + c) * N_VALUE_HIDDEN + j] = fc->data[(size_t)j * KT + c * 64 + s];
+            SCB_CHECK(upload(e, &e->vfc_w_f32, h));
+        } else {
+            std::vector<uint16_t> h((size_t)KV * N_VALUE_HIDDEN);
+            for (int j = 0; j < N_VALUE_HIDDEN; j++)
+                for (int c = 0; c < C_TOWER; c++)
+                    for (int s = 0; s < 64; s++)
+                        h[((size_t)s * C_TOWER + c) * N_VALUE_HIDDEN + j] = f2bf(fc->data[(size_t)j * KT + c * 64 + s]);
+            uint16_t *d = nullptr;
+            SCB_CHECK(upload(e, &d, h));
+            e->vfc_w_bf16 = reinterpret_cast<__nv_bfloat16 *>(d);
+        }
+    }
+    SCB_CHECK(upload_vec(e, b, "value_head.ffn.0.bias", N_VALUE_HIDDEN, &e->v_b1));
+    SCB_CHECK(upload_vec(e, b, "value_head.ffn.2.weight", N_VALUE_HIDDEN, &e->v_w2));
+    SCB_CHECK(upload_vec(e, b, "value_head.ffn.2.bias", 1, &e->v_b2));
+    return SC_OK;
+}
+
+static int alloc_buffers(sc_engine *e)
+{
+    const int B = (e->max_batch + 1) & ~1;
+    e->alloc_boards = B;
+    e->max_moves_total = e->max_batch * SC_MAX_MOVES;
+    SCB_CHECK(dev_alloc(e, &e->d_pos, (size_t)B));
+    SCB_CHECK(dev_alloc(e, &e->d_moves, (size_t)e->max_moves_total));
+    SCB_CHECK(dev_alloc(e, &e->d_off, (size_t)B + 1));
+    SCB_CHECK(dev_alloc(e, &e->d_priors, (size_t)e->max_moves_total));
+    SCB_CHECK(dev_alloc(e, &e->d_index, (size_t)e->max_moves_total));
+    SCB_CHECK(dev_alloc(e, &e->d_value, (size_t)B));
+    SCB_CHECK(dev_alloc(e, &e->d_meta, (size_t)B * 8));
+    SCB_CHECK(dev_alloc(e, &e->logits, (size_t)B * 64 * LD_POLICY));
+    const size_t act = (size_t)B * 64 * C_TOWER;
+    if (e->mode == SC_MODE_FP32) {
+        e->vsplit = 1;
+        SCB_CHECK(dev_alloc(e, &e->f_planes, (size_t)B * 64 * C_IN));
+        SCB_CHECK(dev_alloc(e, &e->f_x, act));
+        SCB_CHECK(dev_alloc(e, &e->f_t, act));
+        SCB_CHECK(dev_alloc(e, &e->f_y, act));
+    } else {
+        e->vsplit = 8;
+        SCB_CHECK(dev_alloc(e, &e->h_planes, (size_t)B * 64 * C_IN_PAD));
+        SCB_CHECK(dev_alloc(e, &e->h_x, act));
+        SCB_CHECK(dev_alloc(e, &e->h_t, act));
+        SCB_CHECK(dev_alloc(e, &e->h_y, act));
+    }
+    SCB_CHECK(dev_alloc(e, &e->vpre, (size_t)e->vsplit * B * N_VALUE_HIDDEN));
+    // scratch for the gates: max(int8 planes + meta, fp32 NCHW planes + logp)
+    e->scratch_bytes = (size_t)B * ((size_t)SC_N_PLANES * 64 * 4 + (size_t)SC_N_POLICY * 4 + 64);
+    SCB_CHECK(dev_alloc(e, reinterpret_cast<char **>(&e->d_scratch), e->scratch_bytes));
+    return SC_OK;
+}
+
+// the network on n boards; planes already in f_planes / h_planes, meta in d_meta.
+static int run_network(sc_engine *e, int n, cudaStream_t st)
+{
+    const int rows = n * 64;
+    if (e->timing) SCB_CUDA(cudaEventRecord(e->ev[1], st));
+    if (e->mode == SC_MODE_FP32) {
+        auto conv = [&](const ConvW &c, const float *in, int lda, float *out, int relu) -> int {
+            SCB_CHECK(launch_gemm_f32(c.taps, in, lda, c.w_f32, c.ldw, c.bias, out, C_TOWER, rows, c.cout, c.cin, st));
+            SCB_CHECK(launch_ln_f32(out, rows, c.cout, C_TOWER, c.gamma, c.beta, relu, st));
+            e->launches += 2;
+            return SC_OK;
+        };
+        SCB_CHECK(conv(e->stem, e->f_planes, C_IN, e->f_x, 1));
+        for (int i = 0; i < e->n_blocks; i++) {
+            SCB_CHECK(conv(e->conv1[i], e->f_x, C_TOWER, e->f_t, 1));
+            SCB_CHECK(conv(e->conv2[i], e->f_t, C_TOWER, e->f_y, 0));
+            SCB_CHECK(launch_se_res_f32(e->f_y, e->f_x, e->f_x, n, e->se[i].w1t, e->se[i].b1, e->se[i].w2t,
+                                        e->se[i].b2, st));
+            e->launches += 1;
+        }
+        if (e->timing) SCB_CUDA(cudaEventRecord(e->ev[2], st));
+        // policy head
+        SCB_CHECK(conv(e->pol1, e->f_x, C_TOWER, e->f_t, 0));
+        SCB_CHECK(launch_gemm_f32(1, e->f_t, C_TOWER, e->pol2.w_f32, e->pol2.ldw, e->pol2.bias, e->logits, LD_POLICY,
+                                  rows, C_POLICY, C_TOWER, st));
+        SCB_CHECK(launch_ln_f32(e->logits, rows, C_POLICY, LD_POLICY, e->pol2.gamma, e->pol2.beta, 0, st));
+        // value head
+        SCB_CHECK(conv(e->val1, e->f_x, C_TOWER, e->f_y, 1));
+        SCB_CHECK(launch_gemm_f32(1, e->f_y, 64 * C_TOWER, e->vfc_w_f32, N_VALUE_HIDDEN, nullptr, e->vpre,
+                                  N_VALUE_HIDDEN, n, N_VALUE_HIDDEN, 64 * C_TOWER, st));
+        e->launches += 3;
+    } else {
+        const int nb = e->alloc_boards;
+        SCB_CHECK(tc_conv_launch(e->stem.tc, e->h_planes, nb, n, e->h_x, 1, e->num_sms, st));
+        e->launches += 1;
+        for (int i = 0; i < e->n_blocks; i++) {
+            SCB_CHECK(tc_conv_launch(e->conv1[i].tc, e->h_x, nb, n, e->h_t, 1, e->num_sms, st));
+            SCB_CHECK(tc_conv_launch(e->conv2[i].tc, e->h_t, nb, n, e->h_y, 0, e->num_sms, st));
+            SCB_CHECK(launch_se_res_bf16(e->h_y, e->h_x, e->h_x, n, e->se[i].w1t, e->se[i].b1, e->se[i].w2t,
+                                         e->se[i].b2, st));
+            e->launches += 3;
+        }
+        if (e->timing) SCB_CUDA(cudaEventRecord(e->ev[2], st));
+        SCB_CHECK(tc_conv_launch(e->pol1.tc, e->h_x, nb, n, e->h_t, 0, e->num_sms, st));
+        SCB_CHECK(launch_policy_conv2_bf16(e->h_t, n, e->pol2_w80, e->pol2.bias, e->pol2.gamma, e->pol2.beta,
+                                           e->logits, st));
+        SCB_CHECK(tc_conv_launch(e->val1.tc, e->h_x, nb, n, e->h_y, 1, e->num_sms, st));
+        SCB_CHECK(launch_value_fc_bf16(e->h_y, n, e->vfc_w_bf16, e->vpre, e->vsplit, st));
+        e->launches += 4;
+    }
+    SCB_CHECK(launch_value_finish(e->vpre, e->vsplit, n, e->d_meta, e->v_wmeta, e->v_b1, e->v_w2, e->v_b2,
+                                  e->d_value, st));
+    e->launches += 1;
+    return SC_OK;
+}
+
+static int encode_for_mode(sc_engine *e, const sc_position *d_pos, int n, cudaStream_t st)
+{
+    e->launches += 1;
+    if (e->mode == SC_MODE_FP32) return launch_encode_f32(d_pos, n, e->f_planes, e->d_meta, st);
+    return launch_encode_bf16(d_pos, n, e->h_planes, e->d_meta, st);
+}
+
+static int finish_timing(sc_engine *e, cudaStream_t st)
+{
+    if (!e->timing) return SC_OK;
+    SCB_CUDA(cudaEventRecord(e->ev[3], st));
+    SCB_CUDA(cudaEventSynchronize(e->ev[3]));
+    SCB_CUDA(cudaEventElapsedTime(&e->last_tower_ms, e->ev[1], e->ev[2]));
+    SCB_CUDA(cudaEventElapsedTime(&e->last_total_ms, e->ev[0], e->ev[3]));
+    return SC_OK;
+}
+
+}  // namespace scb
+
+extern "C" {
+
+const char *sc_last_error(void) { return g_err.c_str(); }
+
+int sc_create(const char *weights_blob_path, int device, int mode, int max_batch, sc_engine **out)
+{
+    if (!out || !weights_blob_path || max_batch <= 0 || (mode != SC_MODE_FP32 && mode != SC_MODE_BF16)) {
+        set_error("sc_create: bad argument");
+        return SC_E_INVAL;
+    }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device >= ndev) {
+        set_error("sc_create: no CUDA device (this backend has no CPU fallback)");
+        return SC_E_NOGPU;
+    }
+    cudaDeviceProp prop;
+    SCB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("sc_create: device is not sm_100 (Blackwell B200); kernels are built for sm_100a only");
+        return SC_E_NOGPU;
+    }
+    SCB_CUDA(cudaSetDevice(device));
+    Blob blob;
+    SCB_CHECK(read_blob(weights_blob_path, blob));
+    sc_engine *e = new sc_engine();
+    e->device = device;
+    e->mode = mode;
+    e->max_batch = max_batch;
+    e->num_sms = prop.multiProcessorCount;
+    int rc = SC_OK;
+    do {
+        if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = SC_E_CUDA; set_error("stream create failed"); break; }
+        for (int i = 0; i < 4; i++)
+            if (cudaEventCreate(&e->ev[i]) != cudaSuccess) { rc = SC_E_CUDA; set_error("event create failed"); break; }
+        if (rc) break;
+        if ((rc = load_weights(e, blob)) != SC_OK) break;
+        if ((rc = alloc_buffers(e)) != SC_OK) break;
+        if (cudaDeviceSynchronize() != cudaSuccess) { rc = SC_E_CUDA; set_error("sync after weight upload failed"); break; }
+    } while (0);
+    if (rc != SC_OK) {
+        sc_destroy(e);
+        return rc;
+    }
+    *out = e;
+    return SC_OK;
+}
+
+int sc_destroy(sc_engine *e)
+{
+    if (!e) return SC_OK;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    auto kill = [](ConvW &c) { if (c.tc) tc_conv_destroy(c.tc); c.tc = nullptr; };
+    kill(e->stem); kill(e->pol1); kill(e->pol2); kill(e->val1);
+    for (auto &c : e->conv1) kill(c);
+    for (auto &c : e->conv2) kill(c);
+    for (void *p : e->allocs) cudaFree(p);
+    for (int i = 0; i < 4; i++)
+        if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return SC_OK;
+}
+
+int sc_info(const sc_engine *e, int *n_res_blocks, int *max_batch, int *mode)
+{
+    if (!e) return SC_E_INVAL;
+    if (n_res_blocks) *n_res_blocks = e->n_blocks;
+    if (max_batch) *max_batch = e->max_batch;
+    if (mode) *mode = e->mode;
+    return SC_OK;
+}
+
+int sc_eval_device(sc_engine *e, int n, const void *d_pos, const void *d_moves, const void *d_move_off,
+                   int n_moves_total, void *d_priors_out, void *d_value_out, void *stream)
+{
+    if (!e || n < 0 || n > e->max_batch) {
+        set_error("sc_eval_device: bad n");
+        return SC_E_INVAL;
+    }
+    (void)n_moves_total;
+    if (n == 0) return SC_OK;
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+    SCB_CUDA(cudaSetDevice(e->device));
+    if (e->timing) SCB_CUDA(cudaEventRecord(e->ev[0], st));
+    const sc_position *pos = static_cast<const sc_position *>(d_pos);
+    SCB_CHECK(encode_for_mode(e, pos, n, st));
+    // value goes straight to the caller's buffer
+    float *saved = e->d_value;
+    e->d_value = static_cast<float *>(d_value_out);
+    int rc = run_network(e, n, st);
+    e->d_value = saved;
+    SCB_CHECK(rc);
+    SCB_CHECK(launch_policy_gather(e->logits, pos, static_cast<const sc_move *>(d_moves),
+                                   static_cast<const int32_t *>(d_move_off), n, static_cast<float *>(d_priors_out), st));
+    e->launches += 1;
+    return finish_timing(e, st);
+}
+
+int sc_eval(sc_engine *e, int n, const sc_position *pos, const sc_move *moves, const int32_t *move_off,
+            float *priors_out, float *value_out, void *stream)
+{
+    if (!e || n < 0 || n > e->max_batch || (n > 0 && (!pos || !moves || !move_off || !priors_out || !value_out))) {
+        set_error("sc_eval: bad argument");
+        return SC_E_INVAL;
+    }
+    if (n == 0) return SC_OK;
+    const int total = move_off[n];
+    if (move_off[0] != 0 || total < 0 || total > e->max_moves_total) {
+        set_error("sc_eval: bad move offsets");
+        return SC_E_INVAL;
+    }
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+    SCB_CUDA(cudaSetDevice(e->device));
+    SCB_CUDA(cudaMemcpyAsync(e->d_pos, pos, sizeof(sc_position) * (size_t)n, cudaMemcpyHostToDevice, st));
+    SCB_CUDA(cudaMemcpyAsync(e->d_off, move_off, sizeof(int32_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+    if (total) SCB_CUDA(cudaMemcpyAsync(e->d_moves, moves, sizeof(sc_move) * (size_t)total, cudaMemcpyHostToDevice, st));
+    SCB_CHECK(sc_eval_device(e, n, e->d_pos, e->d_moves, e->d_off, total, e->d_priors, e->d_value, st));
+    if (total) SCB_CUDA(cudaMemcpyAsync(priors_out, e->d_priors, sizeof(float) * (size_t)total, cudaMemcpyDeviceToHost, st));
+    SCB_CUDA(cudaMemcpyAsync(value_out, e->d_value, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    SCB_CUDA(cudaStreamSynchronize(st));
+    return SC_OK;
+}
+
+int sc_encode_only(sc_engine *e, int n, const sc_position *pos, int8_t *planes_out, int32_t *meta_out)
+{
+    if (!e || n < 0 || n > e->max_batch || (n > 0 && (!pos || !planes_out || !meta_out))) {
+        set_error("sc_encode_only: bad argument");
+        return SC_E_INVAL;
+    }
+    if (n == 0) return SC_OK;
+    cudaStream_t st = e->stream;
+    SCB_CUDA(cudaSetDevice(e->device));
+    int8_t *d_planes = static_cast<int8_t *>(e->d_scratch);
+    int32_t *d_meta = reinterpret_cast<int32_t *>(d_planes + (((size_t)n * 64 * SC_N_PLANES + 255) & ~(size_t)255));
+    SCB_CUDA(cudaMemcpyAsync(e->d_pos, pos, sizeof(sc_position) * (size_t)n, cudaMemcpyHostToDevice, st));
+    SCB_CHECK(launch_encode_i8(e->d_pos, n, d_planes, d_meta, st));
+    e->launches += 1;
+    SCB_CUDA(cudaMemcpyAsync(planes_out, d_planes, (size_t)n * 64 * SC_N_PLANES, cudaMemcpyDeviceToHost, st));
+    SCB_CUDA(cudaMemcpyAsync(meta_out, d_meta, (size_t)n * SC_N_META * 4, cudaMemcpyDeviceToHost, st));
+    SCB_CUDA(cudaStreamSynchronize(st));
+    return SC_OK;
+}
+
+int sc_move_index_only(sc_engine *e, int n, const sc_position *pos, const sc_move *moves, const int32_t *move_off,
+                       int32_t *index_out)
+{
+    if (!e || n < 0 || n > e->max_batch || (n > 0 && (!pos || !moves || !move_off || !index_out))) {
+        set_error("sc_move_index_only: bad argument");
+        return SC_E_INVAL;
+    }
+    if (n == 0) return SC_OK;
+    const int total = move_off[n];
+    if (total < 0 || total > e->max_moves_total) {
+        set_error("sc_move_index_only: bad move offsets");
+        return SC_E_INVAL;
+    }
+    if (total == 0) return SC_OK;
+    cudaStream_t st = e->stream;
+    SCB_CUDA(cudaSetDevice(e->device));
+    SCB_CUDA(cudaMemcpyAsync(e->d_pos, pos, sizeof(sc_position) * (size_t)n, cudaMemcpyHostToDevice, st));
+    SCB_CUDA(cudaMemcpyAsync(e->d_off, move_off, sizeof(int32_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+    SCB_CUDA(cudaMemcpyAsync(e->d_moves, moves, sizeof(sc_move) * (size_t)total, cudaMemcpyHostToDevice, st));
+    SCB_CHECK(launch_move_index(e->d_pos, e->d_moves, e->d_off, n, e->d_index, st));
+    e->launches += 1;
+    SCB_CUDA(cudaMemcpyAsync(index_out, e->d_index, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, st));
+    SCB_CUDA(cudaStreamSynchronize(st));
+    return SC_OK;
+}
+
+int sc_forward_only(sc_engine *e, int n, const float *planes, const float *meta, float *logp_out, float *value_out)
+{
+    if (!e || n < 0 || n > e->max_batch || (n > 0 && (!planes || !meta || !logp_out || !value_out))) {
+        set_error("sc_forward_only: bad argument");
+        return SC_E_INVAL;
+    }
+    if (n == 0) return SC_OK;
+    cudaStream_t st = e->stream;
+    SCB_CUDA(cudaSetDevice(e->device));
+    float *d_nchw = static_cast<float *>(e->d_scratch);
+    float *d_logp = d_nchw + (size_t)n * SC_N_PLANES * 64;
+    SCB_CUDA(cudaMemcpyAsync(d_nchw, planes, (size_t)n * SC_N_PLANES * 64 * 4, cudaMemcpyHostToDevice, st));
+    // meta rows are padded to 8 floats on the device
+    SCB_CUDA(cudaMemsetAsync(e->d_meta, 0, (size_t)n * 8 * 4, st));
+    SCB_CUDA(cudaMemcpy2DAsync(e->d_meta, 8 * 4, meta, SC_N_META * 4, SC_N_META * 4, (size_t)n, cudaMemcpyHostToDevice, st));
+    if (e->mode == SC_MODE_FP32)
+        SCB_CHECK(launch_nchw_to_nhwc_f32(d_nchw, n, e->f_planes, st));
+    else
+        SCB_CHECK(launch_nchw_to_nhwc_bf16(d_nchw, n, e->h_planes, st));
+    e->launches += 1;
+    if (e->timing) SCB_CUDA(cudaEventRecord(e->ev[0], st));
+    SCB_CHECK(run_network(e, n, st));
+    SCB_CHECK(launch_policy_logp_full(e->logits, n, d_logp, st));
+    e->launches += 1;
+    SCB_CHECK(finish_timing(e, st));
+    SCB_CUDA(cudaMemcpyAsync(logp_out, d_logp, (size_t)n * SC_N_POLICY * 4, cudaMemcpyDeviceToHost, st));
+    SCB_CUDA(cudaMemcpyAsync(value_out, e->d_value, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    SCB_CUDA(cudaStreamSynchronize(st));
+    return SC_OK;
+}
+
+int64_t sc_launch_count(const sc_engine *e) { return e ? e->launches : 0; }
+
+int sc_set_timing(sc_engine *e, int enabled)
+{
+    if (!e) return SC_E_INVAL;
+    e->timing = enabled ? 1 : 0;
+    return SC_OK;
+}
+
+int sc_last_timing(sc_engine *e, float *tower_ms, float *total_ms)
+{
+    if (!e) return SC_E_INVAL;
+    if (tower_ms) *tower_ms = e->last_tower_ms;
+    if (total_ms) *total_ms = e->last_total_ms;
+    return SC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,311 @@
+"""GPU parity tests (run on the B200 box with -m gpu).  Everything goes through the C ABI
+(libscb200.so via ctypes) and is compared with the CPU oracle on the same inputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import games_to_batch
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4     # north_star: policy logits and values in fp32 within 1e-4 absolute
+BF16_TOL = 2e-2     # north_star: bf16 mode at 2e-2 (stated on priors and values)
+
+
+@pytest.fixture(scope="module")
+def nets(tmp_path_factory):
+    import net
+    import scb200
+
+    d = tmp_path_factory.mktemp("weights")
+    out = {}
+    sd19 = net.init_state_dict(19, 0)
+    sd2 = net.perturb_norm_params(net.init_state_dict(2, 7), 1234)
+    for name, sd in (("n19", sd19), ("n2", sd2)):
+        p = str(d / f"{name}.scw")
+        scb200.write_blob(sd, p)
+        out[name] = (sd, p)
+    return out
+
+
+@pytest.fixture(scope="module")
+def positions(co, sample_games):
+    games = []
+    for game in sample_games["games"][:12]:
+        g = co.Game()
+        for u in game["uci"].split():
+            games.append(g.dup())
+            g.push(u)
+    games += co.random_play_positions(400, seed=3)
+    games = [g for g in games if len(g.legal_moves()) > 0]
+    return games
+
+
+@pytest.fixture(scope="module")
+def eng_f32_small(nets):
+    import scb200
+
+    e = scb200.Engine(nets["n2"][1], 0, scb200.SC_MODE_FP32, 2048)
+    yield e
+    e.close()
+
+
+def test_encode_bit_exact(co, positions, eng_f32_small):
+    games = positions
+    rng = np.random.RandomState(0)
+    depths = [g.ply if rng.rand() < 0.7 else rng.randint(0, g.ply + 1) for g in games]
+    pos, moves, off, _ = games_to_batch(games, depths)
+    for lo in range(0, len(games), 2048):
+        hi = min(len(games), lo + 2048)
+        planes, meta = eng_f32_small.encode_only(pos[lo:hi])
+        for i in range(lo, hi):
+            p, m = games[i].encode(depths[i])
+            assert np.array_equal(planes[i - lo], p), i
+            assert np.array_equal(meta[i - lo], m), i
+
+
+def test_move_index_bit_exact(co, positions, eng_f32_small):
+    games = positions[:1500]
+    pos, moves, off, mv_all = games_to_batch(games)
+    idx = eng_f32_small.move_index_only(pos, moves, off)
+    ref = np.concatenate([g.move_indices(mv) for g, mv in zip(games, mv_all)])
+    assert np.array_equal(idx, ref)
+    assert idx.min() >= 0 and idx.max() < 4672
+
+
+def test_move_index_exhaustive(co, eng_f32_small):
+    import scb200
+
+    # every (from, to, promo) for both colours, legal or not: same index or the same rejection (-1)
+    moves, turns = [], []
+    for turn in (0, 1):
+        for f in range(64):
+            for t in range(64):
+                for p in (0, 2, 3, 4, 5):
+                    if f != t:
+                        moves.append((f, t, p, 0))
+                        turns.append(turn)
+    moves = np.array(moves, dtype=scb200.MOVE_DTYPE)
+    turns = np.array(turns)
+    n_pos = 2
+    pos = np.zeros(n_pos, dtype=scb200.POSITION_DTYPE)
+    pos["meta"][0, 0] = 0
+    pos["meta"][1, 0] = 1
+    pos["n_hist"][:] = 1
+    order = np.argsort(turns, kind="stable")
+    moves, turns = moves[order], turns[order]
+    n0 = int((turns == 0).sum())
+    # chunks of <= 200 moves per pseudo-leaf
+    ref = np.array([co.move_index((m["from"], m["to"], m["promo"]), t) for m, t in zip(moves, turns)], dtype=np.int32)
+    got = np.zeros_like(ref)
+    for turn, lo, hi in ((0, 0, n0), (1, n0, len(moves))):
+        k = lo
+        while k < hi:
+            e = min(hi, k + 200 * 64)
+            nleaf = (e - k + 199) // 200
+            p = np.zeros(nleaf, dtype=scb200.POSITION_DTYPE)
+            p["meta"][:, 0] = turn
+            p["n_hist"][:] = 1
+            off = np.minimum(np.arange(nleaf + 1) * 200, e - k).astype(np.int32)
+            got[k:e] = eng_f32_small.move_index_only(p, moves[k:e], off)
+            k = e
+    assert np.array_equal(got, ref)
+
+
+def _oracle_forward(sd, games, depths=None):
+    import net
+
+    planes = np.stack([g.encode(None if depths is None else depths[i])[0] for i, g in enumerate(games)])
+    meta = np.stack([g.encode(None if depths is None else depths[i])[1] for i, g in enumerate(games)])
+    x = net.planes_i8_hwc_to_nchw(planes)
+    lp, v = net.forward(sd, x, torch.from_numpy(meta).float())
+    return x.numpy(), meta.astype(np.float32), lp.numpy(), v.numpy().reshape(-1)
+
+
+def test_forward_fp32_small_net(nets, positions, eng_f32_small):
+    sd = nets["n2"][0]
+    games = positions[::7][:96]
+    x, meta, lp, v = _oracle_forward(sd, games)
+    lp_g, v_g = eng_f32_small.forward_only(x, meta)
+    assert np.abs(lp_g - lp).max() < FP32_TOL
+    assert np.abs(v_g - v).max() < FP32_TOL
+
+
+def test_forward_fp32_golden_vectors(nets, net_golden, eng_f32_small):
+    import net
+
+    x = net.planes_i8_hwc_to_nchw(net_golden["planes_i8"]).numpy()
+    meta = net_golden["meta_i32"].astype(np.float32)
+    lp_g, v_g = eng_f32_small.forward_only(x, meta)
+    d = net.state_dict_digest(nets["n2"][0])
+    if abs(d["sum"] - net_golden["info"]["digest2"]["sum"]) > 1e-6:
+        pytest.skip("seeded net differs on this machine; golden vectors not comparable")
+    assert np.abs(lp_g - net_golden["logp2"]).max() < FP32_TOL
+    assert np.abs(v_g - net_golden["value2"]).max() < FP32_TOL
+
+
+def test_forward_fp32_seed0_19_blocks(nets, positions, net_golden):
+    import net
+    import scb200
+
+    sd = nets["n19"][0]
+    e = scb200.Engine(nets["n19"][1], 0, scb200.SC_MODE_FP32, 64)
+    try:
+        games = positions[::29][:32]
+        x, meta, lp, v = _oracle_forward(sd, games)
+        lp_g, v_g = e.forward_only(x, meta)
+        assert np.abs(lp_g - lp).max() < FP32_TOL
+        assert np.abs(v_g - v).max() < FP32_TOL
+        d = net.state_dict_digest(sd)
+        if abs(d["sum"] - net_golden["info"]["digest19"]["sum"]) < 1e-6:
+            xg = net.planes_i8_hwc_to_nchw(net_golden["planes_i8"]).numpy()
+            lp_g, v_g = e.forward_only(xg, net_golden["meta_i32"].astype(np.float32))
+            assert np.abs(lp_g - net_golden["logp19"]).max() < FP32_TOL
+            assert np.abs(v_g - net_golden["value19"]).max() < FP32_TOL
+    finally:
+        e.close()
+
+
+def _oracle_priors(co, lp, games, mv_all):
+    out = []
+    for i, (g, mv) in enumerate(zip(games, mv_all)):
+        out.append(co.post_process(lp[i], g.move_indices(mv)))
+    return np.concatenate(out)
+
+
+def test_eval_fp32_end_to_end(co, nets, positions, eng_f32_small):
+    sd = nets["n2"][0]
+    games = positions[3::11][:130]      # odd / non-multiple-of-tile batch
+    rng = np.random.RandomState(1)
+    depths = [g.ply if rng.rand() < 0.5 else rng.randint(0, g.ply + 1) for g in games]
+    pos, moves, off, mv_all = games_to_batch(games, depths)
+    pri, val = eng_f32_small.eval(pos, moves, off)
+    _, _, lp, v = _oracle_forward(sd, games, depths)
+    ref = _oracle_priors(co, lp, games, mv_all)
+    assert np.abs(val - v).max() < FP32_TOL
+    assert np.abs(pri - ref).max() < FP32_TOL
+    # priors of a leaf sum to S/(S+1e-5) < 1 (chess.rs:891-901)
+    for i in range(len(games)):
+        s = pri[off[i]:off[i + 1]].sum()
+        assert 0.5 < s < 1.0 + 1e-6
+
+
+def test_eval_batch_composition_independence(co, nets, positions, eng_f32_small):
+    games = positions[5::13][:65]
+    pos, moves, off, _ = games_to_batch(games)
+    pri_a, val_a = eng_f32_small.eval(pos, moves, off)
+    pri_a, val_a = pri_a.copy(), val_a.copy()
+    # same leaves in reverse order, and one leaf alone
+    order = np.arange(len(games))[::-1]
+    pos_b, moves_b, off_b, _ = games_to_batch([games[i] for i in order])
+    pri_b, val_b = eng_f32_small.eval(pos_b, moves_b, off_b)
+    assert np.array_equal(val_b[::-1], val_a)
+    for j, i in enumerate(order):
+        assert np.array_equal(pri_b[off_b[j]:off_b[j + 1]], pri_a[off[i]:off[i + 1]])
+    pos_c, moves_c, off_c, _ = games_to_batch([games[7]])
+    pri_c, val_c = eng_f32_small.eval(pos_c, moves_c, off_c)
+    assert val_c[0] == val_a[7] and np.array_equal(pri_c, pri_a[off[7]:off[8]])
+
+
+def test_eval_edge_cases(co, nets, eng_f32_small):
+    import scb200
+
+    # empty batch
+    pri, val = eng_f32_small.eval(np.zeros(0, dtype=scb200.POSITION_DTYPE), np.zeros(0, dtype=scb200.MOVE_DTYPE),
+                                  np.zeros(1, dtype=np.int32))
+    assert len(pri) == 0 and len(val) == 0
+    # 218 legal moves, a single legal move, promotions incl. under-promotions
+    fens = ["R6R/3Q4/1Q4Q1/4Q3/2Q4Q/Q4Q2/pp1Q4/kBNN1KB1 w - - 0 1",
+            "7k/8/8/8/8/8/5q2/7K w - - 0 1",
+            "r3k2r/Pppp1ppp/1b3nbN/nP6/BBP1P3/q4N2/Pp1P2PP/R2Q1RK1 b kq - 0 1"]
+    games = [co.Game(f) for f in fens]
+    pos, moves, off, mv_all = games_to_batch(games)
+    assert off[1] == 218
+    pri, val = eng_f32_small.eval(pos, moves, off)
+    _, _, lp, v = _oracle_forward(nets["n2"][0], games)
+    ref = _oracle_priors(co, lp, games, mv_all)
+    assert np.abs(pri - ref).max() < FP32_TOL and np.abs(val - v).max() < FP32_TOL
+    with pytest.raises(scb200.SCError):
+        eng_f32_small.eval(np.zeros(4096, dtype=scb200.POSITION_DTYPE), np.zeros(0, dtype=scb200.MOVE_DTYPE),
+                           np.zeros(4097, dtype=np.int32))
+
+
+@pytest.fixture(scope="module")
+def eng_bf16_small(nets):
+    import scb200
+
+    e = scb200.Engine(nets["n2"][1], 0, scb200.SC_MODE_BF16, 2048)
+    yield e
+    e.close()
+
+
+def test_forward_bf16_small_net(co, nets, positions, eng_bf16_small):
+    sd = nets["n2"][0]
+    games = positions[::5][:129]
+    x, meta, lp, v = _oracle_forward(sd, games)
+    lp_g, v_g = eng_bf16_small.forward_only(x, meta)
+    assert np.isfinite(lp_g).all()
+    assert np.abs(np.exp(lp_g) - np.exp(lp)).max() < BF16_TOL
+    assert np.abs(v_g - v).max() < BF16_TOL
+    # and it must be a real computation, not a constant: correlation of log-probs with the oracle
+    c = np.corrcoef(lp_g.reshape(-1), lp.reshape(-1))[0, 1]
+    assert c > 0.999, c
+    assert np.abs(lp_g - lp).max() < 0.1
+
+
+def test_eval_bf16_19_blocks(co, nets, positions):
+    import scb200
+
+    sd = nets["n19"][0]
+    e = scb200.Engine(nets["n19"][1], 0, scb200.SC_MODE_BF16, 512)
+    try:
+        games = positions[2::9][:200]
+        pos, moves, off, mv_all = games_to_batch(games)
+        pri, val = e.eval(pos, moves, off)
+        _, _, lp, v = _oracle_forward(sd, games)
+        ref = _oracle_priors(co, lp, games, mv_all)
+        assert np.abs(pri - ref).max() < BF16_TOL
+        assert np.abs(val - v).max() < BF16_TOL
+        # batch-composition independence holds in bf16 mode too (fixed tiling, fixed K order)
+        pos1, moves1, off1, _ = games_to_batch([games[11]])
+        p1, v1 = e.eval(pos1, moves1, off1)
+        assert v1[0] == val[11] and np.array_equal(p1, pri[off[11]:off[12]])
+    finally:
+        e.close()
+
+
+def test_full_size_properties(co, nets):
+    """configs[1] size (1024 random-play positions, default net): size-independent properties --
+    priors of every leaf are a sub-normalised distribution, values in [-1, 1], bf16 argmax move
+    mostly agrees with fp32, mirrored duplicates evaluate identically."""
+    import scb200
+
+    games = co.random_play_positions(1024, seed=11)
+    pos, moves, off, mv_all = games_to_batch(games)
+    res = {}
+    for mode in (scb200.SC_MODE_FP32, scb200.SC_MODE_BF16):
+        e = scb200.Engine(nets["n19"][1], 0, mode, 1024)
+        try:
+            pri, val = e.eval(pos, moves, off)
+            res[mode] = (pri.copy(), val.copy())
+        finally:
+            e.close()
+    for mode, (pri, val) in res.items():
+        assert np.isfinite(pri).all() and np.isfinite(val).all()
+        assert (pri >= 0).all() and (np.abs(val) <= 1).all()
+        sums = np.add.reduceat(pri, off[:-1])
+        assert (sums < 1 + 1e-5).all() and (sums > 0.9).all()
+    pf, vf = res[scb200.SC_MODE_FP32]
+    pb, vb = res[scb200.SC_MODE_BF16]
+    assert np.abs(pf - pb).max() < BF16_TOL and np.abs(vf - vb).max() < BF16_TOL
+    # duplicated leaf at two batch slots -> identical output
+    dup = [games[5], games[900], games[5]]
+    p3, m3, o3, _ = games_to_batch(dup)
+    e = scb200.Engine(nets["n19"][1], 0, scb200.SC_MODE_BF16, 8)
+    try:
+        pri, val = e.eval(p3, m3, o3)
+        assert val[0] == val[2] and np.array_equal(pri[o3[0]:o3[1]], pri[o3[2]:o3[3]])
+    finally:
+        e.close()

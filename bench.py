@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- leaf evals/s of the B200 leaf-evaluation backend (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm
+    python bench.py --impl reference --gpus N --steps K ...   # CPU reference arm (oracle port)
+
+A "step" is one pass of the hot path over one batch: B leaves (one per concurrent search tree,
+BASELINE.json configs[2]: 2048 concurrent trees on 1xB200) -> plane encode -> 19-block
+policy/value network -> move-index gather + renormalisation -> priors/values.  Positions are
+seeded random play with true 8-ply history; the network is the seed-0 random init of the
+reference's architecture (no checkpoints offline).  N > 1: leaves (games) are sharded across
+ranks, no data-path collective ("scaling": "weak").
+
+value   = leaves/s with inputs already resident in HBM (sc_eval_device), CUDA events per step,
+          L2 flushed between timed steps, max over ranks.
+e2e     = same metric through the C-ABI call a Rust shim makes (sc_eval) with pinned HOST
+          buffers: H2D of positions/moves and D2H of priors/values inside the timed region.
+roofline= the dominant kernel (3x3 256->256 tcgen05 conv): algorithmic FLOPs per launch /
+          its average launch duration measured with CUDA event pairs during the timed steps.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "smart-chess-rust_b200"))
+
+FLOP_PER_LEAF = 2 * 1463895040
+FLOP_PER_LEAF_CONV3 = 2 * 64 * 256 * 2304  # one 3x3 256->256 layer, per leaf
+N_BLOCKS = 19
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"tflops": d.get("bf16_tflops_sustained", 1371.0), "tflops_burst": d.get("bf16_tflops", 1666.7),
+                "hbm_gbs": d.get("hbm_gbs", 6547.8), "src": "measured"}
+    return {"tflops": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "src": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------
+# synthetic workload (uses the oracle's rules engine only to GENERATE positions; nothing of the
+# oracle is on the timed path of our arm)
+# ------------------------------------------------------------------------------------------
+def make_workload(n_leaves: int, seed: int):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import chess_oracle as co
+    from conftest import games_to_batch
+
+    games = co.random_play_positions(n_leaves, seed=seed)
+    pos, moves, off, _ = games_to_batch(games)
+    return games, pos, moves, off
+
+
+def make_blob(tmpdir: str, n_blocks: int = N_BLOCKS):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import net
+    import scb200
+
+    sd = net.init_state_dict(n_blocks, 0)   # == load_model(n_res_blocks=19) seed-0 init (py/module.py:184-212)
+    path = os.path.join(tmpdir, f"seed0_{n_blocks}.scw")
+    scb200.write_blob(sd, path)
+    return sd, path
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU baseline (oracle port of the reference path, timed on the box's host cores)
+# ------------------------------------------------------------------------------------------
+def cpu_reference_throughput(sd, games, budget_s: float, batch: int):
+    """encode (C oracle) + module.py forward restated in torch fp32 on CPU + post_process, on a
+    bounded sample of the workload.  Returns (leaves/s batched, leaves/s at batch 1, n, threads)."""
+    import numpy as np
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import chess_oracle as co
+    import net
+
+    def run(sub):
+        planes = np.stack([g.encode()[0] for g in sub])
+        meta = np.stack([g.encode()[1] for g in sub])
+        lp, v = net.forward(sd, net.planes_i8_hwc_to_nchw(planes), torch.from_numpy(meta).float())
+        lp = lp.numpy()
+        for i, g in enumerate(sub):
+            co.post_process(lp[i], g.move_indices())
+        return v
+
+    run(games[:min(batch, 8)])  # warm-up
+    done, t0 = 0, time.perf_counter()
+    while True:
+        sub = [games[(done + i) % len(games)] for i in range(batch)]
+        run(sub)
+        done += batch
+        el = time.perf_counter() - t0
+        if el >= budget_s:
+            break
+    batched = done / el
+    # the reference's real operating point: one position per forward (torch.rs:119 unsqueeze(0))
+    n1, t1 = 0, time.perf_counter()
+    while time.perf_counter() - t1 < min(4.0, budget_s / 3):
+        run([games[n1 % len(games)]])
+        n1 += 1
+    b1 = n1 / (time.perf_counter() - t1)
+    return batched, b1, done, torch.get_num_threads()
+
+
+def reference_arm(args):
+    """`--impl reference`: the reference's CPU implementation of the path.  The Rust binary cannot
+    be built here (no cargo; python-chess and tch-rs absent), so this is the oracle port: the
+    reference's module.py arithmetic on libtorch CPU + chess.rs/queenmoves.rs semantics in C."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import net
+
+    sd = net.init_state_dict(N_BLOCKS, 0)
+    games, _, _, _ = make_workload(256, seed=1000)
+    batch = 64
+    steps, warm = args.steps, args.warmup
+    import numpy as np
+    import chess_oracle as co
+
+    def step():
+        sub = games[:batch]
+        planes = np.stack([g.encode()[0] for g in sub])
+        meta = np.stack([g.encode()[1] for g in sub])
+        lp, v = net.forward(sd, net.planes_i8_hwc_to_nchw(planes), torch.from_numpy(meta).float())
+        lp = lp.numpy()
+        for i, g in enumerate(sub):
+            co.post_process(lp[i], g.move_indices())
+
+    for _ in range(warm):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    el = time.perf_counter() - t0
+    v = steps * batch / el
+    line = {
+        "impl": "reference", "metric": "leaf_evals_per_s", "value": v, "unit": "leaf evals/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": el / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.leaves),
+        "cpu_baseline": {"value": v, "unit": "leaf evals/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{batch} leaves per step (bounded sample of the {args.leaves}-leaf step), "
+                                   f"fp32 libtorch CPU, batched forward"},
+        "e2e": {"value": v, "unit": "leaf evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(leaves):
+    return {"workload": f"batched leaf eval, {leaves} leaves/step = one leaf per concurrent search tree "
+                        f"(BASELINE configs[2]: 2048 concurrent trees, 19-block LayerNorm+SE net, "
+                        f"seeded random-play positions with 8-ply history)",
+            "leaves_per_step": leaves, "n_res_blocks": N_BLOCKS, "l2": "flushed between timed steps (256 MiB memset)",
+            "parallelism": "leaves sharded by game, one process per GPU, no collective on the data path"}
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--leaves", type=int, default=2048, help="leaves per step per GPU")
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline work (rank 0, N=1)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import numpy as np
+    import torch
+
+    import scb200
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this backend has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    B, K, W = args.leaves, args.steps, args.warmup
+    mode = scb200.SC_MODE_BF16 if args.mode == "bf16" else scb200.SC_MODE_FP32
+    tmp = tempfile.mkdtemp(prefix="scb200_bench_")
+    sd, blob = make_blob(tmp)
+    games, pos, moves, off = make_workload(B, seed=1000 + rank)
+    n_moves = int(off[B])
+    eng = scb200.Engine(blob, local_rank, mode, B)
+
+    stream = torch.cuda.Stream(device=local_rank)
+    sh = stream.cuda_stream
+    # device-resident inputs / outputs
+    d_pos = torch.from_numpy(pos.view(np.uint8)).to(f"cuda:{local_rank}")
+    d_moves = torch.from_numpy(moves.view(np.uint8)).to(f"cuda:{local_rank}")
+    d_off = torch.from_numpy(off).to(f"cuda:{local_rank}")
+    d_pri = torch.zeros(n_moves, dtype=torch.float32, device=f"cuda:{local_rank}")
+    d_val = torch.zeros(B, dtype=torch.float32, device=f"cuda:{local_rank}")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
+    # pinned host buffers for the e2e leg
+    h_pos = torch.from_numpy(pos.view(np.uint8)).pin_memory()
+    h_moves = torch.from_numpy(moves.view(np.uint8)).pin_memory()
+    h_off = torch.from_numpy(off).pin_memory()
+    h_pri = torch.zeros(n_moves, dtype=torch.float32).pin_memory()
+    h_val = torch.zeros(B, dtype=torch.float32).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def dev_step():
+        eng.eval_device(B, d_pos, d_moves, d_off, n_moves, d_pri, d_val, sh)
+
+    # ---- device-resident leg (value) --------------------------------------------------------
+    with torch.cuda.stream(stream):
+        for _ in range(W):
+            dev_step()
+        stream.synchronize()
+        eng.set_timing(2)       # event pairs around every 3x3 conv launch, read back after the sync
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        launches0 = eng.launch_count()
+        barrier()
+        step_ms, conv_ms, conv_n = [], [], 0
+        t_wall0 = time.perf_counter()
+        for _ in range(K):
+            flush.zero_()       # L2 flush, outside the per-step event pair
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev0.record(stream)
+            dev_step()          # with timing on, returns after the step's last event completed
+            ev1.record(stream)
+            ev1.synchronize()
+            step_ms.append(ev0.elapsed_time(ev1))
+            a, n = eng.kernel_timing()
+            conv_ms.append(a)
+            conv_n = n
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+        launches = eng.launch_count() - launches0
+        clocks = sampler.stop()
+        eng.set_timing(0)
+    total_ms = float(sum(step_ms))
+
+    # ---- end-to-end leg through the host-buffer C-ABI call -------------------------------------
+    for _ in range(2):
+        eng.eval(h_pos.numpy().view(scb200.POSITION_DTYPE), h_moves, h_off, h_pri, h_val, sh)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        eng.eval(h_pos.numpy().view(scb200.POSITION_DTYPE), h_moves, h_off, h_pri, h_val, sh)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+
+    # ---- max over ranks ------------------------------------------------------------------------
+    if dist is not None:
+        t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_s = float(t[0]), float(t[1])
+    value = world * B * K / (total_ms * 1e-3)
+    e2e = world * B * K / e2e_s
+
+    # sanity: the timed output is a real evaluation (not part of the timed region)
+    pri_chk = d_pri.cpu().numpy()
+    assert np.isfinite(pri_chk).all() and abs(float(pri_chk[: int(off[1])].sum()) - 1.0) < 0.05
+
+    if rank == 0:
+        peaks = _peaks()
+        conv_avg_ms = float(np.mean(conv_ms)) if conv_ms else None
+        roof = None
+        if conv_avg_ms and conv_avg_ms > 0 and args.mode == "bf16":
+            ach = B * FLOP_PER_LEAF_CONV3 / (conv_avg_ms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": "tc_conv_ln_kernel (3x3 256->256, bias+LN fused)",
+                    "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
+                    "peak_kind": f"bf16_tflops_sustained ({peaks['src']})", "traffic": None,
+                    "launches_timed_per_step": conv_n, "avg_launch_ms": conv_avg_ms,
+                    "flops_per_launch": B * FLOP_PER_LEAF_CONV3,
+                    "whole_step_tflops": value / world * FLOP_PER_LEAF / 1e12}
+        cpu = None
+        if world == 1 and args.cpu_budget > 0:
+            b, b1, n, thr = cpu_reference_throughput(sd, games, args.cpu_budget, 64)
+            cpu = {"value": b, "unit": "leaf evals/s", "cores": thr, "kind": "port",
+                   "sample": f"{n} leaves of the same workload in batches of 64 (fp32 libtorch CPU oracle)",
+                   "batch1_value": b1, "host_cpus": os.cpu_count()}
+        h2d = int(pos.nbytes + moves.nbytes + off.nbytes)
+        d2h = int(n_moves * 4 + B * 4)
+        line = {
+            "metric": "leaf_evals_per_s", "value": value, "unit": "leaf evals/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.mode, "data": "synthetic", "config": workload_config(B),
+            "e2e": {"value": e2e, "unit": "leaf evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "wall_s_timed_region": t_wall,
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

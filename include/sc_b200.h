@@ -107,8 +107,12 @@ int64_t sc_launch_count(const sc_engine *e);
 /* average device time in ms of the conv tower kernels / all kernels of the most recent
  * sc_eval* call, measured with CUDA events on the launching stream (profiling aid) */
 int sc_last_timing(sc_engine *e, float *tower_ms, float *total_ms);
-/* enable/disable per-call event timing (adds two event records + one sync per call) */
+/* per-call event timing: 0 off, 1 = tower/total of a call (two event records + one sync per
+ * call), 2 = additionally one event pair around every 3x3 tower convolution launch */
 int sc_set_timing(sc_engine *e, int enabled);
+/* level 2: average device time (ms) of the 3x3 256->256 tower convolution launches of the
+ * most recent call and how many there were (the roofline kernel of bench.py) */
+int sc_kernel_timing(sc_engine *e, float *conv3x3_avg_ms, int *n_launches);
 
 #ifdef __cplusplus
 }

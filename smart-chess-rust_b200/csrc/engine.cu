@@ -138,6 +138,10 @@ struct sc_engine {
     int timing = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float last_tower_ms = 0.f, last_total_ms = 0.f;
+    std::vector<cudaEvent_t> kev;  // level-2 timing: event pairs around the 3x3 256->256 convs
+    int kev_used = 0;
+    float last_conv_avg_ms = 0.f;
+    int last_conv_n = 0;
 };
 
 namespace scb {
@@ -330,10 +334,24 @@ static int alloc_buffers(sc_engine *e)
     return SC_OK;
 }
 
+// level-2 timing: record the next event of the pair list on `st`
+static int kev_mark(sc_engine *e, cudaStream_t st)
+{
+    if (e->timing < 2) return SC_OK;
+    if (e->kev_used == (int)e->kev.size()) {
+        cudaEvent_t ev;
+        SCB_CUDA(cudaEventCreate(&ev));
+        e->kev.push_back(ev);
+    }
+    SCB_CUDA(cudaEventRecord(e->kev[e->kev_used++], st));
+    return SC_OK;
+}
+
 // the network on n boards; planes already in f_planes / h_planes, meta in d_meta.
 static int run_network(sc_engine *e, int n, cudaStream_t st)
 {
     const int rows = n * 64;
+    e->kev_used = 0;
     if (e->timing) SCB_CUDA(cudaEventRecord(e->ev[1], st));
     if (e->mode == SC_MODE_FP32) {
         auto conv = [&](const ConvW &c, const float *in, int lda, float *out, int relu) -> int {
@@ -344,8 +362,18 @@ static int run_network(sc_engine *e, int n, cudaStream_t st)
         };
         SCB_CHECK(conv(e->stem, e->f_planes, C_IN, e->f_x, 1));
         for (int i = 0; i < e->n_blocks; i++) {
-            SCB_CHECK(conv(e->conv1[i], e->f_x, C_TOWER, e->f_t, 1));
-            SCB_CHECK(conv(e->conv2[i], e->f_t, C_TOWER, e->f_y, 0));
+            SCB_CHECK(kev_mark(e, st));
+            SCB_CHECK(launch_gemm_f32(9, e->f_x, C_TOWER, e->conv1[i].w_f32, e->conv1[i].ldw, e->conv1[i].bias, e->f_t,
+                                      C_TOWER, rows, C_TOWER, C_TOWER, st));
+            SCB_CHECK(kev_mark(e, st));
+            SCB_CHECK(launch_ln_f32(e->f_t, rows, C_TOWER, C_TOWER, e->conv1[i].gamma, e->conv1[i].beta, 1, st));
+            e->launches += 2;
+            SCB_CHECK(kev_mark(e, st));
+            SCB_CHECK(launch_gemm_f32(9, e->f_t, C_TOWER, e->conv2[i].w_f32, e->conv2[i].ldw, e->conv2[i].bias, e->f_y,
+                                      C_TOWER, rows, C_TOWER, C_TOWER, st));
+            SCB_CHECK(kev_mark(e, st));
+            SCB_CHECK(launch_ln_f32(e->f_y, rows, C_TOWER, C_TOWER, e->conv2[i].gamma, e->conv2[i].beta, 0, st));
+            e->launches += 2;
             SCB_CHECK(launch_se_res_f32(e->f_y, e->f_x, e->f_x, n, e->se[i].w1t, e->se[i].b1, e->se[i].w2t,
                                         e->se[i].b2, st));
             e->launches += 1;
@@ -366,8 +394,12 @@ static int run_network(sc_engine *e, int n, cudaStream_t st)
         SCB_CHECK(tc_conv_launch(e->stem.tc, e->h_planes, nb, n, e->h_x, 1, e->num_sms, st));
         e->launches += 1;
         for (int i = 0; i < e->n_blocks; i++) {
+            SCB_CHECK(kev_mark(e, st));
             SCB_CHECK(tc_conv_launch(e->conv1[i].tc, e->h_x, nb, n, e->h_t, 1, e->num_sms, st));
+            SCB_CHECK(kev_mark(e, st));
+            SCB_CHECK(kev_mark(e, st));
             SCB_CHECK(tc_conv_launch(e->conv2[i].tc, e->h_t, nb, n, e->h_y, 0, e->num_sms, st));
+            SCB_CHECK(kev_mark(e, st));
             SCB_CHECK(launch_se_res_bf16(e->h_y, e->h_x, e->h_x, n, e->se[i].w1t, e->se[i].b1, e->se[i].w2t,
                                          e->se[i].b2, st));
             e->launches += 3;
@@ -400,6 +432,16 @@ static int finish_timing(sc_engine *e, cudaStream_t st)
     SCB_CUDA(cudaEventSynchronize(e->ev[3]));
     SCB_CUDA(cudaEventElapsedTime(&e->last_tower_ms, e->ev[1], e->ev[2]));
     SCB_CUDA(cudaEventElapsedTime(&e->last_total_ms, e->ev[0], e->ev[3]));
+    if (e->timing >= 2) {
+        float tot = 0.f;
+        for (int i = 0; i + 1 < e->kev_used; i += 2) {
+            float ms = 0.f;
+            SCB_CUDA(cudaEventElapsedTime(&ms, e->kev[i], e->kev[i + 1]));
+            tot += ms;
+        }
+        e->last_conv_n = e->kev_used / 2;
+        e->last_conv_avg_ms = e->last_conv_n ? tot / e->last_conv_n : 0.f;
+    }
     return SC_OK;
 }
 
@@ -465,6 +507,7 @@ int sc_destroy(sc_engine *e)
     for (void *p : e->allocs) cudaFree(p);
     for (int i = 0; i < 4; i++)
         if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    for (cudaEvent_t ev : e->kev) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return SC_OK;
@@ -612,7 +655,15 @@ int64_t sc_launch_count(const sc_engine *e) { return e ? e->launches : 0; }
 int sc_set_timing(sc_engine *e, int enabled)
 {
     if (!e) return SC_E_INVAL;
-    e->timing = enabled ? 1 : 0;
+    e->timing = enabled < 0 ? 0 : (enabled > 2 ? 2 : enabled);
+    return SC_OK;
+}
+
+int sc_kernel_timing(sc_engine *e, float *conv3x3_avg_ms, int *n_launches)
+{
+    if (!e) return SC_E_INVAL;
+    if (conv3x3_avg_ms) *conv3x3_avg_ms = e->last_conv_avg_ms;
+    if (n_launches) *n_launches = e->last_conv_n;
     return SC_OK;
 }
 

@@ -20,7 +20,7 @@ assert POSITION_DTYPE.itemsize == 544 and MOVE_DTYPE.itemsize == 4
 
 DECLARED_SYMBOLS = [
     "sc_create", "sc_destroy", "sc_last_error", "sc_info", "sc_eval", "sc_eval_device", "sc_encode_only",
-    "sc_move_index_only", "sc_forward_only", "sc_launch_count", "sc_last_timing", "sc_set_timing",
+    "sc_move_index_only", "sc_forward_only", "sc_launch_count", "sc_last_timing", "sc_set_timing", "sc_kernel_timing",
 ]
 
 _LIB = None
@@ -57,6 +57,7 @@ def load_library():
         L.sc_launch_count.argtypes = [C.c_void_p]
         L.sc_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.sc_set_timing.argtypes = [C.c_void_p, C.c_int]
+        L.sc_kernel_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]
         _LIB = L
     return _LIB
 
@@ -170,8 +171,14 @@ class Engine:
     def launch_count(self) -> int:
         return int(load_library().sc_launch_count(self._h))
 
-    def set_timing(self, on: bool):
-        _check(load_library().sc_set_timing(self._h, int(on)), "sc_set_timing")
+    def set_timing(self, level: int):
+        _check(load_library().sc_set_timing(self._h, int(level)), "sc_set_timing")
+
+    def kernel_timing(self):
+        """(average ms of a 3x3 tower conv launch in the last call, number of launches)"""
+        a, n = C.c_float(), C.c_int()
+        _check(load_library().sc_kernel_timing(self._h, C.byref(a), C.byref(n)), "sc_kernel_timing")
+        return a.value, n.value
 
     def last_timing(self):
         a, b = C.c_float(), C.c_float()

@@ -68,17 +68,17 @@ int launch_value_finish(const float *hidden_pre, int n_split, int n, const float
 
 // ---- tower_bf16.cu (tcgen05) --------------------------------------------------------------
 struct TcConv;  // opaque per-layer state (tensor maps)
-int tc_conv_create(TcConv **out, const __nv_bfloat16 *w /*[taps][256][cin_pad]*/, int taps, int cin_pad,
-                   const float *bias, const float *gamma, const float *beta);
+enum { TC_EPI_LN = 0, TC_EPI_LN_SE = 1, TC_EPI_LN73 = 2, TC_EPI_RAW = 3 };
+// w: bf16 [taps][bn][k_per_tap] (K-major B operand); bn = 256 (tower / head 1x1 convs),
+// 80 (policy 256->73, rows 73..79 zero) or 128 (value FC, taps = 1, k_per_tap = 16384)
+int tc_conv_create(TcConv **out, const __nv_bfloat16 *w, int taps, int k_per_tap, int bn, int epi, const float *bias,
+                   const float *gamma, const float *beta);
+// squeeze-excitation weights for TC_EPI_LN_SE: fc1 packed [32][128][8] bf16, fc2 packed [16][256][8] bf16
+void tc_conv_set_se(TcConv *c, const void *w1p, const float *b1, const void *w2p, const float *b2);
 void tc_conv_destroy(TcConv *c);
-// out = LN(conv(in) + bias) * gamma + beta, optional ReLU; in/out bf16 NHWC [n_boards][64][C]
-int tc_conv_launch(TcConv *c, const __nv_bfloat16 *in, int n_boards_alloc, int n_boards, __nv_bfloat16 *out,
-                   int relu, int num_sms, cudaStream_t st);
-int launch_se_res_bf16(const __nv_bfloat16 *y, const __nv_bfloat16 *x, __nv_bfloat16 *out, int n,
-                       const float *w1t, const float *b1, const float *w2t, const float *b2, cudaStream_t st);
-int launch_policy_conv2_bf16(const __nv_bfloat16 *p1, int n, const float *w /*[256][80]*/, const float *bias,
-                             const float *gamma, const float *beta, float *logits, cudaStream_t st);
-int launch_value_fc_bf16(const __nv_bfloat16 *v1 /*[n][16384]*/, int n, const __nv_bfloat16 *w /*[16384][128]*/,
-                         float *hidden_pre /*[n_split][n][128]*/, int n_split, cudaStream_t st);
+// convs: in = bf16 NHWC [rows_alloc boards][64][k_per_tap], n_units = boards.
+// value FC (TC_EPI_RAW): in = bf16 [rows_alloc][16384], n_units = rows, out = fp32 [n_splits][n_units][128].
+int tc_conv_launch(TcConv *c, const __nv_bfloat16 *in, int rows_alloc, int n_units, void *out,
+                   const __nv_bfloat16 *resid, int relu, int n_splits, int num_sms, cudaStream_t st);
 
 }  // namespace scb

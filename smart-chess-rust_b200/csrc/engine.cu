@@ -98,7 +98,8 @@ struct ConvW {
 };
 
 struct SeW {
-    float *w1t = nullptr, *b1 = nullptr, *w2t = nullptr, *b2 = nullptr;
+    float *w1t = nullptr, *b1 = nullptr, *w2t = nullptr, *b2 = nullptr;  // fp32 mode
+    uint16_t *w1p = nullptr, *w2p = nullptr;                            // bf16 mode, packed for the fused epilogue
 };
 
 }  // namespace scb
@@ -114,9 +115,8 @@ struct sc_engine {
     std::vector<ConvW> conv1, conv2;
     std::vector<SeW> se;
     ConvW pol1, pol2, val1;
-    float *pol2_w80 = nullptr;            // bf16 mode: [256][80] fp32 for the CUDA-core policy conv
-    float *vfc_w_f32 = nullptr;           // [16384][128]
-    __nv_bfloat16 *vfc_w_bf16 = nullptr;  // [16384][128]
+    float *vfc_w_f32 = nullptr;           // fp32 mode: [16384][128]
+    TcConv *vfc_tc = nullptr;             // bf16 mode: value FC as a split-K tcgen05 GEMM
     float *v_wmeta = nullptr, *v_b1 = nullptr, *v_w2 = nullptr, *v_b2 = nullptr;
     // io
     sc_position *d_pos = nullptr;
@@ -187,7 +187,7 @@ static int upload_vec(sc_engine *e, const Blob &b, const std::string &name, size
 
 // conv weight [cout][cin][k][k] + bias + LayerNorm gamma/beta -> device layouts
 static int load_conv(sc_engine *e, const Blob &b, const std::string &wname, const std::string &lnname, int taps,
-                     int cin, int cout, ConvW &c)
+                     int cin, int cout, ConvW &c, int epi = TC_EPI_LN)
 {
     const Tensor *w = find(b, wname + ".weight");
     if (!w) return SC_E_IO;
@@ -210,16 +210,18 @@ static int load_conv(sc_engine *e, const Blob &b, const std::string &wname, cons
                 for (int t = 0; t < taps; t++)
                     h[((size_t)t * cin + ci) * c.ldw + co] = w->data[((size_t)co * cin + ci) * taps + t];
         SCB_CHECK(upload(e, &c.w_f32, h));
-    } else if (cout == C_TOWER) {
-        std::vector<uint16_t> h((size_t)taps * cout * c.cin_pad, 0);
+    } else {
+        // B operand, K-major: [tap][bn rows][cin_pad]; bn = 256, or 80 for the 73-wide policy conv
+        const int bn = cout == C_TOWER ? C_TOWER : LD_POLICY;
+        std::vector<uint16_t> h((size_t)taps * bn * c.cin_pad, 0);
         for (int co = 0; co < cout; co++)
             for (int ci = 0; ci < cin; ci++)
                 for (int t = 0; t < taps; t++)
-                    h[((size_t)t * cout + co) * c.cin_pad + ci] = f2bf(w->data[((size_t)co * cin + ci) * taps + t]);
+                    h[((size_t)t * bn + co) * c.cin_pad + ci] = f2bf(w->data[((size_t)co * cin + ci) * taps + t]);
         uint16_t *d = nullptr;
         SCB_CHECK(upload(e, &d, h));
         c.w_bf16 = reinterpret_cast<__nv_bfloat16 *>(d);
-        SCB_CHECK(tc_conv_create(&c.tc, c.w_bf16, taps, c.cin_pad, c.bias, c.gamma, c.beta));
+        SCB_CHECK(tc_conv_create(&c.tc, c.w_bf16, taps, c.cin_pad, bn, epi, c.bias, c.gamma, c.beta));
     }
     return SC_OK;
 }
@@ -234,7 +236,7 @@ static int load_weights(sc_engine *e, const Blob &b)
     for (int i = 0; i < b.n_blocks; i++) {
         std::string p = "res_blocks." + std::to_string(i) + ".";
         SCB_CHECK(load_conv(e, b, p + "conv1", p + "bn1", 9, C_TOWER, C_TOWER, e->conv1[i]));
-        SCB_CHECK(load_conv(e, b, p + "conv2", p + "bn2", 9, C_TOWER, C_TOWER, e->conv2[i]));
+        SCB_CHECK(load_conv(e, b, p + "conv2", p + "bn2", 9, C_TOWER, C_TOWER, e->conv2[i], TC_EPI_LN_SE));
         const Tensor *f1 = find(b, p + "se.fc1.weight"), *f2 = find(b, p + "se.fc2.weight");
         if (!f1 || !f2) return SC_E_IO;
         if (f1->numel != (size_t)C_SE * C_TOWER || f2->numel != (size_t)C_SE * C_TOWER) {
@@ -247,21 +249,31 @@ static int load_weights(sc_engine *e, const Blob &b)
                 w1t[(size_t)c * C_SE + j] = f1->data[(size_t)j * C_TOWER + c];
                 w2t[(size_t)j * C_TOWER + c] = f2->data[(size_t)c * C_SE + j];
             }
-        SCB_CHECK(upload(e, &e->se[i].w1t, w1t));
-        SCB_CHECK(upload(e, &e->se[i].w2t, w2t));
         SCB_CHECK(upload_vec(e, b, p + "se.fc1.bias", C_SE, &e->se[i].b1));
         SCB_CHECK(upload_vec(e, b, p + "se.fc2.bias", C_TOWER, &e->se[i].b2));
+        if (e->mode == SC_MODE_FP32) {
+            SCB_CHECK(upload(e, &e->se[i].w1t, w1t));
+            SCB_CHECK(upload(e, &e->se[i].w2t, w2t));
+        } else {
+            // packed so that epilogue thread j (fc1) / channel c (fc2) reads 8 consecutive inputs
+            // with one coalesced 16-byte load: w1p[q][j][i] = fc1[j][8q+i], w2p[q][c][i] = fc2[c][8q+i]
+            std::vector<uint16_t> w1p((size_t)C_TOWER * C_SE), w2p((size_t)C_SE * C_TOWER);
+            for (int q = 0; q < C_TOWER / 8; q++)
+                for (int j = 0; j < C_SE; j++)
+                    for (int k = 0; k < 8; k++)
+                        w1p[((size_t)q * C_SE + j) * 8 + k] = f2bf(f1->data[(size_t)j * C_TOWER + 8 * q + k]);
+            for (int q = 0; q < C_SE / 8; q++)
+                for (int c = 0; c < C_TOWER; c++)
+                    for (int k = 0; k < 8; k++)
+                        w2p[((size_t)q * C_TOWER + c) * 8 + k] = f2bf(f2->data[(size_t)c * C_SE + 8 * q + k]);
+            SCB_CHECK(upload(e, &e->se[i].w1p, w1p));
+            SCB_CHECK(upload(e, &e->se[i].w2p, w2p));
+            tc_conv_set_se(e->conv2[i].tc, e->se[i].w1p, e->se[i].b1, e->se[i].w2p, e->se[i].b2);
+        }
     }
     SCB_CHECK(load_conv(e, b, "policy_head.model.0", "policy_head.model.1", 1, C_TOWER, C_TOWER, e->pol1));
-    SCB_CHECK(load_conv(e, b, "policy_head.model.2", "policy_head.model.3", 1, C_TOWER, C_POLICY, e->pol2));
+    SCB_CHECK(load_conv(e, b, "policy_head.model.2", "policy_head.model.3", 1, C_TOWER, C_POLICY, e->pol2, TC_EPI_LN73));
     SCB_CHECK(load_conv(e, b, "value_head.conv.0", "value_head.conv.1", 1, C_TOWER, C_TOWER, e->val1));
-    if (e->mode == SC_MODE_BF16) {
-        const Tensor *w = find(b, "policy_head.model.2.weight");
-        std::vector<float> h((size_t)C_TOWER * LD_POLICY, 0.f);
-        for (int co = 0; co < C_POLICY; co++)
-            for (int ci = 0; ci < C_TOWER; ci++) h[(size_t)ci * LD_POLICY + co] = w->data[(size_t)co * C_TOWER + ci];
-        SCB_CHECK(upload(e, &e->pol2_w80, h));
-    }
     // value FC: [128][16391], columns c*64+s (NCHW flatten, py/module.py:93) then 7 meta
     const Tensor *fc = find(b, "value_head.ffn.0.weight");
     if (!fc) return SC_E_IO;
@@ -284,14 +296,16 @@ static int load_weights(sc_engine *e, const Blob &b)
                         h[((size_t)s * C_TOWER + c) * N_VALUE_HIDDEN + j] = fc->data[(size_t)j * KT + c * 64 + s];
             SCB_CHECK(upload(e, &e->vfc_w_f32, h));
         } else {
-            std::vector<uint16_t> h((size_t)KV * N_VALUE_HIDDEN);
+            // B operand of the value FC GEMM, K-major: [128][16384] with k' = s*256 + c
+            std::vector<uint16_t> h((size_t)N_VALUE_HIDDEN * KV);
             for (int j = 0; j < N_VALUE_HIDDEN; j++)
                 for (int c = 0; c < C_TOWER; c++)
                     for (int s = 0; s < 64; s++)
-                        h[((size_t)s * C_TOWER + c) * N_VALUE_HIDDEN + j] = f2bf(fc->data[(size_t)j * KT + c * 64 + s]);
+                        h[(size_t)j * KV + (size_t)s * C_TOWER + c] = f2bf(fc->data[(size_t)j * KT + c * 64 + s]);
             uint16_t *d = nullptr;
             SCB_CHECK(upload(e, &d, h));
-            e->vfc_w_bf16 = reinterpret_cast<__nv_bfloat16 *>(d);
+            SCB_CHECK(tc_conv_create(&e->vfc_tc, reinterpret_cast<__nv_bfloat16 *>(d), 1, KV, N_VALUE_HIDDEN, TC_EPI_RAW,
+                                     nullptr, nullptr, nullptr));
         }
     }
     SCB_CHECK(upload_vec(e, b, "value_head.ffn.0.bias", N_VALUE_HIDDEN, &e->v_b1));
@@ -391,25 +405,23 @@ static int run_network(sc_engine *e, int n, cudaStream_t st)
         e->launches += 3;
     } else {
         const int nb = e->alloc_boards;
-        SCB_CHECK(tc_conv_launch(e->stem.tc, e->h_planes, nb, n, e->h_x, 1, e->num_sms, st));
+        SCB_CHECK(tc_conv_launch(e->stem.tc, e->h_planes, nb, n, e->h_x, nullptr, 1, 1, e->num_sms, st));
         e->launches += 1;
         for (int i = 0; i < e->n_blocks; i++) {
             SCB_CHECK(kev_mark(e, st));
-            SCB_CHECK(tc_conv_launch(e->conv1[i].tc, e->h_x, nb, n, e->h_t, 1, e->num_sms, st));
+            SCB_CHECK(tc_conv_launch(e->conv1[i].tc, e->h_x, nb, n, e->h_t, nullptr, 1, 1, e->num_sms, st));
             SCB_CHECK(kev_mark(e, st));
             SCB_CHECK(kev_mark(e, st));
-            SCB_CHECK(tc_conv_launch(e->conv2[i].tc, e->h_t, nb, n, e->h_y, 0, e->num_sms, st));
+            // conv2 + LN + squeeze-excitation + residual + ReLU, in place on the block input x
+            SCB_CHECK(tc_conv_launch(e->conv2[i].tc, e->h_t, nb, n, e->h_x, e->h_x, 0, 1, e->num_sms, st));
             SCB_CHECK(kev_mark(e, st));
-            SCB_CHECK(launch_se_res_bf16(e->h_y, e->h_x, e->h_x, n, e->se[i].w1t, e->se[i].b1, e->se[i].w2t,
-                                         e->se[i].b2, st));
-            e->launches += 3;
+            e->launches += 2;
         }
         if (e->timing) SCB_CUDA(cudaEventRecord(e->ev[2], st));
-        SCB_CHECK(tc_conv_launch(e->pol1.tc, e->h_x, nb, n, e->h_t, 0, e->num_sms, st));
-        SCB_CHECK(launch_policy_conv2_bf16(e->h_t, n, e->pol2_w80, e->pol2.bias, e->pol2.gamma, e->pol2.beta,
-                                           e->logits, st));
-        SCB_CHECK(tc_conv_launch(e->val1.tc, e->h_x, nb, n, e->h_y, 1, e->num_sms, st));
-        SCB_CHECK(launch_value_fc_bf16(e->h_y, n, e->vfc_w_bf16, e->vpre, e->vsplit, st));
+        SCB_CHECK(tc_conv_launch(e->pol1.tc, e->h_x, nb, n, e->h_t, nullptr, 0, 1, e->num_sms, st));
+        SCB_CHECK(tc_conv_launch(e->pol2.tc, e->h_t, nb, n, e->logits, nullptr, 0, 1, e->num_sms, st));
+        SCB_CHECK(tc_conv_launch(e->val1.tc, e->h_x, nb, n, e->h_y, nullptr, 1, 1, e->num_sms, st));
+        SCB_CHECK(tc_conv_launch(e->vfc_tc, e->h_y, nb, n, e->vpre, nullptr, 0, e->vsplit, e->num_sms, st));
         e->launches += 4;
     }
     SCB_CHECK(launch_value_finish(e->vpre, e->vsplit, n, e->d_meta, e->v_wmeta, e->v_b1, e->v_w2, e->v_b2,
@@ -502,6 +514,7 @@ int sc_destroy(sc_engine *e)
     cudaDeviceSynchronize();
     auto kill = [](ConvW &c) { if (c.tc) tc_conv_destroy(c.tc); c.tc = nullptr; };
     kill(e->stem); kill(e->pol1); kill(e->pol2); kill(e->val1);
+    if (e->vfc_tc) tc_conv_destroy(e->vfc_tc);
     for (auto &c : e->conv1) kill(c);
     for (auto &c : e->conv2) kill(c);
     for (void *p : e->allocs) cudaFree(p);

@@ -16,6 +16,9 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
 // warps 2..5 = epilogue (each owns the TMEM lane quadrant warp_id % 4; one thread = one
 // (board, square) row, so LayerNorm over channels is a per-thread reduction).
+// The same kernel, with other template arguments, runs the 1x1 head convolutions, the
+// 256->73 policy convolution (N = 80) with its LayerNorm(73), and the 16384->128 value FC
+// as a split-K GEMM whose rows are boards.
 #include <cuda.h>
 
 #include <vector>
@@ -142,32 +145,145 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N)
 }
 
 // ---- the kernel ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS, 1)
-tc_conv_ln_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-                  __nv_bfloat16 *__restrict__ out, const float *__restrict__ bias, const float *__restrict__ gamma,
-                  const float *__restrict__ beta, int n_tiles, int taps, int kchunks, int relu)
+// Epilogue variants of the one warp-specialised GEMM kernel:
+//   EPI_LN     bias + LayerNorm(256) (+ReLU)                     -> bf16 [rows][256]
+//   EPI_LN_SE  bias + LayerNorm(256) + squeeze-excitation + residual + ReLU, all inside the
+//              epilogue (a tile is two whole boards, so the SE average pool is a reduction
+//              over the tile's own rows)                          -> bf16 [rows][256]
+//   EPI_LN73   bias + LayerNorm(73) of the 80-wide policy map     -> fp32 [rows][80]
+//   EPI_RAW    split-K partial sums of the value FC               -> fp32 [split][M][128]
+enum { EPI_LN = 0, EPI_LN_SE = 1, EPI_LN73 = 2, EPI_RAW = 3 };
+
+struct TcArgs {
+    void *out;
+    const __nv_bfloat16 *resid;          // EPI_LN_SE: block input x (may alias out)
+    const float *bias, *gamma, *beta;
+    const uint4 *se_w1p, *se_w2p;        // EPI_LN_SE: fc1 as [32][128][8] bf16, fc2 as [16][256][8] bf16
+    const float *se_b1, *se_b2;
+    int n_tiles;                         // M tiles of 128 rows
+    int taps, kchunks;                   // k-blocks per work item = taps * kchunks
+    int relu;
+    int n_splits;                        // EPI_RAW: work items = n_tiles * n_splits
+    int m_rows;                          // EPI_RAW: valid rows
+};
+
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32])
 {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    float *s_bias = reinterpret_cast<float *>(smem + TC_STAGES * TC_STAGE_BYTES);
-    float *s_gamma = s_bias + TC_BN;
-    float *s_beta = s_gamma + TC_BN;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(s_beta + TC_BN);
-    // bars: [0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// Sum over the 32 lanes of a warp of 32 per-lane values, result for index `lane` lands in
+// lane `lane` (recursive halving: 16+8+4+2+1 = 31 shuffles instead of 32 x 5).
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane)
+{
+    const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2, b1 = lane & 1;
+    float w16[16], w8[8], w4[4], w2[2];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        float send = b16 ? v[i] : v[i + 16];
+        float keep = b16 ? v[i + 16] : v[i];
+        w16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        float send = b8 ? w16[i] : w16[i + 8];
+        float keep = b8 ? w16[i + 8] : w16[i];
+        w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float send = b4 ? w8[i] : w8[i + 4];
+        float keep = b4 ? w8[i + 4] : w8[i];
+        w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        float send = b2 ? w4[i] : w4[i + 2];
+        float keep = b2 ? w4[i + 2] : w4[i];
+        w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    float send = b1 ? w2[0] : w2[1];
+    float keep = b1 ? w2[1] : w2[0];
+    return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+
+__device__ __forceinline__ void bf16x8_to_float(const uint4 &u, float (&f)[8])
+{
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        f[2 * i] = __uint_as_float(w[i] << 16);
+        f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+
+template <int BN> struct TcCfg {
+    static constexpr int B_BYTES = BN * TC_BK * 2;
+    static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+    static constexpr int SMEM_EPI = 3 * 256 * 4 /*bias,gamma,beta*/ + (4 * 256 + 2 * 256 + 2 * 128 + 2 * 256) * 4 /*SE*/;
+    static constexpr int SMEM_BYTES = TC_STAGES * STAGE_BYTES + SMEM_EPI + 256;
+};
+
+template <int BN, int EPI, bool A4D>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+               const TcArgs args)
+{
+    using Cfg = TcCfg<BN>;
+    constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
+    // Dynamic shared memory is the only shared allocation of this kernel, so it starts at offset 0 of
+    // the CTA window and is 1024-byte aligned (required by the 128B swizzle); checked below.  Deriving
+    // the pointers directly from the __shared__ symbol keeps every access an LDS/STS (a pointer
+    // laundered through an integer cast degrades to generic LD/ST).
+    extern __shared__ __align__(1024) uint8_t smem[];
+    float *s_bias = reinterpret_cast<float *>(smem + TC_STAGES * STAGE_BYTES);
+    float *s_gamma = s_bias + 256;
+    float *s_beta = s_gamma + 256;
+    float *s_pool = s_beta + 256;   // [4 quads][256]
+    float *s_mean = s_pool + 1024;  // [2 boards][256]
+    float *s_hid = s_mean + 512;    // [2][128]
+    float *s_gate = s_hid + 256;    // [2][256]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_gate + 512);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TC_STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = smem_u32(smem);
+    if (smem_base & 1023u) __trap();
     const uint32_t bar_base = smem_u32(bars);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * TC_STAGES + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * TC_STAGES + 2 + s); };
 
-    for (int i = threadIdx.x; i < TC_BN; i += TC_THREADS) {
-        s_bias[i] = bias[i];
-        s_gamma[i] = gamma[i];
-        s_beta[i] = beta[i];
+    if (EPI != EPI_RAW) {
+        constexpr int NV = EPI == EPI_LN73 ? C_POLICY : BN;
+        for (int i = threadIdx.x; i < 256; i += TC_THREADS) {
+            s_bias[i] = i < NV ? args.bias[i] : 0.f;
+            s_gamma[i] = i < NV ? args.gamma[i] : 0.f;
+            s_beta[i] = i < NV ? args.beta[i] : 0.f;
+        }
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; s++) {
@@ -190,7 +306,8 @@ tc_conv_ln_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int nkb = taps * kchunks;
+    const int nkb = args.taps * args.kchunks;
+    const int n_work = EPI == EPI_RAW ? args.n_tiles * args.n_splits : args.n_tiles;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -198,18 +315,25 @@ tc_conv_ln_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int board0 = tile * 2;
-                for (int tap = 0; tap < taps; tap++) {
-                    const int dy = taps == 9 ? tap / 3 - 1 : 0;
-                    const int dx = taps == 9 ? tap % 3 - 1 : 0;
-                    for (int kc = 0; kc < kchunks; kc++) {
+            for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
+                const int tile = EPI == EPI_RAW ? work / args.n_splits : work;
+                const int split = EPI == EPI_RAW ? work % args.n_splits : 0;
+                for (int tap = 0; tap < args.taps; tap++) {
+                    const int dy = args.taps == 9 ? tap / 3 - 1 : 0;
+                    const int dx = args.taps == 9 ? tap % 3 - 1 : 0;
+                    for (int kc = 0; kc < args.kchunks; kc++) {
                         mbar_wait(empty_bar(stage), phase ^ 1u);
-                        const uint32_t a_dst = smem_base + stage * TC_STAGE_BYTES;
+                        const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
                         const uint32_t b_dst = a_dst + TC_A_BYTES;
-                        mbar_expect_tx(full_bar(stage), TC_STAGE_BYTES);
-                        tma_load_4d(a_dst, &map_a, full_bar(stage), kc * TC_BK, dx, dy, board0);
-                        tma_load_2d(b_dst, &map_w, full_bar(stage), kc * TC_BK, tap * TC_BN);
+                        mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+                        if (A4D) {
+                            tma_load_4d(a_dst, &map_a, full_bar(stage), kc * TC_BK, dx, dy, tile * 2);
+                            tma_load_2d(b_dst, &map_w, full_bar(stage), kc * TC_BK, tap * BN);
+                        } else {
+                            const int k0 = (split * args.kchunks + kc) * TC_BK;
+                            tma_load_2d(a_dst, &map_a, full_bar(stage), k0, tile * TC_BM);
+                            tma_load_2d(b_dst, &map_w, full_bar(stage), k0, 0);
+                        }
                         if (++stage == TC_STAGES) {
                             stage = 0;
                             phase ^= 1u;
@@ -220,20 +344,20 @@ tc_conv_ln_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, TC_BN);
+            constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, BN);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+            for (int work = blockIdx.x; work < n_work; work += gridDim.x, it++) {
                 const int as = it & 1;
                 const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
                 mbar_wait(tempty_bar(as), aphase ^ 1u);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(as * TC_BN);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
                 for (int kb = 0; kb < nkb; kb++) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_base + stage * TC_STAGE_BYTES;
+                    const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
                     const uint64_t da = umma_desc_sw128(a_addr);
                     const uint64_t db = umma_desc_sw128(a_addr + TC_A_BYTES);
 #pragma unroll
@@ -254,52 +378,230 @@ tc_conv_ln_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     } else {
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
+        const int te = (warp - 2) * 32 + lane;  // 0..127, FC work split
         int it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+        for (int work = blockIdx.x; work < n_work; work += gridDim.x, it++) {
+            const int tile = EPI == EPI_RAW ? work / args.n_splits : work;
+            const int split = EPI == EPI_RAW ? work % args.n_splits : 0;
             const int as = it & 1;
             const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
             mbar_wait(tfull_bar(as), aphase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * TC_BN);
-            uint32_t r[32];
-            float sum = 0.f;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256);
+
+            if constexpr (EPI == EPI_RAW) {
+                uint32_t r[32];
+                const int grow = tile * TC_BM + row;
+                float4 *o = reinterpret_cast<float4 *>(static_cast<float *>(args.out) +
+                                                       ((size_t)split * args.m_rows + grow) * BN);
 #pragma unroll 1
-            for (int ch = 0; ch < TC_BN / 32; ch++) {
-                tmem_ld32(taddr + ch * 32, r);
+                for (int ch = 0; ch < BN / 32; ch++) {
+                    tmem_ld32(taddr + ch * 32, r);
+                    if (grow < args.m_rows) {
 #pragma unroll
-                for (int j = 0; j < 32; j++) sum += __uint_as_float(r[j]) + s_bias[ch * 32 + j];
-            }
-            const float mean = sum * (1.f / TC_BN);
-            float sq = 0.f;
-#pragma unroll 1
-            for (int ch = 0; ch < TC_BN / 32; ch++) {
-                tmem_ld32(taddr + ch * 32, r);
-#pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    float d = __uint_as_float(r[j]) + s_bias[ch * 32 + j] - mean;
-                    sq = fmaf(d, d, sq);
-                }
-            }
-            const float rstd = rsqrtf(sq * (1.f / TC_BN) + LN_EPS);
-            uint4 *orow = reinterpret_cast<uint4 *>(out + ((size_t)tile * TC_BM + row) * TC_BN);
-#pragma unroll 1
-            for (int ch = 0; ch < TC_BN / 32; ch++) {
-                tmem_ld32(taddr + ch * 32, r);
-                uint32_t pk[16];
-#pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    const int c = ch * 32 + 2 * j;
-                    float y0 = (__uint_as_float(r[2 * j]) + s_bias[c] - mean) * rstd * s_gamma[c] + s_beta[c];
-                    float y1 = (__uint_as_float(r[2 * j + 1]) + s_bias[c + 1] - mean) * rstd * s_gamma[c + 1] + s_beta[c + 1];
-                    if (relu) {
-                        y0 = fmaxf(y0, 0.f);
-                        y1 = fmaxf(y1, 0.f);
+                        for (int q = 0; q < 8; q++)
+                            o[ch * 8 + q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                                        __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
                     }
-                    __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);
-                    pk[j] = *reinterpret_cast<uint32_t *>(&h);
                 }
+            } else if constexpr (EPI == EPI_LN73) {
+                uint32_t r[16];
+                float sum = 0.f;
+#pragma unroll 1
+                for (int ch = 0; ch < BN / 16; ch++) {
+                    tmem_ld16(taddr + ch * 16, r);
 #pragma unroll
-                for (int q = 0; q < 4; q++) orow[ch * 4 + q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                    for (int j = 0; j < 16; j++)
+                        if (ch * 16 + j < C_POLICY) sum += __uint_as_float(r[j]) + s_bias[ch * 16 + j];
+                }
+                const float mean = sum * (1.f / C_POLICY);
+                float sq = 0.f;
+#pragma unroll 1
+                for (int ch = 0; ch < BN / 16; ch++) {
+                    tmem_ld16(taddr + ch * 16, r);
+#pragma unroll
+                    for (int j = 0; j < 16; j++)
+                        if (ch * 16 + j < C_POLICY) {
+                            float d = __uint_as_float(r[j]) + s_bias[ch * 16 + j] - mean;
+                            sq = fmaf(d, d, sq);
+                        }
+                }
+                const float rstd = rsqrtf(sq * (1.f / C_POLICY) + LN_EPS);
+                float4 *o = reinterpret_cast<float4 *>(static_cast<float *>(args.out) + ((size_t)tile * TC_BM + row) * BN);
+#pragma unroll 1
+                for (int ch = 0; ch < BN / 16; ch++) {
+                    tmem_ld16(taddr + ch * 16, r);
+                    float y[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const int c = ch * 16 + j;
+                        y[j] = c < C_POLICY ? (__uint_as_float(r[j]) + s_bias[c] - mean) * rstd * s_gamma[c] + s_beta[c] : 0.f;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; q++) o[ch * 4 + q] = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+                }
+            } else {
+                uint32_t r[32];
+                float mean, rstd;
+                {
+                    // one pass: sum and sum of squares of (acc + bias); fp32 is ample for LN inputs
+                    // (|mean| is of the order of the standard deviation for conv outputs)
+                    uint32_t r2[32];
+                    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 1
+                    for (int ch = 0; ch < BN / 32; ch += 2) {
+                        tmem_ld32_nowait(taddr + ch * 32, r);
+                        tmem_ld32_nowait(taddr + ch * 32 + 32, r2);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const float a = __uint_as_float(r[j]) + s_bias[ch * 32 + j];
+                            const float b = __uint_as_float(r2[j]) + s_bias[ch * 32 + 32 + j];
+                            s0 += a;
+                            q0 = fmaf(a, a, q0);
+                            s1 += b;
+                            q1 = fmaf(b, b, q1);
+                        }
+                    }
+                    mean = (s0 + s1) * (1.f / BN);
+                    const float var = fmaxf((q0 + q1) * (1.f / BN) - mean * mean, 0.f);
+                    rstd = rsqrtf(var + LN_EPS);
+                }
+                const size_t grow = (size_t)tile * TC_BM + row;
+
+                // first 64 bytes of the residual row are requested now, consumed after the SE phase
+                const uint4 *xrow = reinterpret_cast<const uint4 *>(args.resid + grow * BN);
+                uint4 xn[4];
+                if constexpr (EPI == EPI_LN_SE) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) xn[q] = xrow[q];
+                }
+                if constexpr (EPI == EPI_LN_SE) {
+                    // ---- squeeze: per-board channel means of y = LN(conv) (fp32) -------------------
+#pragma unroll 1
+                    for (int ch = 0; ch < BN / 32; ch++) {
+                        tmem_ld32(taddr + ch * 32, r);
+                        float y[32];
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const int c = ch * 32 + j;
+                            y[j] = (__uint_as_float(r[j]) + s_bias[c] - mean) * rstd * s_gamma[c] + s_beta[c];
+                        }
+                        s_pool[quad * 256 + ch * 32 + lane] = warp_transpose_reduce(y, lane);
+                    }
+                    epi_bar_sync();
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int idx = te + 128 * i;  // [board][channel]
+                        const int b = idx >> 8, c = idx & 255;
+                        s_mean[idx] = (s_pool[(2 * b) * 256 + c] + s_pool[(2 * b + 1) * 256 + c]) * (1.f / 64.f);
+                    }
+                    epi_bar_sync();
+                    // ---- excitation FC1 (256 -> 128) + ReLU: thread te owns hidden unit te for both boards
+                    {
+                        float h0 = args.se_b1[te], h1 = h0;
+#pragma unroll 1
+                        for (int q0 = 0; q0 < 32; q0 += 8) {
+                            uint4 wv[8];
+#pragma unroll
+                            for (int u = 0; u < 8; u++) wv[u] = __ldg(args.se_w1p + (q0 + u) * 128 + te);
+#pragma unroll
+                            for (int u = 0; u < 8; u++) {
+                                const int q = q0 + u;
+                                float wf[8];
+                                bf16x8_to_float(wv[u], wf);
+                                const float4 m0a = *reinterpret_cast<const float4 *>(s_mean + q * 8);
+                                const float4 m0b = *reinterpret_cast<const float4 *>(s_mean + q * 8 + 4);
+                                const float4 m1a = *reinterpret_cast<const float4 *>(s_mean + 256 + q * 8);
+                                const float4 m1b = *reinterpret_cast<const float4 *>(s_mean + 256 + q * 8 + 4);
+                                h0 = fmaf(wf[0], m0a.x, h0); h0 = fmaf(wf[1], m0a.y, h0); h0 = fmaf(wf[2], m0a.z, h0); h0 = fmaf(wf[3], m0a.w, h0);
+                                h0 = fmaf(wf[4], m0b.x, h0); h0 = fmaf(wf[5], m0b.y, h0); h0 = fmaf(wf[6], m0b.z, h0); h0 = fmaf(wf[7], m0b.w, h0);
+                                h1 = fmaf(wf[0], m1a.x, h1); h1 = fmaf(wf[1], m1a.y, h1); h1 = fmaf(wf[2], m1a.z, h1); h1 = fmaf(wf[3], m1a.w, h1);
+                                h1 = fmaf(wf[4], m1b.x, h1); h1 = fmaf(wf[5], m1b.y, h1); h1 = fmaf(wf[6], m1b.z, h1); h1 = fmaf(wf[7], m1b.w, h1);
+                            }
+                        }
+                        s_hid[te] = fmaxf(h0, 0.f);
+                        s_hid[128 + te] = fmaxf(h1, 0.f);
+                    }
+                    epi_bar_sync();
+                    // ---- FC2 (128 -> 256) + sigmoid: thread te owns channels te and te + 128
+                    {
+                        float g[2][2];
+                        g[0][0] = g[1][0] = args.se_b2[te];
+                        g[0][1] = g[1][1] = args.se_b2[te + 128];
+#pragma unroll 1
+                        for (int q0 = 0; q0 < 16; q0 += 4) {
+                            uint4 wv[4][2];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                wv[u][0] = __ldg(args.se_w2p + (q0 + u) * 256 + te);
+                                wv[u][1] = __ldg(args.se_w2p + (q0 + u) * 256 + te + 128);
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const int q = q0 + u;
+                                const float4 h0a = *reinterpret_cast<const float4 *>(s_hid + q * 8);
+                                const float4 h0b = *reinterpret_cast<const float4 *>(s_hid + q * 8 + 4);
+                                const float4 h1a = *reinterpret_cast<const float4 *>(s_hid + 128 + q * 8);
+                                const float4 h1b = *reinterpret_cast<const float4 *>(s_hid + 128 + q * 8 + 4);
+                                const float hv0[8] = {h0a.x, h0a.y, h0a.z, h0a.w, h0b.x, h0b.y, h0b.z, h0b.w};
+                                const float hv1[8] = {h1a.x, h1a.y, h1a.z, h1a.w, h1b.x, h1b.y, h1b.z, h1b.w};
+#pragma unroll
+                                for (int half = 0; half < 2; half++) {
+                                    float wf[8];
+                                    bf16x8_to_float(wv[u][half], wf);
+#pragma unroll
+                                    for (int i = 0; i < 8; i++) {
+                                        g[0][half] = fmaf(wf[i], hv0[i], g[0][half]);
+                                        g[1][half] = fmaf(wf[i], hv1[i], g[1][half]);
+                                    }
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int b = 0; b < 2; b++)
+#pragma unroll
+                            for (int half = 0; half < 2; half++)
+                                s_gate[b * 256 + te + 128 * half] = 1.f / (1.f + __expf(-g[b][half]));
+                    }
+                    epi_bar_sync();
+                }
+
+                // ---- final pass: y (recomputed from TMEM), [gate * y + x], ReLU, bf16 store ------
+                const float *gate = s_gate + (quad >> 1) * 256;
+                uint4 *orow = reinterpret_cast<uint4 *>(static_cast<__nv_bfloat16 *>(args.out) + grow * BN);
+#pragma unroll 1
+                for (int ch = 0; ch < BN / 32; ch++) {
+                    tmem_ld32(taddr + ch * 32, r);
+                    uint4 xv[4];
+                    if constexpr (EPI == EPI_LN_SE) {
+#pragma unroll
+                        for (int q = 0; q < 4; q++) xv[q] = xn[q];
+                        if (ch + 1 < BN / 32) {
+#pragma unroll
+                            for (int q = 0; q < 4; q++) xn[q] = xrow[(ch + 1) * 4 + q];
+                        }
+                    }
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const int c = ch * 32 + 2 * j;
+                        float y0 = (__uint_as_float(r[2 * j]) + s_bias[c] - mean) * rstd * s_gamma[c] + s_beta[c];
+                        float y1 = (__uint_as_float(r[2 * j + 1]) + s_bias[c + 1] - mean) * rstd * s_gamma[c + 1] + s_beta[c + 1];
+                        if constexpr (EPI == EPI_LN_SE) {
+                            const uint32_t xw = reinterpret_cast<const uint32_t *>(xv)[j];
+                            y0 = fmaxf(fmaf(gate[c], y0, __uint_as_float(xw << 16)), 0.f);
+                            y1 = fmaxf(fmaf(gate[c + 1], y1, __uint_as_float(xw & 0xffff0000u)), 0.f);
+                        } else if (args.relu) {
+                            y0 = fmaxf(y0, 0.f);
+                            y1 = fmaxf(y1, 0.f);
+                        }
+                        __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);
+                        pk[j] = *reinterpret_cast<uint32_t *>(&h);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; q++) orow[ch * 4 + q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                }
             }
             tc_fence_before();
             mbar_arrive(tempty_bar(as));
@@ -334,268 +636,171 @@ static EncodeTiledFn get_encode()
 
 struct ActMap {
     const void *ptr;
-    int boards, c;
+    int rows, c;
     CUtensorMap map;
 };
 
 struct TcConv {
     CUtensorMap map_w;
-    int taps, cin_pad;
+    int taps, k_per_tap, bn, epi;
     const float *bias, *gamma, *beta;
+    const uint4 *se_w1p = nullptr, *se_w2p = nullptr;
+    const float *se_b1 = nullptr, *se_b2 = nullptr;
     std::vector<ActMap> act_maps;
 };
 
-static int make_act_map(const void *ptr, int boards, int c, CUtensorMap *m)
+static int encode_map(CUtensorMap *m, const void *ptr, int rank, const cuuint64_t *dims, const cuuint64_t *strides,
+                      const cuuint32_t *box, const char *what)
 {
     EncodeTiledFn enc = get_encode();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled not available from the driver");
         return SC_E_CUDA;
     }
-    cuuint64_t dims[4] = {(cuuint64_t)c, 8, 8, (cuuint64_t)boards};
-    cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)c * 16, (cuuint64_t)c * 128};
-    cuuint32_t box[4] = {TC_BK, 8, 8, 2};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(ptr), dims, strides, box,
+                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled(activations) failed: " + std::to_string((int)r));
+        set_error(std::string("cuTensorMapEncodeTiled(") + what + ") failed: " + std::to_string((int)r));
         return SC_E_CUDA;
     }
     return SC_OK;
 }
 
-int tc_conv_create(TcConv **out, const __nv_bfloat16 *w, int taps, int cin_pad, const float *bias,
+// activations as a 4-D tensor {C, file, rank, board}, box = 64 channels of two whole boards
+static int make_act_map_4d(const void *ptr, int boards, int c, CUtensorMap *m)
+{
+    cuuint64_t dims[4] = {(cuuint64_t)c, 8, 8, (cuuint64_t)boards};
+    cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)c * 16, (cuuint64_t)c * 128};
+    cuuint32_t box[4] = {TC_BK, 8, 8, 2};
+    return encode_map(m, ptr, 4, dims, strides, box, "activations 4d");
+}
+
+// plain row-major [rows][k] matrix, box = 64 k x 128 rows
+static int make_act_map_2d(const void *ptr, int rows, int k, CUtensorMap *m)
+{
+    cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)k * 2};
+    cuuint32_t box[2] = {TC_BK, TC_BM};
+    return encode_map(m, ptr, 2, dims, strides, box, "activations 2d");
+}
+
+template <int BN, int EPI, bool A4D> static int set_smem_attr()
+{
+    SCB_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, EPI, A4D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  TcCfg<BN>::SMEM_BYTES));
+    return SC_OK;
+}
+
+int tc_conv_create(TcConv **out, const __nv_bfloat16 *w, int taps, int k_per_tap, int bn, int epi, const float *bias,
                    const float *gamma, const float *beta)
 {
-    EncodeTiledFn enc = get_encode();
-    if (!enc) {
-        set_error("cuTensorMapEncodeTiled not available from the driver");
-        return SC_E_CUDA;
-    }
     TcConv *c = new TcConv();
     c->taps = taps;
-    c->cin_pad = cin_pad;
+    c->k_per_tap = k_per_tap;
+    c->bn = bn;
+    c->epi = epi;
     c->bias = bias;
     c->gamma = gamma;
     c->beta = beta;
-    cuuint64_t dims[2] = {(cuuint64_t)cin_pad, (cuuint64_t)taps * TC_BN};
-    cuuint64_t strides[1] = {(cuuint64_t)cin_pad * 2};
-    cuuint32_t box[2] = {TC_BK, TC_BN};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&c->map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16 *>(w), dims, strides,
-                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
+    // weights [taps * bn rows][k_per_tap], K-major
+    cuuint64_t dims[2] = {(cuuint64_t)k_per_tap, (cuuint64_t)taps * bn};
+    cuuint64_t strides[1] = {(cuuint64_t)k_per_tap * 2};
+    cuuint32_t box[2] = {TC_BK, (cuuint32_t)bn};
+    int rc = encode_map(&c->map_w, w, 2, dims, strides, box, "weights");
+    if (rc != SC_OK) {
         delete c;
-        set_error("cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r));
-        return SC_E_CUDA;
+        return rc;
     }
     static bool attr_set = false;
     if (!attr_set) {
-        SCB_CUDA(cudaFuncSetAttribute(tc_conv_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        SCB_CHECK((set_smem_attr<256, EPI_LN, true>()));
+        SCB_CHECK((set_smem_attr<256, EPI_LN_SE, true>()));
+        SCB_CHECK((set_smem_attr<LD_POLICY, EPI_LN73, true>()));
+        SCB_CHECK((set_smem_attr<N_VALUE_HIDDEN, EPI_RAW, false>()));
         attr_set = true;
     }
     *out = c;
     return SC_OK;
 }
 
+void tc_conv_set_se(TcConv *c, const void *w1p, const float *b1, const void *w2p, const float *b2)
+{
+    c->se_w1p = static_cast<const uint4 *>(w1p);
+    c->se_w2p = static_cast<const uint4 *>(w2p);
+    c->se_b1 = b1;
+    c->se_b2 = b2;
+}
+
 void tc_conv_destroy(TcConv *c) { delete c; }
 
-int tc_conv_launch(TcConv *c, const __nv_bfloat16 *in, int n_boards_alloc, int n_boards, __nv_bfloat16 *out,
-                   int relu, int num_sms, cudaStream_t st)
+int tc_conv_launch(TcConv *c, const __nv_bfloat16 *in, int rows_alloc, int n_units, void *out,
+                   const __nv_bfloat16 *resid, int relu, int n_splits, int num_sms, cudaStream_t st)
 {
-    if (n_boards <= 0) return SC_OK;
+    if (n_units <= 0) return SC_OK;
+    const bool a4d = c->epi != EPI_RAW;
     const CUtensorMap *ma = nullptr;
     for (auto &m : c->act_maps)
-        if (m.ptr == in && m.boards == n_boards_alloc && m.c == c->cin_pad) ma = &m.map;
+        if (m.ptr == in && m.rows == rows_alloc && m.c == c->k_per_tap) ma = &m.map;
     if (!ma) {
         ActMap am;
         am.ptr = in;
-        am.boards = n_boards_alloc;
-        am.c = c->cin_pad;
-        SCB_CHECK(make_act_map(in, n_boards_alloc, c->cin_pad, &am.map));
+        am.rows = rows_alloc;
+        am.c = c->k_per_tap;
+        if (a4d)
+            SCB_CHECK(make_act_map_4d(in, rows_alloc, c->k_per_tap, &am.map));
+        else
+            SCB_CHECK(make_act_map_2d(in, rows_alloc, c->k_per_tap, &am.map));
         c->act_maps.push_back(am);
         ma = &c->act_maps.back().map;
     }
-    const int n_tiles = (n_boards + 1) / 2;
-    const int grid = n_tiles < num_sms ? n_tiles : num_sms;
-    tc_conv_ln_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(*ma, c->map_w, out, c->bias, c->gamma, c->beta, n_tiles,
-                                                               c->taps, c->cin_pad / TC_BK, relu);
-    SCB_CUDA(cudaGetLastError());
-    return SC_OK;
-}
-
-// ---- squeeze-excitation + residual + ReLU on bf16 activations (py/module.py:43-45) ---------
-__global__ void __launch_bounds__(256) se_res_bf16_kernel(const __nv_bfloat16 *__restrict__ y,
-                                                          const __nv_bfloat16 *__restrict__ x,
-                                                          __nv_bfloat16 *__restrict__ out,
-                                                          const float *__restrict__ w1t, const float *__restrict__ b1,
-                                                          const float *__restrict__ w2t, const float *__restrict__ b2)
-{
-    __shared__ float s_mean[C_TOWER];
-    __shared__ float s_hid[C_SE];
-    const int b = blockIdx.x, c = threadIdx.x;
-    const __nv_bfloat16 *yb = y + (size_t)b * 64 * C_TOWER;
-    float yv[64];
-    float sum = 0.f;
-#pragma unroll
-    for (int s = 0; s < 64; s++) {
-        yv[s] = __bfloat162float(yb[s * C_TOWER + c]);
-        sum += yv[s];
+    TcArgs a;
+    a.out = out;
+    a.resid = resid;
+    a.bias = c->bias;
+    a.gamma = c->gamma;
+    a.beta = c->beta;
+    a.se_w1p = c->se_w1p;
+    a.se_w2p = c->se_w2p;
+    a.se_b1 = c->se_b1;
+    a.se_b2 = c->se_b2;
+    a.relu = relu;
+    a.n_splits = n_splits > 0 ? n_splits : 1;
+    a.m_rows = n_units;
+    if (a4d) {
+        a.n_tiles = (n_units + 1) / 2;  // units = boards, two per tile
+        a.taps = c->taps;
+        a.kchunks = c->k_per_tap / TC_BK;
+    } else {
+        a.n_tiles = (n_units + TC_BM - 1) / TC_BM;  // units = rows
+        a.taps = 1;
+        a.kchunks = c->k_per_tap / TC_BK / a.n_splits;
     }
-    s_mean[c] = sum * (1.f / 64.f);
-    __syncthreads();
-    if (c < C_SE) {
-        float a = b1[c];
-        for (int k = 0; k < C_TOWER; k++) a = fmaf(w1t[k * C_SE + c], s_mean[k], a);
-        s_hid[c] = fmaxf(a, 0.f);
-    }
-    __syncthreads();
-    float g = b2[c];
-    for (int k = 0; k < C_SE; k++) g = fmaf(w2t[k * C_TOWER + c], s_hid[k], g);
-    g = 1.f / (1.f + __expf(-g));
-    const __nv_bfloat16 *xb = x + (size_t)b * 64 * C_TOWER;
-    __nv_bfloat16 *ob = out + (size_t)b * 64 * C_TOWER;
-#pragma unroll
-    for (int s = 0; s < 64; s++)
-        ob[s * C_TOWER + c] = __float2bfloat16(fmaxf(fmaf(g, yv[s], __bfloat162float(xb[s * C_TOWER + c])), 0.f));
-}
-
-int launch_se_res_bf16(const __nv_bfloat16 *y, const __nv_bfloat16 *x, __nv_bfloat16 *out, int n, const float *w1t,
-                       const float *b1, const float *w2t, const float *b2, cudaStream_t st)
-{
-    if (n <= 0) return SC_OK;
-    se_res_bf16_kernel<<<n, 256, 0, st>>>(y, x, out, w1t, b1, w2t, b2);
-    SCB_CUDA(cudaGetLastError());
-    return SC_OK;
-}
-
-// ---- policy conv 256 -> 73 + LayerNorm(73) (py/module.py:73-74), CUDA-core version ----------
-// one block per board: 64 rows x 80 (73 valid) outputs, thread = (row, 20-column quarter)
-__global__ void __launch_bounds__(256) policy_conv2_bf16_kernel(const __nv_bfloat16 *__restrict__ p1,
-                                                                const float *__restrict__ w /*[256][80]*/,
-                                                                const float *__restrict__ bias,
-                                                                const float *__restrict__ gamma,
-                                                                const float *__restrict__ beta,
-                                                                float *__restrict__ logits)
-{
-    __shared__ __align__(16) float s_w[32][LD_POLICY];
-    __shared__ __nv_bfloat16 s_a[64][C_TOWER + 2];
-    const int b = blockIdx.x, tid = threadIdx.x;
-    const int r = tid >> 2, q = tid & 3;
-    const __nv_bfloat16 *src = p1 + (size_t)b * 64 * C_TOWER;
-    for (int i = tid; i < 64 * C_TOWER; i += 256) s_a[i >> 8][i & 255] = src[i];
-    float acc[20];
-#pragma unroll
-    for (int j = 0; j < 20; j++) acc[j] = 0.f;
-    for (int k0 = 0; k0 < C_TOWER; k0 += 32) {
-        __syncthreads();
-        for (int i = tid; i < 32 * LD_POLICY; i += 256) s_w[i / LD_POLICY][i % LD_POLICY] = w[(size_t)k0 * LD_POLICY + i];
-        __syncthreads();
-#pragma unroll 4
-        for (int k = 0; k < 32; k++) {
-            const float a = __bfloat162float(s_a[r][k0 + k]);
-            const float4 *wp = reinterpret_cast<const float4 *>(&s_w[k][q * 20]);
-#pragma unroll
-            for (int j = 0; j < 5; j++) {
-                float4 v = wp[j];
-                acc[4 * j + 0] = fmaf(a, v.x, acc[4 * j + 0]);
-                acc[4 * j + 1] = fmaf(a, v.y, acc[4 * j + 1]);
-                acc[4 * j + 2] = fmaf(a, v.z, acc[4 * j + 2]);
-                acc[4 * j + 3] = fmaf(a, v.w, acc[4 * j + 3]);
-            }
+    const int n_work = a4d ? a.n_tiles : a.n_tiles * a.n_splits;
+    const int grid = n_work < num_sms ? n_work : num_sms;
+    switch (c->epi) {
+    case EPI_LN:
+        tc_gemm_kernel<256, EPI_LN, true><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, st>>>(*ma, c->map_w, a);
+        break;
+    case EPI_LN_SE:
+        if (!c->se_w1p || !resid) {
+            set_error("tc_conv_launch: SE epilogue without SE weights / residual");
+            return SC_E_INVAL;
         }
+        tc_gemm_kernel<256, EPI_LN_SE, true><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, st>>>(*ma, c->map_w, a);
+        break;
+    case EPI_LN73:
+        tc_gemm_kernel<LD_POLICY, EPI_LN73, true><<<grid, TC_THREADS, TcCfg<LD_POLICY>::SMEM_BYTES, st>>>(*ma, c->map_w, a);
+        break;
+    case EPI_RAW:
+        tc_gemm_kernel<N_VALUE_HIDDEN, EPI_RAW, false><<<grid, TC_THREADS, TcCfg<N_VALUE_HIDDEN>::SMEM_BYTES, st>>>(
+            *ma, c->map_w, a);
+        break;
+    default:
+        set_error("tc_conv_launch: bad epilogue");
+        return SC_E_INVAL;
     }
-    float sum = 0.f;
-#pragma unroll
-    for (int j = 0; j < 20; j++) {
-        int c = q * 20 + j;
-        acc[j] = c < C_POLICY ? acc[j] + bias[c] : 0.f;
-        sum += acc[j];
-    }
-    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-    const float mean = sum * (1.f / C_POLICY);
-    float sq = 0.f;
-#pragma unroll
-    for (int j = 0; j < 20; j++) {
-        int c = q * 20 + j;
-        float d = c < C_POLICY ? acc[j] - mean : 0.f;
-        sq = fmaf(d, d, sq);
-    }
-    sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-    sq += __shfl_xor_sync(0xffffffffu, sq, 2);
-    const float rstd = rsqrtf(sq * (1.f / C_POLICY) + LN_EPS);
-    float *o = logits + ((size_t)b * 64 + r) * LD_POLICY + q * 20;
-#pragma unroll
-    for (int j = 0; j < 20; j++) {
-        int c = q * 20 + j;
-        o[j] = c < C_POLICY ? (acc[j] - mean) * rstd * gamma[c] + beta[c] : 0.f;
-    }
-}
-
-int launch_policy_conv2_bf16(const __nv_bfloat16 *p1, int n, const float *w, const float *bias, const float *gamma,
-                             const float *beta, float *logits, cudaStream_t st)
-{
-    if (n <= 0) return SC_OK;
-    policy_conv2_bf16_kernel<<<n, 256, 0, st>>>(p1, w, bias, gamma, beta, logits);
-    SCB_CUDA(cudaGetLastError());
-    return SC_OK;
-}
-
-// ---- value FC 16384 -> 128 (py/module.py:95), CUDA-core split-K version ----------------------
-// grid (ceil(n/32), n_split); block 256 = 32 boards x 8 column groups of 16
-__global__ void __launch_bounds__(256) value_fc_bf16_kernel(const __nv_bfloat16 *__restrict__ v1, int n,
-                                                            const __nv_bfloat16 *__restrict__ w,
-                                                            float *__restrict__ pre, int k_per_split)
-{
-    __shared__ __nv_bfloat16 s_a[32][64 + 2];
-    __shared__ __align__(16) __nv_bfloat16 s_w[64][N_VALUE_HIDDEN];
-    const int tid = threadIdx.x;
-    const int b0 = blockIdx.x * 32, sp = blockIdx.y;
-    const int rb = tid >> 3, cg = tid & 7;
-    float acc[16];
-#pragma unroll
-    for (int j = 0; j < 16; j++) acc[j] = 0.f;
-    const int kbeg = sp * k_per_split;
-    for (int k0 = kbeg; k0 < kbeg + k_per_split; k0 += 64) {
-        __syncthreads();
-        for (int i = tid; i < 32 * 64; i += 256) {
-            int rr = i >> 6, kk = i & 63;
-            s_a[rr][kk] = (b0 + rr < n) ? v1[(size_t)(b0 + rr) * (64 * C_TOWER) + k0 + kk] : __float2bfloat16(0.f);
-        }
-        const uint4 *wsrc = reinterpret_cast<const uint4 *>(w + (size_t)k0 * N_VALUE_HIDDEN);
-        uint4 *wdst = reinterpret_cast<uint4 *>(&s_w[0][0]);
-        for (int i = tid; i < 64 * N_VALUE_HIDDEN / 8; i += 256) wdst[i] = wsrc[i];
-        __syncthreads();
-#pragma unroll 4
-        for (int k = 0; k < 64; k++) {
-            const float a = __bfloat162float(s_a[rb][k]);
-            const __nv_bfloat162 *wp = reinterpret_cast<const __nv_bfloat162 *>(&s_w[k][cg * 16]);
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                float2 f = __bfloat1622float2(wp[j]);
-                acc[2 * j] = fmaf(a, f.x, acc[2 * j]);
-                acc[2 * j + 1] = fmaf(a, f.y, acc[2 * j + 1]);
-            }
-        }
-    }
-    if (b0 + rb < n) {
-        float *o = pre + ((size_t)sp * n + b0 + rb) * N_VALUE_HIDDEN + cg * 16;
-#pragma unroll
-        for (int j = 0; j < 16; j++) o[j] = acc[j];
-    }
-}
-
-int launch_value_fc_bf16(const __nv_bfloat16 *v1, int n, const __nv_bfloat16 *w, float *hidden_pre, int n_split,
-                         cudaStream_t st)
-{
-    if (n <= 0) return SC_OK;
-    const int K = 64 * C_TOWER;
-    dim3 grid((n + 31) / 32, n_split);
-    value_fc_bf16_kernel<<<grid, 256, 0, st>>>(v1, n, w, hidden_pre, K / n_split);
     SCB_CUDA(cudaGetLastError());
     return SC_OK;
 }

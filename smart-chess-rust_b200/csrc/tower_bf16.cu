@@ -21,6 +21,8 @@
 // as a split-K GEMM whose rows are boards.
 #include <cuda.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -34,7 +36,7 @@ constexpr int TC_STAGES = 4;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KB
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;  // 32 KB
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
 constexpr int TC_SMEM_PARAMS = 3 * TC_BN * 4;
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_SMEM_PARAMS + 256 + 1024;
 
@@ -165,6 +167,7 @@ struct TcArgs {
     int relu;
     int n_splits;                        // EPI_RAW: work items = n_tiles * n_splits
     int m_rows;                          // EPI_RAW: valid rows
+    long long *prof;                     // optional [grid][16] phase cycle counters (SCB200_PHASE_PROFILE=1)
 };
 
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32])
@@ -192,7 +195,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // Sum over the 32 lanes of a warp of 32 per-lane values, result for index `lane` lands in
 // lane `lane` (recursive halving: 16+8+4+2+1 = 31 shuffles instead of 32 x 5).
@@ -239,10 +242,45 @@ __device__ __forceinline__ void bf16x8_to_float(const uint4 &u, float (&f)[8])
     }
 }
 
+// Per-warp staging tile of 32 rows x 64 bytes used to turn the epilogue's thread-per-row data
+// into coalesced global accesses (a row-per-lane access has a 512-byte lane stride and costs 32
+// half-used sectors per instruction; through the tile every instruction covers 8 rows x 64 B =
+// 16 full sectors).  16-byte chunk q of row r lives at chunk q ^ ((r >> 1) & 3): conflict-free
+// for both the row-per-lane and the 4-lanes-per-row access.
+__device__ __forceinline__ uint32_t stg_off(int row, int q) { return (uint32_t)(row * 64 + ((q ^ ((row >> 1) & 3)) << 4)); }
+
+// lane's own 64 bytes (row = lane) -> staging -> global rows gbase + r * row_stride (+ 16-byte chunk)
+__device__ __forceinline__ void staged_store_64B(uint8_t *stg, int lane, const uint4 (&v)[4], uint8_t *gbase,
+                                                 size_t row_stride, int rows_valid)
+{
+#pragma unroll
+    for (int q = 0; q < 4; q++) *reinterpret_cast<uint4 *>(stg + stg_off(lane, q)) = v[q];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int rr = (lane >> 2) + 8 * k;
+        const uint4 t = *reinterpret_cast<const uint4 *>(stg + stg_off(rr, lane & 3));
+        if (rr < rows_valid) *reinterpret_cast<uint4 *>(gbase + (size_t)rr * row_stride + (lane & 3) * 16) = t;
+    }
+    __syncwarp();
+}
+
+// 4 registers loaded with the coalesced mapping (row (lane>>2)+8k, chunk lane&3) -> lane's own row
+__device__ __forceinline__ void staged_gather_64B(uint8_t *stg, int lane, const uint4 *coal /*[4]*/, uint4 (&mine)[4])
+{
+#pragma unroll
+    for (int k = 0; k < 4; k++) *reinterpret_cast<uint4 *>(stg + stg_off((lane >> 2) + 8 * k, lane & 3)) = coal[k];
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 4; q++) mine[q] = *reinterpret_cast<const uint4 *>(stg + stg_off(lane, q));
+    __syncwarp();
+}
+
 template <int BN> struct TcCfg {
     static constexpr int B_BYTES = BN * TC_BK * 2;
     static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
-    static constexpr int SMEM_EPI = 3 * 256 * 4 /*bias,gamma,beta*/ + (4 * 256 + 2 * 256 + 2 * 128 + 2 * 256) * 4 /*SE*/;
+    static constexpr int SMEM_EPI = 3 * 256 * 4 /*bias,gamma,beta*/ + (4 * 256 + 2 * 256 + 2 * 128 + 2 * 256) * 4 /*SE*/ +
+                                    (2 * 256 + 4 * 128) * 4 /*LN partials, FC1 partials*/ + 8 * 2048 /*store staging*/;
     static constexpr int SMEM_BYTES = TC_STAGES * STAGE_BYTES + SMEM_EPI + 256;
 };
 
@@ -265,7 +303,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     float *s_mean = s_pool + 1024;  // [2 boards][256]
     float *s_hid = s_mean + 512;    // [2][128]
     float *s_gate = s_hid + 256;    // [2][256]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(s_gate + 512);
+    float *s_stat = s_gate + 512;   // [2 column halves][128 rows][sum, sumsq]
+    float *s_hidp = s_stat + 512;   // [2 channel halves][2 boards][128]
+    uint8_t *s_stage = reinterpret_cast<uint8_t *>(s_hidp + 512);  // [8 epilogue warps][32 rows][64 B]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_stage + 8 * 2048);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TC_STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -292,7 +333,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         for (int s = 0; s < 2; s++) {
             mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), 128);
+            mbar_init(tempty_bar(s), (EPI == EPI_LN || EPI == EPI_LN_SE) ? 256 : 128);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -315,6 +356,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
             int stage = 0;
             uint32_t phase = 0;
+            long long pc_wait_empty = 0;
             for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
                 const int tile = EPI == EPI_RAW ? work / args.n_splits : work;
                 const int split = EPI == EPI_RAW ? work % args.n_splits : 0;
@@ -322,7 +364,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const int dy = args.taps == 9 ? tap / 3 - 1 : 0;
                     const int dx = args.taps == 9 ? tap % 3 - 1 : 0;
                     for (int kc = 0; kc < args.kchunks; kc++) {
+                        const long long t0 = args.prof ? clock64() : 0;
                         mbar_wait(empty_bar(stage), phase ^ 1u);
+                        if (args.prof) pc_wait_empty += clock64() - t0;
                         const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
                         const uint32_t b_dst = a_dst + TC_A_BYTES;
                         mbar_expect_tx(full_bar(stage), STAGE_BYTES);
@@ -341,6 +385,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                 }
             }
+            if (args.prof) args.prof[blockIdx.x * 16 + 0] = pc_wait_empty;
         }
     } else if (warp == 1) {
         if (lane == 0) {
@@ -348,14 +393,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
+            long long pc_wait_tempty = 0, pc_wait_full = 0, pc_total = args.prof ? clock64() : 0;
             for (int work = blockIdx.x; work < n_work; work += gridDim.x, it++) {
                 const int as = it & 1;
                 const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+                long long t0 = args.prof ? clock64() : 0;
                 mbar_wait(tempty_bar(as), aphase ^ 1u);
+                if (args.prof) pc_wait_tempty += clock64() - t0;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
                 for (int kb = 0; kb < nkb; kb++) {
+                    t0 = args.prof ? clock64() : 0;
                     mbar_wait(full_bar(stage), phase);
+                    if (args.prof) pc_wait_full += clock64() - t0;
                     tc_fence_after();
                     const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
                     const uint64_t da = umma_desc_sw128(a_addr);
@@ -374,34 +424,50 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
                 tc_commit(tfull_bar(as));
             }
+            if (args.prof) {
+                args.prof[blockIdx.x * 16 + 1] = pc_wait_tempty;
+                args.prof[blockIdx.x * 16 + 2] = pc_wait_full;
+                args.prof[blockIdx.x * 16 + 3] = clock64() - pc_total;
+                args.prof[blockIdx.x * 16 + 4] = it;
+            }
         }
-    } else {
+    } else if ((EPI == EPI_LN || EPI == EPI_LN_SE) || warp < 6) {
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
-        const int te = (warp - 2) * 32 + lane;  // 0..127, FC work split
+        const int te = (warp - 2) * 32 + lane;  // 0..255 (0..127 for the 4-warp epilogues)
+        const int chalf = (warp - 2) >> 2;      // which 128-column half of the tile this warp owns
         int it = 0;
+        long long pe_wait = 0, pe_work = 0, pe_stats = 0, pe_pool = 0, pe_fc = 0, pe_final = 0;
+        const bool prof = args.prof != nullptr && te == 0;
         for (int work = blockIdx.x; work < n_work; work += gridDim.x, it++) {
             const int tile = EPI == EPI_RAW ? work / args.n_splits : work;
             const int split = EPI == EPI_RAW ? work % args.n_splits : 0;
             const int as = it & 1;
             const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+            long long tp0 = prof ? clock64() : 0;
             mbar_wait(tfull_bar(as), aphase);
+            long long tp1 = prof ? clock64() : 0;
+            pe_wait += tp1 - tp0;
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256);
 
             if constexpr (EPI == EPI_RAW) {
                 uint32_t r[32];
-                const int grow = tile * TC_BM + row;
-                float4 *o = reinterpret_cast<float4 *>(static_cast<float *>(args.out) +
-                                                       ((size_t)split * args.m_rows + grow) * BN);
+                uint8_t *stg = s_stage + (warp - 2) * 2048;
+                const int wrow0 = tile * TC_BM + quad * 32;  // first global row of this warp
+                uint8_t *gbase = reinterpret_cast<uint8_t *>(static_cast<float *>(args.out) +
+                                                             ((size_t)split * args.m_rows + wrow0) * BN);
+                const int rows_valid = args.m_rows - wrow0;
 #pragma unroll 1
                 for (int ch = 0; ch < BN / 32; ch++) {
                     tmem_ld32(taddr + ch * 32, r);
-                    if (grow < args.m_rows) {
 #pragma unroll
-                        for (int q = 0; q < 8; q++)
-                            o[ch * 8 + q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                                                        __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                    for (int hf = 0; hf < 2; hf++) {
+                        uint4 v[4];
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+                            v[q] = make_uint4(r[hf * 16 + 4 * q], r[hf * 16 + 4 * q + 1], r[hf * 16 + 4 * q + 2], r[hf * 16 + 4 * q + 3]);
+                        staged_store_64B(stg, lane, v, gbase + (ch * 32 + hf * 16) * 4, (size_t)BN * 4, rows_valid);
                     }
                 }
             } else if constexpr (EPI == EPI_LN73) {
@@ -427,84 +493,106 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         }
                 }
                 const float rstd = rsqrtf(sq * (1.f / C_POLICY) + LN_EPS);
-                float4 *o = reinterpret_cast<float4 *>(static_cast<float *>(args.out) + ((size_t)tile * TC_BM + row) * BN);
+                uint8_t *stg = s_stage + (warp - 2) * 2048;
+                uint8_t *gbase = reinterpret_cast<uint8_t *>(static_cast<float *>(args.out) +
+                                                             ((size_t)tile * TC_BM + quad * 32) * BN);
 #pragma unroll 1
                 for (int ch = 0; ch < BN / 16; ch++) {
                     tmem_ld16(taddr + ch * 16, r);
-                    float y[16];
+                    uint4 v[4];
 #pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        const int c = ch * 16 + j;
-                        y[j] = c < C_POLICY ? (__uint_as_float(r[j]) + s_bias[c] - mean) * rstd * s_gamma[c] + s_beta[c] : 0.f;
+                    for (int q = 0; q < 4; q++) {
+                        float y[4];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const int c = ch * 16 + 4 * q + i;
+                            y[i] = c < C_POLICY ? (__uint_as_float(r[4 * q + i]) + s_bias[c] - mean) * rstd * s_gamma[c] + s_beta[c] : 0.f;
+                        }
+                        v[q] = make_uint4(__float_as_uint(y[0]), __float_as_uint(y[1]), __float_as_uint(y[2]), __float_as_uint(y[3]));
                     }
-#pragma unroll
-                    for (int q = 0; q < 4; q++) o[ch * 4 + q] = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+                    staged_store_64B(stg, lane, v, gbase + ch * 64, (size_t)BN * 4, 32);
                 }
             } else {
+                // ---- bias + LayerNorm(256) [+ SE + residual] ; this warp owns columns [c0, c0 + 128) of
+                //      its 32 rows, the sibling warp (same TMEM quadrant) owns the other half --------------
+                const int c0 = chalf * 128;
+                const uint32_t tcol = taddr + (uint32_t)c0;
                 uint32_t r[32];
                 float mean, rstd;
                 {
                     // one pass: sum and sum of squares of (acc + bias); fp32 is ample for LN inputs
-                    // (|mean| is of the order of the standard deviation for conv outputs)
                     uint32_t r2[32];
                     float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll 1
-                    for (int ch = 0; ch < BN / 32; ch += 2) {
-                        tmem_ld32_nowait(taddr + ch * 32, r);
-                        tmem_ld32_nowait(taddr + ch * 32 + 32, r2);
+                    for (int ch = 0; ch < 4; ch += 2) {
+                        tmem_ld32_nowait(tcol + ch * 32, r);
+                        tmem_ld32_nowait(tcol + ch * 32 + 32, r2);
                         tmem_wait_ld();
 #pragma unroll
                         for (int j = 0; j < 32; j++) {
-                            const float a = __uint_as_float(r[j]) + s_bias[ch * 32 + j];
-                            const float b = __uint_as_float(r2[j]) + s_bias[ch * 32 + 32 + j];
+                            const float a = __uint_as_float(r[j]) + s_bias[c0 + ch * 32 + j];
+                            const float b = __uint_as_float(r2[j]) + s_bias[c0 + ch * 32 + 32 + j];
                             s0 += a;
                             q0 = fmaf(a, a, q0);
                             s1 += b;
                             q1 = fmaf(b, b, q1);
                         }
                     }
-                    mean = (s0 + s1) * (1.f / BN);
-                    const float var = fmaxf((q0 + q1) * (1.f / BN) - mean * mean, 0.f);
+                    s0 += s1;
+                    q0 += q1;
+                    *reinterpret_cast<float2 *>(s_stat + (chalf * 128 + row) * 2) = make_float2(s0, q0);
+                    epi_bar_sync();
+                    const float2 o = *reinterpret_cast<const float2 *>(s_stat + ((chalf ^ 1) * 128 + row) * 2);
+                    mean = (s0 + o.x) * (1.f / BN);
+                    const float var = fmaxf((q0 + o.y) * (1.f / BN) - mean * mean, 0.f);
                     rstd = rsqrtf(var + LN_EPS);
                 }
-                const size_t grow = (size_t)tile * TC_BM + row;
-
-                // first 64 bytes of the residual row are requested now, consumed after the SE phase
-                const uint4 *xrow = reinterpret_cast<const uint4 *>(args.resid + grow * BN);
-                uint4 xn[4];
+                long long tp2 = prof ? clock64() : 0;
+                pe_stats += tp2 - tp1;
+                // residual: this warp's 32 rows x 128 columns, requested now with a coalesced mapping
+                // (xa[ch*4+k] = row (lane>>2)+8k, 16-byte chunk lane&3 of 32-column chunk ch), consumed
+                // after the SE phase through the staging tile
+                uint8_t *stg = s_stage + (warp - 2) * 2048;
+                const size_t wrow0 = (size_t)tile * TC_BM + quad * 32;  // first global row of this warp
+                uint4 xa[16];
                 if constexpr (EPI == EPI_LN_SE) {
+                    const uint4 *xw = reinterpret_cast<const uint4 *>(args.resid + (wrow0 + (lane >> 2)) * BN + c0) + (lane & 3);
 #pragma unroll
-                    for (int q = 0; q < 4; q++) xn[q] = xrow[q];
+                    for (int ch = 0; ch < 4; ch++)
+#pragma unroll
+                        for (int k = 0; k < 4; k++) xa[ch * 4 + k] = xw[(size_t)k * 8 * (BN / 8) + ch * 4];
                 }
                 if constexpr (EPI == EPI_LN_SE) {
                     // ---- squeeze: per-board channel means of y = LN(conv) (fp32) -------------------
 #pragma unroll 1
-                    for (int ch = 0; ch < BN / 32; ch++) {
-                        tmem_ld32(taddr + ch * 32, r);
+                    for (int ch = 0; ch < 4; ch++) {
+                        tmem_ld32(tcol + ch * 32, r);
                         float y[32];
 #pragma unroll
                         for (int j = 0; j < 32; j++) {
-                            const int c = ch * 32 + j;
+                            const int c = c0 + ch * 32 + j;
                             y[j] = (__uint_as_float(r[j]) + s_bias[c] - mean) * rstd * s_gamma[c] + s_beta[c];
                         }
-                        s_pool[quad * 256 + ch * 32 + lane] = warp_transpose_reduce(y, lane);
+                        s_pool[quad * 256 + c0 + ch * 32 + lane] = warp_transpose_reduce(y, lane);
                     }
                     epi_bar_sync();
+                    if (prof) { const long long t = clock64(); pe_pool += t - tp2; tp2 = t; }
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const int idx = te + 128 * i;  // [board][channel]
+                    for (int i = 0; i < 2; i++) {
+                        const int idx = te + 256 * i;  // [board][channel]
                         const int b = idx >> 8, c = idx & 255;
                         s_mean[idx] = (s_pool[(2 * b) * 256 + c] + s_pool[(2 * b + 1) * 256 + c]) * (1.f / 64.f);
                     }
                     epi_bar_sync();
-                    // ---- excitation FC1 (256 -> 128) + ReLU: thread te owns hidden unit te for both boards
+                    // ---- excitation FC1 (256 -> 128): thread = (hidden unit j, channel half hc), both boards
                     {
-                        float h0 = args.se_b1[te], h1 = h0;
+                        const int j = te & 127, hc = te >> 7;
+                        float h0 = 0.f, h1 = 0.f;
 #pragma unroll 1
-                        for (int q0 = 0; q0 < 32; q0 += 8) {
+                        for (int q0 = hc * 16; q0 < hc * 16 + 16; q0 += 8) {
                             uint4 wv[8];
 #pragma unroll
-                            for (int u = 0; u < 8; u++) wv[u] = __ldg(args.se_w1p + (q0 + u) * 128 + te);
+                            for (int u = 0; u < 8; u++) wv[u] = __ldg(args.se_w1p + (q0 + u) * 128 + j);
 #pragma unroll
                             for (int u = 0; u < 8; u++) {
                                 const int q = q0 + u;
@@ -520,76 +608,62 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                 h1 = fmaf(wf[4], m1b.x, h1); h1 = fmaf(wf[5], m1b.y, h1); h1 = fmaf(wf[6], m1b.z, h1); h1 = fmaf(wf[7], m1b.w, h1);
                             }
                         }
-                        s_hid[te] = fmaxf(h0, 0.f);
-                        s_hid[128 + te] = fmaxf(h1, 0.f);
+                        s_hidp[(hc * 2 + 0) * 128 + j] = h0;
+                        s_hidp[(hc * 2 + 1) * 128 + j] = h1;
                     }
                     epi_bar_sync();
-                    // ---- FC2 (128 -> 256) + sigmoid: thread te owns channels te and te + 128
                     {
-                        float g[2][2];
-                        g[0][0] = g[1][0] = args.se_b2[te];
-                        g[0][1] = g[1][1] = args.se_b2[te + 128];
+                        const int b = te >> 7, j = te & 127;  // [board][hidden unit]
+                        s_hid[te] = fmaxf(args.se_b1[j] + s_hidp[b * 128 + j] + s_hidp[(2 + b) * 128 + j], 0.f);
+                    }
+                    epi_bar_sync();
+                    // ---- FC2 (128 -> 256) + sigmoid: thread te owns channel te for both boards
+                    {
+                        float g0 = args.se_b2[te], g1 = g0;
 #pragma unroll 1
-                        for (int q0 = 0; q0 < 16; q0 += 4) {
-                            uint4 wv[4][2];
+                        for (int q0 = 0; q0 < 16; q0 += 8) {
+                            uint4 wv[8];
 #pragma unroll
-                            for (int u = 0; u < 4; u++) {
-                                wv[u][0] = __ldg(args.se_w2p + (q0 + u) * 256 + te);
-                                wv[u][1] = __ldg(args.se_w2p + (q0 + u) * 256 + te + 128);
-                            }
+                            for (int u = 0; u < 8; u++) wv[u] = __ldg(args.se_w2p + (q0 + u) * 256 + te);
 #pragma unroll
-                            for (int u = 0; u < 4; u++) {
+                            for (int u = 0; u < 8; u++) {
                                 const int q = q0 + u;
+                                float wf[8];
+                                bf16x8_to_float(wv[u], wf);
                                 const float4 h0a = *reinterpret_cast<const float4 *>(s_hid + q * 8);
                                 const float4 h0b = *reinterpret_cast<const float4 *>(s_hid + q * 8 + 4);
                                 const float4 h1a = *reinterpret_cast<const float4 *>(s_hid + 128 + q * 8);
                                 const float4 h1b = *reinterpret_cast<const float4 *>(s_hid + 128 + q * 8 + 4);
-                                const float hv0[8] = {h0a.x, h0a.y, h0a.z, h0a.w, h0b.x, h0b.y, h0b.z, h0b.w};
-                                const float hv1[8] = {h1a.x, h1a.y, h1a.z, h1a.w, h1b.x, h1b.y, h1b.z, h1b.w};
-#pragma unroll
-                                for (int half = 0; half < 2; half++) {
-                                    float wf[8];
-                                    bf16x8_to_float(wv[u][half], wf);
-#pragma unroll
-                                    for (int i = 0; i < 8; i++) {
-                                        g[0][half] = fmaf(wf[i], hv0[i], g[0][half]);
-                                        g[1][half] = fmaf(wf[i], hv1[i], g[1][half]);
-                                    }
-                                }
+                                g0 = fmaf(wf[0], h0a.x, g0); g0 = fmaf(wf[1], h0a.y, g0); g0 = fmaf(wf[2], h0a.z, g0); g0 = fmaf(wf[3], h0a.w, g0);
+                                g0 = fmaf(wf[4], h0b.x, g0); g0 = fmaf(wf[5], h0b.y, g0); g0 = fmaf(wf[6], h0b.z, g0); g0 = fmaf(wf[7], h0b.w, g0);
+                                g1 = fmaf(wf[0], h1a.x, g1); g1 = fmaf(wf[1], h1a.y, g1); g1 = fmaf(wf[2], h1a.z, g1); g1 = fmaf(wf[3], h1a.w, g1);
+                                g1 = fmaf(wf[4], h1b.x, g1); g1 = fmaf(wf[5], h1b.y, g1); g1 = fmaf(wf[6], h1b.z, g1); g1 = fmaf(wf[7], h1b.w, g1);
                             }
                         }
-#pragma unroll
-                        for (int b = 0; b < 2; b++)
-#pragma unroll
-                            for (int half = 0; half < 2; half++)
-                                s_gate[b * 256 + te + 128 * half] = 1.f / (1.f + __expf(-g[b][half]));
+                        s_gate[te] = 1.f / (1.f + __expf(-g0));
+                        s_gate[256 + te] = 1.f / (1.f + __expf(-g1));
                     }
                     epi_bar_sync();
+                    if (prof) { const long long t = clock64(); pe_fc += t - tp2; tp2 = t; }
                 }
 
                 // ---- final pass: y (recomputed from TMEM), [gate * y + x], ReLU, bf16 store ------
                 const float *gate = s_gate + (quad >> 1) * 256;
-                uint4 *orow = reinterpret_cast<uint4 *>(static_cast<__nv_bfloat16 *>(args.out) + grow * BN);
-#pragma unroll 1
-                for (int ch = 0; ch < BN / 32; ch++) {
-                    tmem_ld32(taddr + ch * 32, r);
-                    uint4 xv[4];
-                    if constexpr (EPI == EPI_LN_SE) {
+                uint8_t *gout = reinterpret_cast<uint8_t *>(static_cast<__nv_bfloat16 *>(args.out) + wrow0 * BN + c0);
 #pragma unroll
-                        for (int q = 0; q < 4; q++) xv[q] = xn[q];
-                        if (ch + 1 < BN / 32) {
-#pragma unroll
-                            for (int q = 0; q < 4; q++) xn[q] = xrow[(ch + 1) * 4 + q];
-                        }
-                    }
-                    uint32_t pk[16];
+                for (int ch = 0; ch < 4; ch++) {
+                    tmem_ld32(tcol + ch * 32, r);
+                    uint4 xr[4];
+                    if constexpr (EPI == EPI_LN_SE) staged_gather_64B(stg, lane, xa + ch * 4, xr);
+                    uint4 pk[4];
 #pragma unroll
                     for (int j = 0; j < 16; j++) {
-                        const int c = ch * 32 + 2 * j;
+                        const int c = c0 + ch * 32 + 2 * j;
                         float y0 = (__uint_as_float(r[2 * j]) + s_bias[c] - mean) * rstd * s_gamma[c] + s_beta[c];
                         float y1 = (__uint_as_float(r[2 * j + 1]) + s_bias[c + 1] - mean) * rstd * s_gamma[c + 1] + s_beta[c + 1];
                         if constexpr (EPI == EPI_LN_SE) {
-                            const uint32_t xw = reinterpret_cast<const uint32_t *>(xv)[j];
+                            const uint4 xq = xr[j >> 2];
+                            const uint32_t xw = (j & 3) == 0 ? xq.x : ((j & 3) == 1 ? xq.y : ((j & 3) == 2 ? xq.z : xq.w));
                             y0 = fmaxf(fmaf(gate[c], y0, __uint_as_float(xw << 16)), 0.f);
                             y1 = fmaxf(fmaf(gate[c + 1], y1, __uint_as_float(xw & 0xffff0000u)), 0.f);
                         } else if (args.relu) {
@@ -597,14 +671,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             y1 = fmaxf(y1, 0.f);
                         }
                         __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);
-                        pk[j] = *reinterpret_cast<uint32_t *>(&h);
+                        const uint32_t hv = *reinterpret_cast<uint32_t *>(&h);
+                        if ((j & 3) == 0) pk[j >> 2].x = hv;
+                        else if ((j & 3) == 1) pk[j >> 2].y = hv;
+                        else if ((j & 3) == 2) pk[j >> 2].z = hv;
+                        else pk[j >> 2].w = hv;
                     }
-#pragma unroll
-                    for (int q = 0; q < 4; q++) orow[ch * 4 + q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                    staged_store_64B(stg, lane, pk, gout + ch * 64, (size_t)BN * 2, 32);
                 }
+                if (prof) pe_final += clock64() - tp2;
             }
             tc_fence_before();
             mbar_arrive(tempty_bar(as));
+            if (prof) pe_work += clock64() - tp1;
+        }
+        if (prof) {
+            args.prof[blockIdx.x * 16 + 5] = pe_wait;
+            args.prof[blockIdx.x * 16 + 6] = pe_work;
+            args.prof[blockIdx.x * 16 + 7] = pe_stats;
+            args.prof[blockIdx.x * 16 + 8] = pe_pool;
+            args.prof[blockIdx.x * 16 + 9] = pe_fc;
+            args.prof[blockIdx.x * 16 + 10] = pe_final;
         }
     }
 
@@ -756,6 +843,14 @@ int tc_conv_launch(TcConv *c, const __nv_bfloat16 *in, int rows_alloc, int n_uni
         ma = &c->act_maps.back().map;
     }
     TcArgs a;
+    a.prof = nullptr;
+    static long long *d_prof = nullptr;
+    static const bool want_prof = getenv("SCB200_PHASE_PROFILE") != nullptr;
+    if (want_prof) {
+        if (!d_prof) SCB_CUDA(cudaMalloc(&d_prof, 148 * 16 * sizeof(long long)));
+        SCB_CUDA(cudaMemsetAsync(d_prof, 0, 148 * 16 * sizeof(long long), st));
+        a.prof = d_prof;
+    }
     a.out = out;
     a.resid = resid;
     a.bias = c->bias;
@@ -802,6 +897,19 @@ int tc_conv_launch(TcConv *c, const __nv_bfloat16 *in, int rows_alloc, int n_uni
         return SC_E_INVAL;
     }
     SCB_CUDA(cudaGetLastError());
+    if (want_prof) {
+        // debugging aid: per-phase SM-cycle counters of this launch, averaged over CTAs (synchronous!)
+        static long long h[148 * 16];
+        SCB_CUDA(cudaStreamSynchronize(st));
+        SCB_CUDA(cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost));
+        double acc[16] = {0};
+        for (int b = 0; b < grid; b++)
+            for (int k = 0; k < 16; k++) acc[k] += (double)h[b * 16 + k] / grid;
+        fprintf(stderr,
+                "[tc epi=%d taps=%d grid=%d] tiles/cta %.2f | producer wait_empty %.0f | mma: total %.0f wait_tmem_empty %.0f "
+                "wait_full %.0f | epilogue: wait_tmem_full %.0f work %.0f (stats %.0f pool %.0f fc %.0f final %.0f)\n",
+                c->epi, c->taps, grid, acc[4], acc[0], acc[3], acc[1], acc[2], acc[5], acc[6], acc[7], acc[8], acc[9], acc[10]);
+    }
     return SC_OK;
 }
 

@@ -555,25 +555,38 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 uint8_t *stg = s_stage + (warp - 2) * 2048;
                 const size_t wrow0 = (size_t)tile * TC_BM + quad * 32;  // first global row of this warp
                 uint4 xa[16];
+                // FC1 weights do not depend on anything computed here: request them before the pooling pass
+                // so their L2 latency is hidden (thread = (hidden unit j, channel half hc))
+                uint4 w1v[16];
                 if constexpr (EPI == EPI_LN_SE) {
-                    const uint4 *xw = reinterpret_cast<const uint4 *>(args.resid + (wrow0 + (lane >> 2)) * BN + c0) + (lane & 3);
+                    const int j = te & 127, hc = te >> 7;
 #pragma unroll
-                    for (int ch = 0; ch < 4; ch++)
-#pragma unroll
-                        for (int k = 0; k < 4; k++) xa[ch * 4 + k] = xw[(size_t)k * 8 * (BN / 8) + ch * 4];
+                    for (int u = 0; u < 8; u++) w1v[u] = __ldg(args.se_w1p + (hc * 16 + u) * 128 + j);
                 }
                 if constexpr (EPI == EPI_LN_SE) {
                     // ---- squeeze: per-board channel means of y = LN(conv) (fp32) -------------------
-#pragma unroll 1
+                    uint32_t rn[32];
+                    tmem_ld32(tcol, r);
+#pragma unroll
                     for (int ch = 0; ch < 4; ch++) {
-                        tmem_ld32(tcol + ch * 32, r);
+                        // request the next 32 columns while this chunk is normalised and reduced
+                        if (ch < 3) tmem_ld32_nowait(tcol + (ch + 1) * 32, (ch & 1) ? r : rn);
+                        const uint32_t(&cur)[32] = (ch & 1) ? rn : r;
                         float y[32];
 #pragma unroll
                         for (int j = 0; j < 32; j++) {
                             const int c = c0 + ch * 32 + j;
-                            y[j] = (__uint_as_float(r[j]) + s_bias[c] - mean) * rstd * s_gamma[c] + s_beta[c];
+                            y[j] = (__uint_as_float(cur[j]) + s_bias[c] - mean) * rstd * s_gamma[c] + s_beta[c];
                         }
                         s_pool[quad * 256 + c0 + ch * 32 + lane] = warp_transpose_reduce(y, lane);
+                        if (ch < 3) tmem_wait_ld();
+                    }
+                    {
+                        // second half of the FC1 weights (the register file holds 10 warps at <= 168 registers,
+                        // so only half of them could be requested before the pooling pass)
+                        const int j = te & 127, hc = te >> 7;
+#pragma unroll
+                        for (int u = 8; u < 16; u++) w1v[u] = __ldg(args.se_w1p + (hc * 16 + u) * 128 + j);
                     }
                     epi_bar_sync();
                     if (prof) { const long long t = clock64(); pe_pool += t - tp2; tp2 = t; }
@@ -585,31 +598,37 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                     epi_bar_sync();
                     // ---- excitation FC1 (256 -> 128): thread = (hidden unit j, channel half hc), both boards
+                    uint4 w2v[16];
                     {
                         const int j = te & 127, hc = te >> 7;
                         float h0 = 0.f, h1 = 0.f;
-#pragma unroll 1
-                        for (int q0 = hc * 16; q0 < hc * 16 + 16; q0 += 8) {
-                            uint4 wv[8];
 #pragma unroll
-                            for (int u = 0; u < 8; u++) wv[u] = __ldg(args.se_w1p + (q0 + u) * 128 + j);
-#pragma unroll
-                            for (int u = 0; u < 8; u++) {
-                                const int q = q0 + u;
-                                float wf[8];
-                                bf16x8_to_float(wv[u], wf);
-                                const float4 m0a = *reinterpret_cast<const float4 *>(s_mean + q * 8);
-                                const float4 m0b = *reinterpret_cast<const float4 *>(s_mean + q * 8 + 4);
-                                const float4 m1a = *reinterpret_cast<const float4 *>(s_mean + 256 + q * 8);
-                                const float4 m1b = *reinterpret_cast<const float4 *>(s_mean + 256 + q * 8 + 4);
-                                h0 = fmaf(wf[0], m0a.x, h0); h0 = fmaf(wf[1], m0a.y, h0); h0 = fmaf(wf[2], m0a.z, h0); h0 = fmaf(wf[3], m0a.w, h0);
-                                h0 = fmaf(wf[4], m0b.x, h0); h0 = fmaf(wf[5], m0b.y, h0); h0 = fmaf(wf[6], m0b.z, h0); h0 = fmaf(wf[7], m0b.w, h0);
-                                h1 = fmaf(wf[0], m1a.x, h1); h1 = fmaf(wf[1], m1a.y, h1); h1 = fmaf(wf[2], m1a.z, h1); h1 = fmaf(wf[3], m1a.w, h1);
-                                h1 = fmaf(wf[4], m1b.x, h1); h1 = fmaf(wf[5], m1b.y, h1); h1 = fmaf(wf[6], m1b.z, h1); h1 = fmaf(wf[7], m1b.w, h1);
-                            }
+                        for (int u = 0; u < 16; u++) {
+                            const int q = hc * 16 + u;
+                            float wf[8];
+                            bf16x8_to_float(w1v[u], wf);
+                            const float4 m0a = *reinterpret_cast<const float4 *>(s_mean + q * 8);
+                            const float4 m0b = *reinterpret_cast<const float4 *>(s_mean + q * 8 + 4);
+                            const float4 m1a = *reinterpret_cast<const float4 *>(s_mean + 256 + q * 8);
+                            const float4 m1b = *reinterpret_cast<const float4 *>(s_mean + 256 + q * 8 + 4);
+                            h0 = fmaf(wf[0], m0a.x, h0); h0 = fmaf(wf[1], m0a.y, h0); h0 = fmaf(wf[2], m0a.z, h0); h0 = fmaf(wf[3], m0a.w, h0);
+                            h0 = fmaf(wf[4], m0b.x, h0); h0 = fmaf(wf[5], m0b.y, h0); h0 = fmaf(wf[6], m0b.z, h0); h0 = fmaf(wf[7], m0b.w, h0);
+                            h1 = fmaf(wf[0], m1a.x, h1); h1 = fmaf(wf[1], m1a.y, h1); h1 = fmaf(wf[2], m1a.z, h1); h1 = fmaf(wf[3], m1a.w, h1);
+                            h1 = fmaf(wf[4], m1b.x, h1); h1 = fmaf(wf[5], m1b.y, h1); h1 = fmaf(wf[6], m1b.z, h1); h1 = fmaf(wf[7], m1b.w, h1);
                         }
                         s_hidp[(hc * 2 + 0) * 128 + j] = h0;
                         s_hidp[(hc * 2 + 1) * 128 + j] = h1;
+                    }
+                    // FC2 weights (thread = channel te) and the residual rows are requested now; both are
+                    // consumed two barriers later
+#pragma unroll
+                    for (int u = 0; u < 16; u++) w2v[u] = __ldg(args.se_w2p + u * 256 + te);
+                    {
+                        const uint4 *xw = reinterpret_cast<const uint4 *>(args.resid + (wrow0 + (lane >> 2)) * BN + c0) + (lane & 3);
+#pragma unroll
+                        for (int ch = 0; ch < 4; ch++)
+#pragma unroll
+                            for (int k = 0; k < 4; k++) xa[ch * 4 + k] = xw[(size_t)k * 8 * (BN / 8) + ch * 4];
                     }
                     epi_bar_sync();
                     {
@@ -620,25 +639,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     // ---- FC2 (128 -> 256) + sigmoid: thread te owns channel te for both boards
                     {
                         float g0 = args.se_b2[te], g1 = g0;
-#pragma unroll 1
-                        for (int q0 = 0; q0 < 16; q0 += 8) {
-                            uint4 wv[8];
 #pragma unroll
-                            for (int u = 0; u < 8; u++) wv[u] = __ldg(args.se_w2p + (q0 + u) * 256 + te);
-#pragma unroll
-                            for (int u = 0; u < 8; u++) {
-                                const int q = q0 + u;
-                                float wf[8];
-                                bf16x8_to_float(wv[u], wf);
-                                const float4 h0a = *reinterpret_cast<const float4 *>(s_hid + q * 8);
-                                const float4 h0b = *reinterpret_cast<const float4 *>(s_hid + q * 8 + 4);
-                                const float4 h1a = *reinterpret_cast<const float4 *>(s_hid + 128 + q * 8);
-                                const float4 h1b = *reinterpret_cast<const float4 *>(s_hid + 128 + q * 8 + 4);
-                                g0 = fmaf(wf[0], h0a.x, g0); g0 = fmaf(wf[1], h0a.y, g0); g0 = fmaf(wf[2], h0a.z, g0); g0 = fmaf(wf[3], h0a.w, g0);
-                                g0 = fmaf(wf[4], h0b.x, g0); g0 = fmaf(wf[5], h0b.y, g0); g0 = fmaf(wf[6], h0b.z, g0); g0 = fmaf(wf[7], h0b.w, g0);
-                                g1 = fmaf(wf[0], h1a.x, g1); g1 = fmaf(wf[1], h1a.y, g1); g1 = fmaf(wf[2], h1a.z, g1); g1 = fmaf(wf[3], h1a.w, g1);
-                                g1 = fmaf(wf[4], h1b.x, g1); g1 = fmaf(wf[5], h1b.y, g1); g1 = fmaf(wf[6], h1b.z, g1); g1 = fmaf(wf[7], h1b.w, g1);
-                            }
+                        for (int q = 0; q < 16; q++) {
+                            float wf[8];
+                            bf16x8_to_float(w2v[q], wf);
+                            const float4 h0a = *reinterpret_cast<const float4 *>(s_hid + q * 8);
+                            const float4 h0b = *reinterpret_cast<const float4 *>(s_hid + q * 8 + 4);
+                            const float4 h1a = *reinterpret_cast<const float4 *>(s_hid + 128 + q * 8);
+                            const float4 h1b = *reinterpret_cast<const float4 *>(s_hid + 128 + q * 8 + 4);
+                            g0 = fmaf(wf[0], h0a.x, g0); g0 = fmaf(wf[1], h0a.y, g0); g0 = fmaf(wf[2], h0a.z, g0); g0 = fmaf(wf[3], h0a.w, g0);
+                            g0 = fmaf(wf[4], h0b.x, g0); g0 = fmaf(wf[5], h0b.y, g0); g0 = fmaf(wf[6], h0b.z, g0); g0 = fmaf(wf[7], h0b.w, g0);
+                            g1 = fmaf(wf[0], h1a.x, g1); g1 = fmaf(wf[1], h1a.y, g1); g1 = fmaf(wf[2], h1a.z, g1); g1 = fmaf(wf[3], h1a.w, g1);
+                            g1 = fmaf(wf[4], h1b.x, g1); g1 = fmaf(wf[5], h1b.y, g1); g1 = fmaf(wf[6], h1b.z, g1); g1 = fmaf(wf[7], h1b.w, g1);
                         }
                         s_gate[te] = 1.f / (1.f + __expf(-g0));
                         s_gate[256 + te] = 1.f / (1.f + __expf(-g1));
@@ -650,17 +662,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 // ---- final pass: y (recomputed from TMEM), [gate * y + x], ReLU, bf16 store ------
                 const float *gate = s_gate + (quad >> 1) * 256;
                 uint8_t *gout = reinterpret_cast<uint8_t *>(static_cast<__nv_bfloat16 *>(args.out) + wrow0 * BN + c0);
+                uint32_t rm[32];
+                tmem_ld32(tcol, r);
 #pragma unroll
                 for (int ch = 0; ch < 4; ch++) {
-                    tmem_ld32(tcol + ch * 32, r);
+                    if (ch < 3) tmem_ld32_nowait(tcol + (ch + 1) * 32, (ch & 1) ? r : rm);
+                    const uint32_t(&cur)[32] = (ch & 1) ? rm : r;
                     uint4 xr[4];
                     if constexpr (EPI == EPI_LN_SE) staged_gather_64B(stg, lane, xa + ch * 4, xr);
                     uint4 pk[4];
 #pragma unroll
                     for (int j = 0; j < 16; j++) {
                         const int c = c0 + ch * 32 + 2 * j;
-                        float y0 = (__uint_as_float(r[2 * j]) + s_bias[c] - mean) * rstd * s_gamma[c] + s_beta[c];
-                        float y1 = (__uint_as_float(r[2 * j + 1]) + s_bias[c + 1] - mean) * rstd * s_gamma[c + 1] + s_beta[c + 1];
+                        float y0 = (__uint_as_float(cur[2 * j]) + s_bias[c] - mean) * rstd * s_gamma[c] + s_beta[c];
+                        float y1 = (__uint_as_float(cur[2 * j + 1]) + s_bias[c + 1] - mean) * rstd * s_gamma[c + 1] + s_beta[c + 1];
                         if constexpr (EPI == EPI_LN_SE) {
                             const uint4 xq = xr[j >> 2];
                             const uint32_t xw = (j & 3) == 0 ? xq.x : ((j & 3) == 1 ? xq.y : ((j & 3) == 2 ? xq.z : xq.w));
@@ -678,6 +693,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         else pk[j >> 2].w = hv;
                     }
                     staged_store_64B(stg, lane, pk, gout + ch * 64, (size_t)BN * 2, 32);
+                    if (ch < 3) tmem_wait_ld();
                 }
                 if (prof) pe_final += clock64() - tp2;
             }

@@ -86,6 +86,16 @@ int sc_eval(sc_engine *e, int n, const sc_position *pos, const sc_move *moves, c
 int sc_eval_device(sc_engine *e, int n, const void *d_pos, const void *d_moves, const void *d_move_off,
                    int n_moves_total, void *d_priors_out, void *d_value_out, void *stream);
 
+/* asynchronous form of sc_eval for double-buffered callers: submit returns as soon as the work is
+ * queued on `stream` (host buffers must be pinned and stay untouched until the wait returns);
+ * moves and priors are STRIDED: leaf i owns moves[i*SC_MAX_MOVES .. +move_cnt[i]) and the same
+ * range of priors_out.  At most SC_MAX_INFLIGHT tickets may be outstanding. */
+#define SC_MAX_INFLIGHT 4
+int sc_eval_submit(sc_engine *e, int n, const sc_position *pos, const sc_move *moves_strided,
+                   const int32_t *move_cnt, float *priors_out_strided, float *value_out, void *stream,
+                   int *ticket);
+int sc_eval_wait(sc_engine *e, int ticket);
+
 /* -------- bit-exact gates ------------------------------------------------------------------ */
 /* `_encode` (src/chess.rs:845-877): planes_out int8 [n][8][8][112] (rank, file, channel), the
  * `Array3<i8>` the reference builds; meta_out int32 [n][7].  Host pointers. */
@@ -113,6 +123,63 @@ int sc_set_timing(sc_engine *e, int enabled);
 /* level 2: average device time (ms) of the 3x3 256->256 tower convolution launches of the
  * most recent call and how many there were (the roofline kernel of bench.py) */
 int sc_kernel_timing(sc_engine *e, float *conv3x3_avg_ms, int *n_launches);
+
+/* ===================== batched self-play driver (host side, C++) ================================
+ * Replaces the single-tree loop of the `selfplay` binary (src/main.rs:153-238) and `mcts::mcts` /
+ * `mcts::step` (src/mcts.rs:237-328) for thousands of concurrent games: every search tree keeps the
+ * reference's sequential semantics (one rollout at a time per tree: select by PUCT, expand all legal
+ * moves, back up the white-perspective value), and the leaves of all trees are evaluated as one
+ * device batch per step.  Priors are stored on the children at expansion, which removes the
+ * reference's re-evaluation of every node on each descent (src/mcts.rs:149-153) without changing
+ * any result.  Field names follow the reference's CLI (src/main.rs:25-60). */
+typedef struct sc_selfplay_config {
+    int32_t n_trees;            /* games in flight (BASELINE configs[2]: 2048) */
+    int32_t rollout_num;        /* --rollout-num */
+    int32_t num_steps;          /* --num-steps: maximum plies per game */
+    float cpuct;                /* --cpuct */
+    float epsilon;              /* --epsilon: Dirichlet(0.3) mix at the root (src/mcts.rs:171-184) */
+    int32_t with_noise;         /* main.rs passes true; parity runs pass 0 */
+    int32_t temperature_switch; /* --temperature-switch: plies played at temperature 1 */
+    float temperature;          /* --temperature after the switch (0 = first max-N child) */
+    uint64_t seed;              /* per-tree RNG streams derive from this */
+    int32_t n_threads;          /* host worker threads walking the trees */
+    int32_t evaluator;          /* 0 = the engine (GPU); 1 = position-hash stand-in (test hook, no engine) */
+    int32_t pipeline_groups;    /* 1 or 2: trees are split in groups that alternate between host and device */
+    int32_t keep_traces;        /* keep the traces of finished games in memory (sc_selfplay_trace_json) */
+} sc_selfplay_config;
+
+typedef struct sc_selfplay_stats {
+    int64_t leaf_evals;     /* network-evaluated leaves */
+    int64_t terminal_evals; /* rollouts that ended in a position without legal moves (no network call) */
+    int64_t rollouts;
+    int64_t moves;          /* plies played (search results consumed) */
+    int64_t games_finished;
+    int64_t white_wins, black_wins, draws, unfinished; /* unfinished = hit num_steps without an outcome */
+    int64_t batches;
+    double seconds;         /* wall time of sc_selfplay_run */
+    double wait_seconds;    /* of which: host waiting for the device */
+} sc_selfplay_stats;
+
+typedef struct sc_selfplay sc_selfplay;
+
+int sc_selfplay_create(sc_engine *e, const sc_selfplay_config *cfg, sc_selfplay **out);
+/* plays until `max_games` games have finished (each tree slot starts a new game when one ends), or
+ * until `max_moves` plies were played in total (<= 0: no limit), or `max_seconds` elapsed (<= 0: none) */
+int sc_selfplay_run(sc_selfplay *sp, int64_t max_games, int64_t max_moves, double max_seconds,
+                    sc_selfplay_stats *stats);
+/* trace of the k-th finished game in the format of src/trace.rs:23-32
+ * ({"steps": [[uci, q, [[uci, n, q, uct], ...]], ...], "outcome": {...} | null}); returns the number
+ * of bytes needed (including the NUL); copies at most `cap`. */
+int64_t sc_selfplay_trace_json(sc_selfplay *sp, int64_t k, char *buf, int64_t cap);
+int sc_selfplay_destroy(sc_selfplay *sp);
+
+/* Host rules probe: replays `n_history` moves from the start position with the driver's native rules
+ * (the replacement of the python-chess calls at src/chess.rs:665-788) and reports what the reference
+ * would see there: legal moves in python-chess generation order, the packed leaf `_encode` would be
+ * given (node depth = ply), and outcome(claim_draw=True) (termination code of src/chess.rs:87-105 or
+ * 0, winner 1/0/-1).  Returns SC_E_INVAL if a history move is not legal. */
+int sc_rules_probe(const sc_move *history, int n_history, sc_move *legal_out, int *n_legal, sc_position *packed_out,
+                   int *termination, int *winner);
 
 #ifdef __cplusplus
 }

@@ -51,8 +51,10 @@ int launch_nchw_to_nhwc_bf16(const float *in, int n, __nv_bfloat16 *out, cudaStr
 // exp, sequential renormalisation; optional move index dump / full logp dump.
 int launch_move_index(const sc_position *d_pos, const sc_move *d_moves, const int32_t *d_off, int n,
                       int32_t *d_index, cudaStream_t st);
+// moves are CSR (d_off[n+1], d_cnt == nullptr) or strided (d_off == nullptr: leaf b owns
+// [b*SC_MAX_MOVES, +d_cnt[b]) of d_moves and d_priors)
 int launch_policy_gather(const float *logits, const sc_position *d_pos, const sc_move *d_moves,
-                         const int32_t *d_off, int n, float *d_priors, cudaStream_t st);
+                         const int32_t *d_off, const int32_t *d_cnt, int n, float *d_priors, cudaStream_t st);
 int launch_policy_logp_full(const float *logits, int n, float *d_logp /*[n][4672]*/, cudaStream_t st);
 
 // ---- tower_f32.cu -------------------------------------------------------------------------

@@ -138,6 +138,9 @@ struct sc_engine {
     int timing = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float last_tower_ms = 0.f, last_total_ms = 0.f;
+    cudaEvent_t tickets[SC_MAX_INFLIGHT] = {nullptr, nullptr, nullptr, nullptr};
+    int next_ticket = 0;
+    int32_t *d_cnt = nullptr;
     std::vector<cudaEvent_t> kev;  // level-2 timing: event pairs around the 3x3 256->256 convs
     int kev_used = 0;
     float last_conv_avg_ms = 0.f;
@@ -322,6 +325,7 @@ static int alloc_buffers(sc_engine *e)
     SCB_CHECK(dev_alloc(e, &e->d_pos, (size_t)B));
     SCB_CHECK(dev_alloc(e, &e->d_moves, (size_t)e->max_moves_total));
     SCB_CHECK(dev_alloc(e, &e->d_off, (size_t)B + 1));
+    SCB_CHECK(dev_alloc(e, &e->d_cnt, (size_t)B + 1));
     SCB_CHECK(dev_alloc(e, &e->d_priors, (size_t)e->max_moves_total));
     SCB_CHECK(dev_alloc(e, &e->d_index, (size_t)e->max_moves_total));
     SCB_CHECK(dev_alloc(e, &e->d_value, (size_t)B));
@@ -521,6 +525,8 @@ int sc_destroy(sc_engine *e)
     for (int i = 0; i < 4; i++)
         if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     for (cudaEvent_t ev : e->kev) cudaEventDestroy(ev);
+    for (int i = 0; i < SC_MAX_INFLIGHT; i++)
+        if (e->tickets[i]) cudaEventDestroy(e->tickets[i]);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return SC_OK;
@@ -556,7 +562,8 @@ int sc_eval_device(sc_engine *e, int n, const void *d_pos, const void *d_moves, 
     e->d_value = saved;
     SCB_CHECK(rc);
     SCB_CHECK(launch_policy_gather(e->logits, pos, static_cast<const sc_move *>(d_moves),
-                                   static_cast<const int32_t *>(d_move_off), n, static_cast<float *>(d_priors_out), st));
+                                   static_cast<const int32_t *>(d_move_off), nullptr, n,
+                                   static_cast<float *>(d_priors_out), st));
     e->launches += 1;
     return finish_timing(e, st);
 }
@@ -583,6 +590,50 @@ int sc_eval(sc_engine *e, int n, const sc_position *pos, const sc_move *moves, c
     if (total) SCB_CUDA(cudaMemcpyAsync(priors_out, e->d_priors, sizeof(float) * (size_t)total, cudaMemcpyDeviceToHost, st));
     SCB_CUDA(cudaMemcpyAsync(value_out, e->d_value, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, st));
     SCB_CUDA(cudaStreamSynchronize(st));
+    return SC_OK;
+}
+
+int sc_eval_submit(sc_engine *e, int n, const sc_position *pos, const sc_move *moves_strided, const int32_t *move_cnt,
+                   float *priors_out_strided, float *value_out, void *stream, int *ticket)
+{
+    if (!e || !ticket || n < 0 || n > e->max_batch ||
+        (n > 0 && (!pos || !moves_strided || !move_cnt || !priors_out_strided || !value_out))) {
+        set_error("sc_eval_submit: bad argument");
+        return SC_E_INVAL;
+    }
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+    SCB_CUDA(cudaSetDevice(e->device));
+    const int t = e->next_ticket;
+    e->next_ticket = (t + 1) % SC_MAX_INFLIGHT;
+    if (!e->tickets[t]) SCB_CUDA(cudaEventCreateWithFlags(&e->tickets[t], cudaEventDisableTiming));
+    if (n > 0) {
+        const size_t nm = (size_t)n * SC_MAX_MOVES;
+        SCB_CUDA(cudaMemcpyAsync(e->d_pos, pos, sizeof(sc_position) * (size_t)n, cudaMemcpyHostToDevice, st));
+        SCB_CUDA(cudaMemcpyAsync(e->d_cnt, move_cnt, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+        SCB_CUDA(cudaMemcpyAsync(e->d_moves, moves_strided, sizeof(sc_move) * nm, cudaMemcpyHostToDevice, st));
+        SCB_CHECK(encode_for_mode(e, e->d_pos, n, st));
+        const int saved_timing = e->timing;
+        e->timing = 0;  // asynchronous path never synchronises
+        int rc = run_network(e, n, st);
+        e->timing = saved_timing;
+        SCB_CHECK(rc);
+        SCB_CHECK(launch_policy_gather(e->logits, e->d_pos, e->d_moves, nullptr, e->d_cnt, n, e->d_priors, st));
+        e->launches += 1;
+        SCB_CUDA(cudaMemcpyAsync(priors_out_strided, e->d_priors, sizeof(float) * nm, cudaMemcpyDeviceToHost, st));
+        SCB_CUDA(cudaMemcpyAsync(value_out, e->d_value, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    }
+    SCB_CUDA(cudaEventRecord(e->tickets[t], st));
+    *ticket = t;
+    return SC_OK;
+}
+
+int sc_eval_wait(sc_engine *e, int ticket)
+{
+    if (!e || ticket < 0 || ticket >= SC_MAX_INFLIGHT || !e->tickets[ticket]) {
+        set_error("sc_eval_wait: bad ticket");
+        return SC_E_INVAL;
+    }
+    SCB_CUDA(cudaEventSynchronize(e->tickets[ticket]));
     return SC_OK;
 }
 

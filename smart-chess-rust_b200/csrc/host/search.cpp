@@ -1,0 +1,829 @@
+// Batched self-play driver: thousands of concurrent PUCT search trees whose leaves are evaluated
+// as one device batch per step.
+//
+// Per tree the semantics are those of the reference, restated from:
+//   `Node`, `uct`, `find_max`, `backward`, `select`, `mcts`   src/mcts.rs:16-24, 61-98, 132-289
+//   `step` (move choice + reset of the chosen child)          src/mcts.rs:292-328
+//   the self-play move loop and its termination rules         src/main.rs:153-238
+//   `predict` terminal rule (no legal moves -> +1/-1/0)       src/backends/torch.rs:96-106
+//   `reverse_q` (node's side to move is Black)                src/backends/torch.rs:49-52
+//   trace format                                              src/trace.rs:5-42
+// What is new (north_star): the trees advance in lock-step, each contributing one leaf per step
+// (so every tree still runs its rollouts strictly one after another, exactly like `mcts::mcts`),
+// priors are stored on the children at expansion instead of re-running `predict` at every level of
+// every descent, positions are native bitboards (host/chess_rules.hpp) instead of python-chess
+// objects, and trees are split in two groups that alternate between host work and device work.
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <condition_variable>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../common.cuh"
+#include "chess_rules.hpp"
+
+using namespace scb;
+using namespace scb::chess;
+
+namespace {
+
+// ---- deterministic per-tree RNG (splitmix64 / xoshiro256**) --------------------------------------
+struct Rng {
+    uint64_t s[4];
+    static uint64_t splitmix(uint64_t &x)
+    {
+        uint64_t z = (x += 0x9E3779B97F4A7C15ULL);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+        return z ^ (z >> 31);
+    }
+    void seed(uint64_t v)
+    {
+        for (int i = 0; i < 4; i++) s[i] = splitmix(v);
+    }
+    static uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+    uint64_t next()
+    {
+        uint64_t r = rotl(s[1] * 5, 7) * 9, t = s[1] << 17;
+        s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3];
+        s[2] ^= t;
+        s[3] = rotl(s[3], 45);
+        return r;
+    }
+    double uniform() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
+    double normal()
+    {
+        double u1 = uniform(), u2 = uniform();
+        if (u1 < 1e-300) u1 = 1e-300;
+        return std::sqrt(-2.0 * std::log(u1)) * std::cos(6.283185307179586 * u2);
+    }
+    // Marsaglia-Tsang; alpha < 1 handled by the boost gamma(a) = gamma(a+1) * U^(1/a)
+    double gamma(double alpha)
+    {
+        if (alpha < 1.0) {
+            double u = uniform();
+            if (u < 1e-300) u = 1e-300;
+            return gamma(alpha + 1.0) * std::pow(u, 1.0 / alpha);
+        }
+        const double d = alpha - 1.0 / 3.0, c = 1.0 / std::sqrt(9.0 * d);
+        for (;;) {
+            double x = normal(), v = 1.0 + c * x;
+            if (v <= 0) continue;
+            v = v * v * v;
+            double u = uniform();
+            if (u < 1.0 - 0.0331 * x * x * x * x) return d * v;
+            if (std::log(u) < 0.5 * x * x + d * (1.0 - v + std::log(v))) return d * v;
+        }
+    }
+};
+
+// ---- position-hash stand-in evaluator (test hook; same specification as the oracle's) ----------
+inline uint64_t mix64(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+uint64_t position_hash(const Position &p)
+{
+    uint64_t h = mix64(p.pt[PAWN]);
+    h = mix64(h ^ p.pt[KNIGHT]);
+    h = mix64(h ^ p.pt[BISHOP]);
+    h = mix64(h ^ p.pt[ROOK]);
+    h = mix64(h ^ p.pt[QUEEN]);
+    h = mix64(h ^ p.pt[KING]);
+    h = mix64(h ^ p.occ[WHITE]);
+    h = mix64(h ^ (uint64_t)p.turn);
+    h = mix64(h ^ p.clean_castling());
+    h = mix64(h ^ (uint64_t)(p.ep + 1));
+    return h;
+}
+float hash_eval(const Position &p, const Move *mv, int n, float *priors)
+{
+    const uint64_t h = position_hash(p);
+    float sum = 0.f;
+    for (int i = 0; i < n; i++) {
+        uint64_t m = mix64(h ^ ((uint64_t)mv[i].from << 16) ^ ((uint64_t)mv[i].to << 8) ^ mv[i].promo);
+        priors[i] = (float)((m >> 40) + 1) * (1.0f / 16777216.0f);
+        sum += priors[i];
+    }
+    sum += 1e-5f;
+    for (int i = 0; i < n; i++) priors[i] = priors[i] / sum;
+    uint64_t v = mix64(h ^ 0xABCDEF);
+    return ((float)(v >> 40) * (1.0f / 16777216.0f)) * 2.f - 1.f;
+}
+
+// ---- tree ------------------------------------------------------------------------------------------
+struct Node {
+    Move mv;
+    uint8_t step_color;  // Step.1: the side to move AFTER the move (src/chess.rs:65-66)
+    int32_t depth;
+    float q;             // sum of backed-up rewards, White's perspective
+    int32_t n;
+    float uct;
+    float prior;         // stored at expansion (the reference recomputes it on every descent)
+    int32_t parent;
+    int32_t first_child;
+    int32_t n_children;
+};
+
+struct TraceStep {
+    Move mv;
+    float q;
+    std::vector<Move> cmv;
+    std::vector<int32_t> cn;
+    std::vector<float> cq, cu;
+};
+
+struct TraceRec {
+    std::vector<TraceStep> steps;
+    int termination = T_NONE;
+    int winner = -1;
+    bool has_outcome = false;
+};
+
+struct Tree {
+    std::vector<Node> nodes;
+    int root = 0;
+    Game game;         // state at the search root + scratch pushes along the current path
+    int root_ply = 0;
+    Rng rng;
+    // current rollout
+    std::vector<int> path;
+    int pending_leaf = -1;   // node waiting for the network
+    MoveList pending_moves;
+    // current search / game
+    int rollouts_done = 0;
+    int move_index = 0;      // `i` of the self-play loop (main.rs:168)
+    bool active = true;
+    TraceRec trace;
+    std::vector<float> noisy;  // scratch for root priors mixed with Dirichlet noise
+
+    void new_game(uint64_t seed)
+    {
+        game = Game();
+        nodes.clear();
+        Node r{};
+        r.step_color = WHITE;  // Step(None, White), main.rs:157-165
+        r.parent = -1;
+        r.first_child = -1;
+        nodes.push_back(r);
+        root = 0;
+        root_ply = 0;
+        rollouts_done = 0;
+        move_index = 0;
+        pending_leaf = -1;
+        trace = TraceRec();
+        (void)seed;
+    }
+};
+
+}  // namespace
+
+struct sc_selfplay {
+    sc_engine *eng = nullptr;
+    sc_selfplay_config cfg{};
+    std::vector<Tree> trees;
+    // pinned batch buffers per pipeline group
+    struct Group {
+        int first = 0, count = 0;
+        sc_position *pos = nullptr;
+        sc_move *moves = nullptr;
+        int32_t *cnt = nullptr;
+        float *priors = nullptr, *value = nullptr;
+        int ticket = -1;
+        bool inflight = false;
+    } groups[2];
+    int n_groups = 1;
+    // stats
+    std::atomic<int64_t> leaf_evals{0}, terminal_evals{0}, rollouts{0}, moves{0}, games_finished{0}, white{0}, black{0},
+        draws{0}, unfinished{0}, games_started{0};
+    int64_t batches = 0;
+    int64_t max_games = 0, max_moves = 0;
+    std::mutex trace_mu;
+    std::vector<std::string> traces;
+    // worker pool
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv_start, cv_done;
+    int job_gen = 0, job_group = -1, job_pending = 0;
+    bool quit = false;
+    std::string err;
+};
+
+namespace {
+
+const char *term_name(int t)
+{
+    switch (t) {
+    case T_CHECKMATE: return "Checkmate";
+    case T_STALEMATE: return "Stalemate";
+    case T_INSUFFICIENT: return "InsufficientMaterial";
+    case T_SEVENTYFIVE: return "SeventyfiveMoves";
+    case T_FIVEFOLD: return "FivefoldRepetition";
+    case T_FIFTY: return "FiftyMoves";
+    case T_THREEFOLD: return "ThreefoldRepetition";
+    default: return "VariantDraw";
+    }
+}
+
+void append_float(std::string &s, float v)
+{
+    char b[48];
+    if (v == (float)(long long)v && std::fabs(v) < 1e15f)
+        snprintf(b, sizeof(b), "%.1f", (double)v);
+    else
+        snprintf(b, sizeof(b), "%.9g", (double)v);
+    s += b;
+}
+
+// src/trace.rs:23-32: {"steps": [[move, q, [[move, n, q, uct], ...]], ...], "outcome": ...}
+std::string trace_to_json(const TraceRec &t)
+{
+    std::string s = "{\"outcome\": ";
+    if (t.has_outcome) {
+        s += "{\"termination\": \"";
+        s += term_name(t.termination);
+        s += "\", \"winner\": ";
+        s += t.winner == WHITE ? "\"White\"" : (t.winner == BLACK ? "\"Black\"" : "null");
+        s += "}";
+    } else
+        s += "null";
+    s += ", \"steps\": [";
+    char u[8];
+    for (size_t i = 0; i < t.steps.size(); i++) {
+        const TraceStep &st = t.steps[i];
+        if (i) s += ", ";
+        uci(st.mv, u);
+        s += "[\"";
+        s += u;
+        s += "\", ";
+        append_float(s, st.q);
+        s += ", [";
+        for (size_t k = 0; k < st.cmv.size(); k++) {
+            if (k) s += ", ";
+            uci(st.cmv[k], u);
+            s += "[\"";
+            s += u;
+            s += "\", ";
+            s += std::to_string(st.cn[k]);
+            s += ", ";
+            append_float(s, st.cq[k]);
+            s += ", ";
+            append_float(s, st.cu[k]);
+            s += "]";
+        }
+        s += "]]";
+    }
+    s += "]}";
+    return s;
+}
+
+// `uct` (src/mcts.rs:61-76), same f32 operation order
+inline float uct_score(float sqrt_total, float prior, float q, int n_act, bool reverse_q, float cpuct)
+{
+    const float avg = q / ((float)n_act + 1e-4f) * (reverse_q ? -1.f : 1.f);
+    const float expl = (sqrt_total + 0.01f) / (1.f + (float)n_act) * cpuct * prior;
+    return avg + expl;
+}
+
+void pack_leaf(const Tree &t, int node_depth, sc_position *out)
+{
+    const Game &g = t.game;
+    int n_hist = node_depth + 1;  // history stops at the game root (src/chess.rs:851-867)
+    if (n_hist > SC_LOOKBACK) n_hist = SC_LOOKBACK;
+    if (n_hist > g.ply() + 1) n_hist = g.ply() + 1;
+    memset(out->slot, 0, sizeof(out->slot));
+    for (int k = 0; k < n_hist; k++) {
+        const int ply = g.ply() - k;
+        const Position &p = g.pos_at(ply);
+        uint64_t *s = out->slot[k];
+        for (int i = 0; i < 6; i++) s[i] = p.pt[i + 1];
+        s[6] = p.occ[WHITE];
+        s[7] = g.rep_at(ply);
+    }
+    const Position &c = g.cur;
+    out->meta[0] = c.turn;
+    out->meta[1] = c.fullmove;
+    out->meta[2] = c.has_kingside(c.turn);
+    out->meta[3] = c.has_queenside(c.turn);
+    out->meta[4] = c.has_kingside(!c.turn);
+    out->meta[5] = c.has_queenside(!c.turn);
+    out->meta[6] = c.halfmove;
+    out->n_hist = n_hist;
+}
+
+// expansion (src/mcts.rs:269-283) + backward (src/mcts.rs:90-98) for the pending leaf
+void finish_rollout(sc_selfplay *sp, Tree &t, const float *priors, float value)
+{
+    const int leaf = t.pending_leaf;
+    const int n = t.pending_moves.n;
+    if (n > 0) {
+        const int first = (int)t.nodes.size();
+        const int child_color = !t.game.cur.turn;
+        const int depth = t.nodes[leaf].depth + 1;
+        t.nodes.resize(first + n);
+        for (int i = 0; i < n; i++) {
+            Node &c = t.nodes[first + i];
+            c.mv = t.pending_moves.m[i];
+            c.step_color = (uint8_t)child_color;
+            c.depth = depth;
+            c.q = 0.f;
+            c.n = 0;
+            c.uct = 0.f;
+            c.prior = priors[i];
+            c.parent = leaf;
+            c.first_child = -1;
+            c.n_children = 0;
+        }
+        t.nodes[leaf].first_child = first;
+        t.nodes[leaf].n_children = n;
+    }
+    for (int idx : t.path) {
+        t.nodes[idx].n += 1;
+        t.nodes[idx].q += value;
+    }
+    // unwind the scratch pushes back to the search root
+    while (t.game.ply() > t.root_ply) t.game.pop();
+    t.pending_leaf = -1;
+    t.rollouts_done++;
+    sp->rollouts.fetch_add(1, std::memory_order_relaxed);
+}
+
+// one `select` descent (src/mcts.rs:132-227). Returns true if the leaf needs the network.
+bool descend(sc_selfplay *sp, Tree &t)
+{
+    const sc_selfplay_config &cfg = sp->cfg;
+    t.path.clear();
+    int node = t.root;
+    t.path.push_back(node);
+    for (;;) {
+        Node &nd = t.nodes[node];
+        if (nd.n_children == 0) break;  // leaf: unexplored or terminal
+        int best;
+        if (nd.n_children == 1)
+            best = nd.first_child;
+        else {
+            const bool reverse_q = nd.step_color == BLACK;
+            const Node *ch = &t.nodes[nd.first_child];
+            int tot = 0;
+            for (int i = 0; i < nd.n_children; i++) tot += ch[i].n;
+            const float sq = std::sqrt((float)tot);
+            const float *pri = nullptr;
+            const bool is_root = t.path.size() == 1;
+            if (is_root && cfg.with_noise && nd.n_children >= 2) {
+                // fresh Dirichlet(0.3) sample on every rollout (src/mcts.rs:123-130, 171-184)
+                t.noisy.resize(nd.n_children);
+                double tot_g = 0.0;
+                std::vector<double> g(nd.n_children);
+                for (int i = 0; i < nd.n_children; i++) {
+                    g[i] = t.rng.gamma(0.3);
+                    tot_g += g[i];
+                }
+                for (int i = 0; i < nd.n_children; i++)
+                    t.noisy[i] = ch[i].prior * (1.0f - cfg.epsilon) + (float)(g[i] / tot_g) * cfg.epsilon;
+                pri = t.noisy.data();
+            }
+            int bi = 0;
+            float bu = 0.f;
+            for (int i = 0; i < nd.n_children; i++) {
+                Node &c = t.nodes[nd.first_child + i];
+                const float u = uct_score(sq, pri ? pri[i] : c.prior, c.q, c.n, reverse_q, cfg.cpuct);
+                c.uct = u;
+                if (i == 0 || u >= bu) {  // Iterator::max_by keeps the LAST maximum
+                    bu = u;
+                    bi = i;
+                }
+            }
+            best = nd.first_child + bi;
+        }
+        t.game.push(t.nodes[best].mv);
+        t.path.push_back(best);
+        node = best;
+    }
+    // `predict` at the leaf: legal moves; none -> terminal value without the network
+    t.pending_leaf = node;
+    t.game.cur.legal_moves(t.pending_moves);
+    if (t.pending_moves.n == 0) {
+        float v = 0.f;
+        if (t.game.cur.in_check()) v = t.game.cur.turn == WHITE ? -1.f : 1.f;  // winner = side that mated
+        sp->terminal_evals.fetch_add(1, std::memory_order_relaxed);
+        finish_rollout(sp, t, nullptr, v);
+        return false;
+    }
+    return true;
+}
+
+// the move choice of `mcts::step` (src/mcts.rs:292-328) + the loop body of main.rs:198-228.
+// Returns false when the game is over.
+bool play_move(sc_selfplay *sp, Tree &t)
+{
+    const sc_selfplay_config &cfg = sp->cfg;
+    Node &root = t.nodes[t.root];
+    bool over = false;
+    if (root.n_children == 0) {
+        // step() == None: no legal move at the root -> outcome, break (main.rs:212-216)
+        int w;
+        int term = t.game.outcome(true, &w);
+        t.trace.has_outcome = term != T_NONE;
+        t.trace.termination = term;
+        t.trace.winner = w;
+        over = true;
+    } else {
+        const float temperature = t.move_index < cfg.temperature_switch ? 1.0f : cfg.temperature;
+        const Node *ch = &t.nodes[root.first_child];
+        int choice = 0;
+        if (temperature == 0.0f) {
+            for (int i = 1; i < root.n_children; i++)
+                if (ch[i].n > ch[choice].n) choice = i;  // position() of the FIRST maximum
+        } else {
+            // WeightedIndex over N^(1/T)
+            const float power = 1.0f / temperature;
+            double tot = 0.0;
+            std::vector<double> w(root.n_children);
+            for (int i = 0; i < root.n_children; i++) {
+                w[i] = std::pow((float)ch[i].n, power);
+                tot += w[i];
+            }
+            double r = t.rng.uniform() * tot, acc = 0.0;
+            choice = root.n_children - 1;
+            for (int i = 0; i < root.n_children; i++) {
+                acc += w[i];
+                if (r < acc) {
+                    choice = i;
+                    break;
+                }
+            }
+        }
+        TraceStep st;
+        st.mv = ch[choice].mv;
+        st.q = root.q;
+        if (cfg.keep_traces) {
+            st.cmv.resize(root.n_children);
+            st.cn.resize(root.n_children);
+            st.cq.resize(root.n_children);
+            st.cu.resize(root.n_children);
+            for (int i = 0; i < root.n_children; i++) {
+                st.cmv[i] = ch[i].mv;
+                st.cn[i] = ch[i].n;
+                st.cq[i] = ch[i].q;
+                st.cu[i] = ch[i].uct;
+            }
+            t.trace.steps.push_back(std::move(st));
+        }
+        // navigate_down + reset(): the chosen child becomes a fresh root (q = 0, n = 0, no children)
+        Node nr = ch[choice];
+        nr.q = 0.f;
+        nr.n = 0;
+        nr.first_child = -1;
+        nr.n_children = 0;
+        nr.parent = -1;
+        t.game.push(nr.mv);
+        t.root_ply = t.game.ply();
+        t.nodes.clear();
+        t.nodes.push_back(nr);
+        t.root = 0;
+        sp->moves.fetch_add(1, std::memory_order_relaxed);
+        // main.rs:223-228: the outcome is only looked at after move index 100
+        if (t.move_index > 100) {
+            int w;
+            int term = t.game.outcome(true, &w);
+            if (term != T_NONE) {
+                t.trace.has_outcome = true;
+                t.trace.termination = term;
+                t.trace.winner = w;
+                over = true;
+            }
+        }
+        t.move_index++;
+        if (!over && t.move_index >= cfg.num_steps) over = true;  // loop bound: trace saved without outcome
+    }
+    t.rollouts_done = 0;
+    if (over) {
+        if (t.trace.has_outcome) {
+            if (t.trace.winner == WHITE) sp->white++;
+            else if (t.trace.winner == BLACK) sp->black++;
+            else sp->draws++;
+        } else
+            sp->unfinished++;
+        if (cfg.keep_traces) {
+            std::string js = trace_to_json(t.trace);
+            std::lock_guard<std::mutex> lk(sp->trace_mu);
+            sp->traces.push_back(std::move(js));
+        }
+        sp->games_finished++;
+    }
+    return !over;
+}
+
+// advance one tree until it has a leaf for the network (true) or has no more work (false)
+bool advance_tree(sc_selfplay *sp, Tree &t, sc_position *pos, sc_move *moves, int32_t *cnt, const float *priors,
+                  const float *value)
+{
+    if (t.pending_leaf >= 0) {
+        if (sp->cfg.evaluator == 0)
+            finish_rollout(sp, t, priors, *value);
+    }
+    *cnt = 0;
+    for (;;) {
+        if (!t.active) return false;
+        if (t.rollouts_done >= sp->cfg.rollout_num) {
+            if (!play_move(sp, t)) {
+                // start the next game in this slot if the run still needs games
+                int64_t started = sp->games_started.fetch_add(1) + 1;
+                if (sp->max_games > 0 && started > sp->max_games) {
+                    t.active = false;
+                    return false;
+                }
+                t.new_game(0);
+            }
+            if (sp->max_moves > 0 && sp->moves.load(std::memory_order_relaxed) >= sp->max_moves) {
+                t.active = false;
+                return false;
+            }
+            continue;
+        }
+        if (descend(sp, t)) {
+            if (sp->cfg.evaluator == 1) {
+                float pri[256];
+                float v = hash_eval(t.game.cur, t.pending_moves.m, t.pending_moves.n, pri);
+                sp->leaf_evals.fetch_add(1, std::memory_order_relaxed);
+                finish_rollout(sp, t, pri, v);
+                continue;
+            }
+            pack_leaf(t, t.nodes[t.pending_leaf].depth, pos);
+            for (int i = 0; i < t.pending_moves.n; i++) {
+                moves[i].from = t.pending_moves.m[i].from;
+                moves[i].to = t.pending_moves.m[i].to;
+                moves[i].promo = t.pending_moves.m[i].promo;
+                moves[i].pad = 0;
+            }
+            *cnt = t.pending_moves.n;
+            sp->leaf_evals.fetch_add(1, std::memory_order_relaxed);
+            return true;
+        }
+    }
+}
+
+void run_group_slice(sc_selfplay *sp, int g, int worker, int n_workers)
+{
+    sc_selfplay::Group &G = sp->groups[g];
+    const int per = (G.count + n_workers - 1) / n_workers;
+    const int lo = worker * per, hi = std::min(G.count, lo + per);
+    for (int i = lo; i < hi; i++) {
+        Tree &t = sp->trees[G.first + i];
+        advance_tree(sp, t, G.pos + i, G.moves + (size_t)i * SC_MAX_MOVES, G.cnt + i,
+                     G.priors + (size_t)i * SC_MAX_MOVES, G.value + i);
+    }
+}
+
+void worker_main(sc_selfplay *sp, int worker, int n_workers)
+{
+    int seen = 0;
+    for (;;) {
+        int g;
+        {
+            std::unique_lock<std::mutex> lk(sp->mu);
+            sp->cv_start.wait(lk, [&] { return sp->quit || sp->job_gen != seen; });
+            if (sp->quit) return;
+            seen = sp->job_gen;
+            g = sp->job_group;
+        }
+        run_group_slice(sp, g, worker, n_workers);
+        {
+            std::lock_guard<std::mutex> lk(sp->mu);
+            if (--sp->job_pending == 0) sp->cv_done.notify_one();
+        }
+    }
+}
+
+void parallel_advance(sc_selfplay *sp, int g)
+{
+    const int nw = (int)sp->workers.size();
+    if (nw == 0) {
+        run_group_slice(sp, g, 0, 1);
+        return;
+    }
+    {
+        std::lock_guard<std::mutex> lk(sp->mu);
+        sp->job_group = g;
+        sp->job_pending = nw;
+        sp->job_gen++;
+    }
+    sp->cv_start.notify_all();
+    std::unique_lock<std::mutex> lk(sp->mu);
+    sp->cv_done.wait(lk, [&] { return sp->job_pending == 0; });
+}
+
+}  // namespace
+
+extern "C" {
+
+int sc_selfplay_create(sc_engine *e, const sc_selfplay_config *cfg, sc_selfplay **out)
+{
+    if (!cfg || !out || cfg->n_trees <= 0 || cfg->rollout_num <= 0 || cfg->num_steps <= 0 ||
+        (cfg->evaluator == 0 && !e) || (cfg->evaluator != 0 && cfg->evaluator != 1)) {
+        set_error("sc_selfplay_create: bad argument");
+        return SC_E_INVAL;
+    }
+    sc_selfplay *sp = new sc_selfplay();
+    sp->eng = e;
+    sp->cfg = *cfg;
+    sp->n_groups = cfg->pipeline_groups >= 2 && cfg->n_trees >= 2 && cfg->evaluator == 0 ? 2 : 1;
+    if (e) {
+        int mb = 0;
+        sc_info(e, nullptr, &mb, nullptr);
+        const int per_group = (cfg->n_trees + sp->n_groups - 1) / sp->n_groups;
+        if (per_group > mb) {
+            delete sp;
+            set_error("sc_selfplay_create: trees per pipeline group exceed the engine's max_batch");
+            return SC_E_INVAL;
+        }
+    }
+    sp->trees.resize(cfg->n_trees);
+    for (int i = 0; i < cfg->n_trees; i++) {
+        sp->trees[i].rng.seed(cfg->seed * 0x9E3779B97F4A7C15ULL + (uint64_t)i + 1);
+        sp->trees[i].new_game(0);
+    }
+    const int per = (cfg->n_trees + sp->n_groups - 1) / sp->n_groups;
+    for (int g = 0; g < sp->n_groups; g++) {
+        sc_selfplay::Group &G = sp->groups[g];
+        G.first = g * per;
+        G.count = std::min(per, cfg->n_trees - G.first);
+        const size_t nm = (size_t)G.count * SC_MAX_MOVES;
+        if (cfg->evaluator == 0) {
+            if (cudaMallocHost(&G.pos, sizeof(sc_position) * G.count) != cudaSuccess ||
+                cudaMallocHost(&G.moves, sizeof(sc_move) * nm) != cudaSuccess ||
+                cudaMallocHost(&G.cnt, sizeof(int32_t) * G.count) != cudaSuccess ||
+                cudaMallocHost(&G.priors, sizeof(float) * nm) != cudaSuccess ||
+                cudaMallocHost(&G.value, sizeof(float) * G.count) != cudaSuccess) {
+                set_error("sc_selfplay_create: pinned allocation failed");
+                sc_selfplay_destroy(sp);
+                return SC_E_CUDA;
+            }
+        } else {
+            G.pos = new sc_position[G.count];
+            G.moves = new sc_move[nm];
+            G.cnt = new int32_t[G.count];
+            G.priors = new float[nm];
+            G.value = new float[G.count];
+        }
+        memset(G.cnt, 0, sizeof(int32_t) * G.count);
+    }
+    const int nt = cfg->n_threads > 1 ? cfg->n_threads : 0;
+    for (int w = 0; w < nt; w++) sp->workers.emplace_back(worker_main, sp, w, nt);
+    *out = sp;
+    return SC_OK;
+}
+
+int sc_selfplay_run(sc_selfplay *sp, int64_t max_games, int64_t max_moves, double max_seconds, sc_selfplay_stats *stats)
+{
+    if (!sp) return SC_E_INVAL;
+    using clk = std::chrono::steady_clock;
+    const auto t0 = clk::now();
+    sp->max_games = max_games;
+    sp->max_moves = max_moves;
+    // the games already sitting in the tree slots count as started
+    if (sp->games_started.load() == 0) sp->games_started = (int64_t)sp->trees.size();
+    if (max_games > 0)
+        for (size_t i = 0; i < sp->trees.size(); i++)
+            if ((int64_t)i >= max_games && sp->trees[i].move_index == 0 && sp->trees[i].rollouts_done == 0)
+                sp->trees[i].active = false;
+    double wait_s = 0.0;
+    int rc = SC_OK;
+    bool any = true;
+    while (any && rc == SC_OK) {
+        any = false;
+        for (int g = 0; g < sp->n_groups && rc == SC_OK; g++) {
+            sc_selfplay::Group &G = sp->groups[g];
+            if (G.inflight) {
+                const auto w0 = clk::now();
+                rc = sc_eval_wait(sp->eng, G.ticket);
+                wait_s += std::chrono::duration<double>(clk::now() - w0).count();
+                G.inflight = false;
+                if (rc != SC_OK) break;
+            }
+            parallel_advance(sp, g);
+            int n_leaves = 0;
+            for (int i = 0; i < G.count; i++) n_leaves += G.cnt[i] > 0;
+            if (sp->cfg.evaluator == 0 && n_leaves > 0) {
+                rc = sc_eval_submit(sp->eng, G.count, G.pos, G.moves, G.cnt, G.priors, G.value, nullptr, &G.ticket);
+                G.inflight = rc == SC_OK;
+                sp->batches++;
+                any = true;
+            }
+        }
+        if (max_seconds > 0 && std::chrono::duration<double>(clk::now() - t0).count() > max_seconds) {
+            for (auto &t : sp->trees) t.active = false;
+            for (int g = 0; g < sp->n_groups; g++)
+                if (sp->groups[g].inflight) {
+                    sc_eval_wait(sp->eng, sp->groups[g].ticket);
+                    sp->groups[g].inflight = false;
+                }
+            break;
+        }
+    }
+    if (stats) {
+        stats->leaf_evals = sp->leaf_evals;
+        stats->terminal_evals = sp->terminal_evals;
+        stats->rollouts = sp->rollouts;
+        stats->moves = sp->moves;
+        stats->games_finished = sp->games_finished;
+        stats->white_wins = sp->white;
+        stats->black_wins = sp->black;
+        stats->draws = sp->draws;
+        stats->unfinished = sp->unfinished;
+        stats->batches = sp->batches;
+        stats->seconds = std::chrono::duration<double>(clk::now() - t0).count();
+        stats->wait_seconds = wait_s;
+    }
+    return rc;
+}
+
+int64_t sc_selfplay_trace_json(sc_selfplay *sp, int64_t k, char *buf, int64_t cap)
+{
+    if (!sp) return -1;
+    std::lock_guard<std::mutex> lk(sp->trace_mu);
+    if (k < 0 || k >= (int64_t)sp->traces.size()) return -1;
+    const std::string &s = sp->traces[(size_t)k];
+    if (buf && cap > 0) {
+        const int64_t n = std::min<int64_t>(cap - 1, (int64_t)s.size());
+        memcpy(buf, s.data(), (size_t)n);
+        buf[n] = 0;
+    }
+    return (int64_t)s.size() + 1;
+}
+
+int sc_rules_probe(const sc_move *history, int n_history, sc_move *legal_out, int *n_legal, sc_position *packed_out,
+                   int *termination, int *winner)
+{
+    if (n_history < 0 || (n_history > 0 && !history)) {
+        set_error("sc_rules_probe: bad argument");
+        return SC_E_INVAL;
+    }
+    Tree t;
+    t.new_game(0);
+    MoveList l;
+    for (int i = 0; i < n_history; i++) {
+        t.game.cur.legal_moves(l);
+        Move m{history[i].from, history[i].to, history[i].promo};
+        bool ok = false;
+        for (int k = 0; k < l.n; k++) ok = ok || (l.m[k] == m);
+        if (!ok) {
+            set_error("sc_rules_probe: illegal move in history at ply " + std::to_string(i));
+            return SC_E_INVAL;
+        }
+        t.game.push(m);
+    }
+    t.game.cur.legal_moves(l);
+    if (n_legal) *n_legal = l.n;
+    if (legal_out)
+        for (int k = 0; k < l.n; k++) legal_out[k] = sc_move{l.m[k].from, l.m[k].to, l.m[k].promo, 0};
+    if (packed_out) pack_leaf(t, t.game.ply(), packed_out);
+    if (termination) {
+        int w = -1;
+        *termination = t.game.outcome(true, &w);
+        if (winner) *winner = w;
+    }
+    return SC_OK;
+}
+
+int sc_selfplay_destroy(sc_selfplay *sp)
+{
+    if (!sp) return SC_OK;
+    {
+        std::lock_guard<std::mutex> lk(sp->mu);
+        sp->quit = true;
+    }
+    sp->cv_start.notify_all();
+    for (auto &w : sp->workers) w.join();
+    for (int g = 0; g < sp->n_groups; g++) {
+        sc_selfplay::Group &G = sp->groups[g];
+        if (sp->cfg.evaluator == 0) {
+            if (G.inflight && sp->eng) sc_eval_wait(sp->eng, G.ticket);
+            cudaFreeHost(G.pos);
+            cudaFreeHost(G.moves);
+            cudaFreeHost(G.cnt);
+            cudaFreeHost(G.priors);
+            cudaFreeHost(G.value);
+        } else {
+            delete[] G.pos;
+            delete[] G.moves;
+            delete[] G.cnt;
+            delete[] G.priors;
+            delete[] G.value;
+        }
+    }
+    delete sp;
+    return SC_OK;
+}
+
+}  // extern "C"

@@ -119,7 +119,8 @@ __device__ __forceinline__ void leaf_lse(const float *__restrict__ lg, int lane,
 __global__ void __launch_bounds__(POL_WARPS * 32) policy_gather_kernel(const float *__restrict__ logits,
                                                                        const sc_position *__restrict__ pos,
                                                                        const sc_move *__restrict__ moves,
-                                                                       const int32_t *__restrict__ off, int n,
+                                                                       const int32_t *__restrict__ off,
+                                                                       const int32_t *__restrict__ cnts, int n,
                                                                        float *__restrict__ priors)
 {
     __shared__ int8_t s_q[9], s_k[25];
@@ -134,8 +135,8 @@ __global__ void __launch_bounds__(POL_WARPS * 32) policy_gather_kernel(const flo
     float mx, lsum;
     leaf_lse(lg, lane, mx, lsum);
     const int turn = pos[b].meta[0];
-    const int beg = off[b];
-    int cnt = off[b + 1] - beg;
+    const int beg = off ? off[b] : b * SC_MAX_MOVES;
+    int cnt = off ? off[b + 1] - beg : cnts[b];
     if (cnt > SC_MAX_MOVES) cnt = SC_MAX_MOVES;
     for (int k = lane; k < cnt; k += 32) {
         int idx = move_index_dev(moves[beg + k], turn, s_q, s_k);
@@ -181,11 +182,11 @@ int launch_move_index(const sc_position *d_pos, const sc_move *d_moves, const in
 }
 
 int launch_policy_gather(const float *logits, const sc_position *d_pos, const sc_move *d_moves,
-                         const int32_t *d_off, int n, float *d_priors, cudaStream_t st)
+                         const int32_t *d_off, const int32_t *d_cnt, int n, float *d_priors, cudaStream_t st)
 {
     if (n <= 0) return SC_OK;
     policy_gather_kernel<<<(n + POL_WARPS - 1) / POL_WARPS, POL_WARPS * 32, 0, st>>>(logits, d_pos, d_moves, d_off,
-                                                                                      n, d_priors);
+                                                                                      d_cnt, n, d_priors);
     SCB_CUDA(cudaGetLastError());
     return SC_OK;
 }

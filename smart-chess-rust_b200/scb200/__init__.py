@@ -6,6 +6,8 @@ CPU box), but creating an Engine without an sm_100 device raises.
 """
 from .binding import (  # noqa: F401
     Engine,
+    SelfPlay,
+    rules_probe,
     SCError,
     SC_MODE_BF16,
     SC_MODE_FP32,

@@ -21,7 +21,28 @@ assert POSITION_DTYPE.itemsize == 544 and MOVE_DTYPE.itemsize == 4
 DECLARED_SYMBOLS = [
     "sc_create", "sc_destroy", "sc_last_error", "sc_info", "sc_eval", "sc_eval_device", "sc_encode_only",
     "sc_move_index_only", "sc_forward_only", "sc_launch_count", "sc_last_timing", "sc_set_timing", "sc_kernel_timing",
+    "sc_eval_submit", "sc_eval_wait", "sc_selfplay_create", "sc_selfplay_run", "sc_selfplay_trace_json",
+    "sc_selfplay_destroy", "sc_rules_probe",
 ]
+
+
+class SelfPlayConfig(C.Structure):
+    """struct sc_selfplay_config (field names follow the reference CLI, src/main.rs:25-60)"""
+    _fields_ = [("n_trees", C.c_int32), ("rollout_num", C.c_int32), ("num_steps", C.c_int32), ("cpuct", C.c_float),
+                ("epsilon", C.c_float), ("with_noise", C.c_int32), ("temperature_switch", C.c_int32),
+                ("temperature", C.c_float), ("seed", C.c_uint64), ("n_threads", C.c_int32), ("evaluator", C.c_int32),
+                ("pipeline_groups", C.c_int32), ("keep_traces", C.c_int32)]
+
+
+class SelfPlayStats(C.Structure):
+    _fields_ = [("leaf_evals", C.c_int64), ("terminal_evals", C.c_int64), ("rollouts", C.c_int64), ("moves", C.c_int64),
+                ("games_finished", C.c_int64), ("white_wins", C.c_int64), ("black_wins", C.c_int64),
+                ("draws", C.c_int64), ("unfinished", C.c_int64), ("batches", C.c_int64), ("seconds", C.c_double),
+                ("wait_seconds", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
 
 _LIB = None
 
@@ -58,6 +79,15 @@ def load_library():
         L.sc_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.sc_set_timing.argtypes = [C.c_void_p, C.c_int]
         L.sc_kernel_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+        L.sc_eval_submit.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 6 + [C.POINTER(C.c_int)]
+        L.sc_eval_wait.argtypes = [C.c_void_p, C.c_int]
+        L.sc_selfplay_create.argtypes = [C.c_void_p, C.POINTER(SelfPlayConfig), C.POINTER(C.c_void_p)]
+        L.sc_selfplay_run.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_double, C.POINTER(SelfPlayStats)]
+        L.sc_selfplay_trace_json.restype = C.c_int64
+        L.sc_selfplay_trace_json.argtypes = [C.c_void_p, C.c_int64, C.c_char_p, C.c_int64]
+        L.sc_selfplay_destroy.argtypes = [C.c_void_p]
+        L.sc_rules_probe.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.c_void_p,
+                                     C.POINTER(C.c_int), C.POINTER(C.c_int)]
         _LIB = L
     return _LIB
 
@@ -184,3 +214,63 @@ class Engine:
         a, b = C.c_float(), C.c_float()
         _check(load_library().sc_last_timing(self._h, C.byref(a), C.byref(b)), "sc_last_timing")
         return a.value, b.value
+
+
+class SelfPlay:
+    """Batched counterpart of the `selfplay` binary (src/main.rs:153-238): n_trees games in flight,
+    one leaf per tree per device batch.  evaluator="hash" needs no engine (test hook)."""
+
+    def __init__(self, engine, n_trees=2048, rollout_num=180, num_steps=150, cpuct=2.5, epsilon=0.15,
+                 with_noise=True, temperature_switch=4, temperature=0.0, seed=0, n_threads=0, evaluator="engine",
+                 pipeline_groups=2, keep_traces=False):
+        import json as _json
+
+        self._json = _json
+        L = load_library()
+        cfg = SelfPlayConfig(n_trees, rollout_num, num_steps, cpuct, epsilon, int(with_noise), temperature_switch,
+                             temperature, seed, n_threads, 0 if evaluator == "engine" else 1, pipeline_groups,
+                             int(keep_traces))
+        h = C.c_void_p()
+        self._engine = engine  # keep alive
+        _check(L.sc_selfplay_create(engine.handle if engine is not None else None, C.byref(cfg), C.byref(h)),
+               "sc_selfplay_create")
+        self._h = h
+
+    def run(self, max_games=0, max_moves=0, max_seconds=0.0):
+        st = SelfPlayStats()
+        _check(load_library().sc_selfplay_run(self._h, max_games, max_moves, max_seconds, C.byref(st)), "sc_selfplay_run")
+        return st.as_dict()
+
+    def trace(self, k: int):
+        L = load_library()
+        n = L.sc_selfplay_trace_json(self._h, k, None, 0)
+        if n < 0:
+            return None
+        buf = C.create_string_buffer(n)
+        L.sc_selfplay_trace_json(self._h, k, buf, n)
+        return self._json.loads(buf.value.decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().sc_selfplay_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def rules_probe(history):
+    """history: list of (from, to, promo) -> (legal moves [n,3] uint8, sc_position record, (termination, winner))."""
+    h = np.zeros(len(history), dtype=MOVE_DTYPE)
+    for i, m in enumerate(history):
+        h[i] = (int(m[0]), int(m[1]), int(m[2]), 0)
+    legal = np.zeros(256, dtype=MOVE_DTYPE)
+    n, term, win = C.c_int(), C.c_int(), C.c_int()
+    pos = np.zeros(1, dtype=POSITION_DTYPE)
+    _check(load_library().sc_rules_probe(_ptr(h) if len(h) else None, len(h), _ptr(legal), C.byref(n), _ptr(pos),
+                                         C.byref(term), C.byref(win)), "sc_rules_probe")
+    mv = np.stack([legal["from"][: n.value], legal["to"][: n.value], legal["promo"][: n.value]], axis=1)
+    return mv, pos[0], (term.value, win.value)

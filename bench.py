@@ -232,6 +232,8 @@ def main():
     ap.add_argument("--leaves", type=int, default=2048, help="leaves per step per GPU")
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline work (rank 0, N=1)")
+    ap.add_argument("--selfplay-moves", type=int, default=4096, help="plies of batched self-play to time (0 = skip)")
+    ap.add_argument("--threads", type=int, default=0, help="host worker threads for self-play (0 = cores / ranks)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -260,7 +262,9 @@ def main():
     mode = scb200.SC_MODE_BF16 if args.mode == "bf16" else scb200.SC_MODE_FP32
     tmp = tempfile.mkdtemp(prefix="scb200_bench_")
     sd, blob = make_blob(tmp)
-    games, pos, moves, off = make_workload(B, seed=1000 + rank)
+    from scb200 import shard
+
+    games, pos, moves, off = make_workload(B, seed=shard.rank_seed(1000, rank) % (2**31 - 1))
     n_moves = int(off[B])
     eng = scb200.Engine(blob, local_rank, mode, B)
 
@@ -330,11 +334,31 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
 
+    # ---- batched self-play at 180 rollouts (BASELINE configs[2]: 2048 concurrent trees) ---------------
+    sp_stats = None
+    if args.selfplay_moves > 0:
+        nthr = args.threads or max(1, (os.cpu_count() or 8) // max(world, 1) - 1)
+        eng_sp = scb200.Engine(blob, local_rank, mode, B // 2)
+        sp = scb200.SelfPlay(eng_sp, n_trees=B, rollout_num=180, num_steps=150, cpuct=2.5, epsilon=0.15,
+                             with_noise=True, temperature_switch=4, temperature=0.0, seed=shard.rank_seed(100, rank),
+                             n_threads=nthr, pipeline_groups=2)
+        barrier()
+        sp_stats = sp.run(max_moves=args.selfplay_moves)
+        sp_stats["threads"] = nthr
+        sp.close()
+        eng_sp.close()
+
     # ---- max over ranks ------------------------------------------------------------------------
+    sp_secs = sp_stats["seconds"] if sp_stats else 0.0
+    sp_moves = float(sp_stats["moves"]) if sp_stats else 0.0
+    sp_evals = float(sp_stats["leaf_evals"]) if sp_stats else 0.0
     if dist is not None:
-        t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
+        t = torch.tensor([total_ms, e2e_s, sp_secs], dtype=torch.float64, device=f"cuda:{local_rank}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_s = float(t[0]), float(t[1])
+        total_ms, e2e_s, sp_secs = float(t[0]), float(t[1]), float(t[2])
+        t2 = torch.tensor([sp_moves, sp_evals], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t2, op=dist.ReduceOp.SUM)
+        sp_moves, sp_evals = float(t2[0]), float(t2[1])
     value = world * B * K / (total_ms * 1e-3)
     e2e = world * B * K / e2e_s
 
@@ -370,6 +394,14 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "wall_s_timed_region": t_wall,
         }
+        if sp_stats:
+            line["selfplay"] = {
+                "moves_per_s": sp_moves / sp_secs, "leaf_evals_per_s": sp_evals / sp_secs, "unit": "plies/s at 180 rollouts/move",
+                "config": "2048 concurrent trees per GPU, rollout-num 180, cpuct 2.5, temperature-switch 4, epsilon 0.15 noise on, "
+                          "two pipeline groups of 1024 leaves, host threads = %d per GPU" % sp_stats["threads"],
+                "plies": sp_moves, "seconds": sp_secs, "device_wait_frac_rank0": sp_stats["wait_seconds"] / sp_stats["seconds"],
+                "games_finished_rank0": sp_stats["games_finished"],
+            }
         print(json.dumps(line), flush=True)
     eng.close()
     if dist is not None:

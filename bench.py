@@ -178,6 +178,7 @@ def reference_arm(args):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import net
 
+    torch.set_num_threads(os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1; use every host core
     sd = net.init_state_dict(N_BLOCKS, 0)
     games, _, _, _ = make_workload(256, seed=1000)
     batch = 64
@@ -338,7 +339,7 @@ def main():
     sp_stats = None
     if args.selfplay_moves > 0:
         nthr = args.threads or max(1, (os.cpu_count() or 8) // max(world, 1) - 1)
-        eng_sp = scb200.Engine(blob, local_rank, mode, B // 2)
+        eng_sp = scb200.Engine(blob, local_rank, mode, B)
         sp = scb200.SelfPlay(eng_sp, n_trees=B, rollout_num=180, num_steps=150, cpuct=2.5, epsilon=0.15,
                              with_noise=True, temperature_switch=4, temperature=0.0, seed=shard.rank_seed(100, rank),
                              n_threads=nthr, pipeline_groups=2)

@@ -173,6 +173,16 @@ int sc_selfplay_run(sc_selfplay *sp, int64_t max_games, int64_t max_moves, doubl
 int64_t sc_selfplay_trace_json(sc_selfplay *sp, int64_t k, char *buf, int64_t cap);
 int sc_selfplay_destroy(sc_selfplay *sp);
 
+/* ---- arena: two networks play each other (the `play` binary with --black-type nn, src/play.rs:241-343,
+ * and scripts/leader-board).  Both players share one configuration, as the reference's CLI does
+ * (src/play.rs:43-81): rollout_num = --rollout, cpuct, temperature, temperature_switch; noise is off
+ * (play.rs:250), temperature 0 picks uniformly among the most visited children (play.rs:269-278), a game
+ * ends when outcome(claim_draw=true) is set after a ply or after num_steps (200) plies.  `white` moves on
+ * even plies.  Games are played in rounds of n_trees; within a pipeline group every tree is at the same
+ * ply, so each device batch belongs to one network.  Colour-swapped rounds = a second arena with the
+ * engines exchanged, as scripts/leader-board:49-54 does. */
+int sc_arena_create(sc_engine *white, sc_engine *black, const sc_selfplay_config *cfg, sc_selfplay **out);
+
 /* Host rules probe: replays `n_history` moves from the start position with the driver's native rules
  * (the replacement of the python-chess calls at src/chess.rs:665-788) and reports what the reference
  * would see there: legal moves in python-chess generation order, the packed leaf `_encode` would be

@@ -164,6 +164,7 @@ struct Tree {
     int rollouts_done = 0;
     int move_index = 0;      // `i` of the self-play loop (main.rs:168)
     bool active = true;
+    bool game_over = false;  // arena: waiting for the round to end
     TraceRec trace;
     std::vector<float> noisy;  // scratch for root priors mixed with Dirichlet noise
 
@@ -181,6 +182,7 @@ struct Tree {
         rollouts_done = 0;
         move_index = 0;
         pending_leaf = -1;
+        game_over = false;
         trace = TraceRec();
         (void)seed;
     }
@@ -190,6 +192,9 @@ struct Tree {
 
 struct sc_selfplay {
     sc_engine *eng = nullptr;
+    sc_engine *eng_black = nullptr;  // arena mode: eng plays White, eng_black plays Black
+    bool arena = false;
+    int group_ply[2] = {0, 0};       // arena: the ply every tree of the group is searching
     sc_selfplay_config cfg{};
     std::vector<Tree> trees;
     // pinned batch buffers per pipeline group
@@ -201,6 +206,7 @@ struct sc_selfplay {
         float *priors = nullptr, *value = nullptr;
         int ticket = -1;
         bool inflight = false;
+        sc_engine *eng = nullptr;  // engine the in-flight batch was submitted to
     } groups[2];
     int n_groups = 1;
     // stats
@@ -524,6 +530,118 @@ bool play_move(sc_selfplay *sp, Tree &t)
     return !over;
 }
 
+// arena: `NNPlayer::bestmove` choice + `step` + the loop test of `play_loop` (src/play.rs:253-343)
+void play_move_arena(sc_selfplay *sp, Tree &t)
+{
+    const sc_selfplay_config &cfg = sp->cfg;
+    Node &root = t.nodes[t.root];
+    const Node *ch = &t.nodes[root.first_child];
+    const float temperature = root.depth < cfg.temperature_switch ? 1.0f : cfg.temperature;
+    int choice = 0;
+    if (temperature == 0.0f) {
+        int mx = 0, cnt = 0;
+        for (int i = 0; i < root.n_children; i++) mx = std::max(mx, ch[i].n);
+        for (int i = 0; i < root.n_children; i++) cnt += ch[i].n == mx;
+        int pick = (int)(t.rng.uniform() * cnt);  // uniform among the most visited (play.rs:269-278)
+        if (pick >= cnt) pick = cnt - 1;
+        for (int i = 0; i < root.n_children; i++)
+            if (ch[i].n == mx && pick-- == 0) {
+                choice = i;
+                break;
+            }
+    } else {
+        const float power = 1.0f / temperature;
+        double tot = 0.0;
+        std::vector<double> w(root.n_children);
+        for (int i = 0; i < root.n_children; i++) {
+            w[i] = std::pow((float)ch[i].n, power);
+            tot += w[i];
+        }
+        double r = t.rng.uniform() * tot, acc = 0.0;
+        choice = root.n_children - 1;
+        for (int i = 0; i < root.n_children; i++) {
+            acc += w[i];
+            if (r < acc) {
+                choice = i;
+                break;
+            }
+        }
+    }
+    if (cfg.keep_traces) {
+        TraceStep st;
+        st.mv = ch[choice].mv;
+        st.q = root.q;
+        for (int i = 0; i < root.n_children; i++) {
+            st.cmv.push_back(ch[i].mv);
+            st.cn.push_back(ch[i].n);
+            st.cq.push_back(ch[i].q);
+            st.cu.push_back(ch[i].uct);
+        }
+        t.trace.steps.push_back(std::move(st));
+    }
+    Node nr = ch[choice];
+    nr.q = 0.f;
+    nr.n = 0;
+    nr.first_child = -1;
+    nr.n_children = 0;
+    nr.parent = -1;
+    t.game.push(nr.mv);
+    t.root_ply = t.game.ply();
+    t.nodes.clear();
+    t.nodes.push_back(nr);
+    t.root = 0;
+    t.rollouts_done = 0;
+    t.move_index++;
+    sp->moves.fetch_add(1, std::memory_order_relaxed);
+    int w;
+    const int term = t.game.outcome(true, &w);
+    if (term != T_NONE || t.move_index >= cfg.num_steps) {
+        t.trace.has_outcome = term != T_NONE;
+        t.trace.termination = term;
+        t.trace.winner = w;
+        t.game_over = true;
+        if (term == T_NONE) sp->unfinished++;
+        else if (w == WHITE) sp->white++;
+        else if (w == BLACK) sp->black++;
+        else sp->draws++;
+        if (cfg.keep_traces) {
+            std::string js = trace_to_json(t.trace);
+            std::lock_guard<std::mutex> lk(sp->trace_mu);
+            sp->traces.push_back(std::move(js));
+        }
+        sp->games_finished++;
+    }
+}
+
+// arena: a tree only searches the ply its pipeline group is at, then waits for the others
+bool advance_tree_arena(sc_selfplay *sp, Tree &t, int group_ply, sc_position *pos, sc_move *moves, int32_t *cnt,
+                        const float *priors, const float *value)
+{
+    if (t.pending_leaf >= 0) finish_rollout(sp, t, priors, *value);
+    *cnt = 0;
+    for (;;) {
+        if (!t.active || t.game_over || t.move_index > group_ply) return false;
+        if (t.rollouts_done >= sp->cfg.rollout_num) {
+            play_move_arena(sp, t);
+            continue;
+        }
+        if (descend(sp, t)) {
+            if (sp->cfg.evaluator == 1) {
+                float pri[256];
+                float v = hash_eval(t.game.cur, t.pending_moves.m, t.pending_moves.n, pri);
+                sp->leaf_evals.fetch_add(1, std::memory_order_relaxed);
+                finish_rollout(sp, t, pri, v);
+                continue;
+            }
+            pack_leaf(t, t.nodes[t.pending_leaf].depth, pos);
+            for (int i = 0; i < t.pending_moves.n; i++) moves[i] = sc_move{t.pending_moves.m[i].from, t.pending_moves.m[i].to, t.pending_moves.m[i].promo, 0};
+            *cnt = t.pending_moves.n;
+            sp->leaf_evals.fetch_add(1, std::memory_order_relaxed);
+            return true;
+        }
+    }
+}
+
 // advance one tree until it has a leaf for the network (true) or has no more work (false)
 bool advance_tree(sc_selfplay *sp, Tree &t, sc_position *pos, sc_move *moves, int32_t *cnt, const float *priors,
                   const float *value)
@@ -580,8 +698,12 @@ void run_group_slice(sc_selfplay *sp, int g, int worker, int n_workers)
     const int lo = worker * per, hi = std::min(G.count, lo + per);
     for (int i = lo; i < hi; i++) {
         Tree &t = sp->trees[G.first + i];
-        advance_tree(sp, t, G.pos + i, G.moves + (size_t)i * SC_MAX_MOVES, G.cnt + i,
-                     G.priors + (size_t)i * SC_MAX_MOVES, G.value + i);
+        if (sp->arena)
+            advance_tree_arena(sp, t, sp->group_ply[g], G.pos + i, G.moves + (size_t)i * SC_MAX_MOVES, G.cnt + i,
+                               G.priors + (size_t)i * SC_MAX_MOVES, G.value + i);
+        else
+            advance_tree(sp, t, G.pos + i, G.moves + (size_t)i * SC_MAX_MOVES, G.cnt + i,
+                         G.priors + (size_t)i * SC_MAX_MOVES, G.value + i);
     }
 }
 
@@ -638,11 +760,21 @@ int sc_selfplay_create(sc_engine *e, const sc_selfplay_config *cfg, sc_selfplay 
     sp->eng = e;
     sp->cfg = *cfg;
     sp->n_groups = cfg->pipeline_groups >= 2 && cfg->n_trees >= 2 && cfg->evaluator == 0 ? 2 : 1;
+    // Group sizes: the conv kernels run one 2-board tile per SM per wave, so a batch costs
+    // ceil(boards / (2 * SMs)) waves.  Splitting 2048 trees as 1024 + 1024 costs 4 + 4 waves; sizing the
+    // first group to a whole number of waves (888 = 3 * 296 boards on 148 SMs) costs 3 + 4 = the 7 waves
+    // of a single 2048 batch.
+    int size0 = sp->n_groups == 1 ? cfg->n_trees : (cfg->n_trees + 1) / 2;
+    if (sp->n_groups == 2 && e) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+        const int wave = 2 * sms;
+        if (size0 >= wave) size0 = size0 / wave * wave;
+    }
     if (e) {
         int mb = 0;
         sc_info(e, nullptr, &mb, nullptr);
-        const int per_group = (cfg->n_trees + sp->n_groups - 1) / sp->n_groups;
-        if (per_group > mb) {
+        if (std::max(size0, cfg->n_trees - size0) > mb) {
             delete sp;
             set_error("sc_selfplay_create: trees per pipeline group exceed the engine's max_batch");
             return SC_E_INVAL;
@@ -653,11 +785,10 @@ int sc_selfplay_create(sc_engine *e, const sc_selfplay_config *cfg, sc_selfplay 
         sp->trees[i].rng.seed(cfg->seed * 0x9E3779B97F4A7C15ULL + (uint64_t)i + 1);
         sp->trees[i].new_game(0);
     }
-    const int per = (cfg->n_trees + sp->n_groups - 1) / sp->n_groups;
     for (int g = 0; g < sp->n_groups; g++) {
         sc_selfplay::Group &G = sp->groups[g];
-        G.first = g * per;
-        G.count = std::min(per, cfg->n_trees - G.first);
+        G.first = g == 0 ? 0 : size0;
+        G.count = sp->n_groups == 1 ? cfg->n_trees : (g == 0 ? size0 : cfg->n_trees - size0);
         const size_t nm = (size_t)G.count * SC_MAX_MOVES;
         if (cfg->evaluator == 0) {
             if (cudaMallocHost(&G.pos, sizeof(sc_position) * G.count) != cudaSuccess ||
@@ -684,6 +815,33 @@ int sc_selfplay_create(sc_engine *e, const sc_selfplay_config *cfg, sc_selfplay 
     return SC_OK;
 }
 
+int sc_arena_create(sc_engine *white, sc_engine *black, const sc_selfplay_config *cfg, sc_selfplay **out)
+{
+    if (!cfg || (cfg->evaluator == 0 && (!white || !black))) {
+        set_error("sc_arena_create: bad argument");
+        return SC_E_INVAL;
+    }
+    sc_selfplay_config c = *cfg;
+    c.with_noise = 0;  // play.rs:250 turns the Dirichlet noise off
+    int rc = sc_selfplay_create(white, &c, out);
+    if (rc != SC_OK) return rc;
+    if (black) {
+        int mb = 0;
+        sc_info(black, nullptr, &mb, nullptr);
+        int need = 0;
+        for (int g = 0; g < (*out)->n_groups; g++) need = std::max(need, (*out)->groups[g].count);
+        if (need > mb) {
+            sc_selfplay_destroy(*out);
+            *out = nullptr;
+            set_error("sc_arena_create: trees per pipeline group exceed the black engine's max_batch");
+            return SC_E_INVAL;
+        }
+    }
+    (*out)->arena = true;
+    (*out)->eng_black = black;
+    return SC_OK;
+}
+
 int sc_selfplay_run(sc_selfplay *sp, int64_t max_games, int64_t max_moves, double max_seconds, sc_selfplay_stats *stats)
 {
     if (!sp) return SC_E_INVAL;
@@ -706,7 +864,7 @@ int sc_selfplay_run(sc_selfplay *sp, int64_t max_games, int64_t max_moves, doubl
             sc_selfplay::Group &G = sp->groups[g];
             if (G.inflight) {
                 const auto w0 = clk::now();
-                rc = sc_eval_wait(sp->eng, G.ticket);
+                rc = sc_eval_wait(G.eng ? G.eng : sp->eng, G.ticket);
                 wait_s += std::chrono::duration<double>(clk::now() - w0).count();
                 G.inflight = false;
                 if (rc != SC_OK) break;
@@ -714,9 +872,47 @@ int sc_selfplay_run(sc_selfplay *sp, int64_t max_games, int64_t max_moves, doubl
             parallel_advance(sp, g);
             int n_leaves = 0;
             for (int i = 0; i < G.count; i++) n_leaves += G.cnt[i] > 0;
+            if (sp->arena) {
+                // nobody produced a leaf: the whole group finished this ply -> next ply, or next round
+                for (int guard = 0; n_leaves == 0 && guard < 1000000; guard++) {
+                    bool playing = false;
+                    for (int i = 0; i < G.count; i++) {
+                        const Tree &t = sp->trees[G.first + i];
+                        playing = playing || (t.active && !t.game_over);
+                    }
+                    if (playing)
+                        sp->group_ply[g]++;
+                    else {
+                        bool started = false;
+                        for (int i = 0; i < G.count; i++) {
+                            Tree &t = sp->trees[G.first + i];
+                            if (!t.active) continue;
+                            int64_t k = sp->games_started.fetch_add(1) + 1;
+                            if (sp->max_games > 0 && k > sp->max_games) {
+                                t.active = false;
+                                continue;
+                            }
+                            t.new_game(0);
+                            started = true;
+                        }
+                        if (!started) break;
+                        sp->group_ply[g] = 0;
+                    }
+                    parallel_advance(sp, g);
+                    for (int i = 0; i < G.count; i++) n_leaves += G.cnt[i] > 0;
+                    if (sp->cfg.evaluator == 1) {
+                        // hash evaluator never leaves a leaf pending: keep stepping plies until the round is over
+                        bool left = false;
+                        for (int i = 0; i < G.count; i++) left = left || sp->trees[G.first + i].active;
+                        if (!left) break;
+                    }
+                }
+            }
             if (sp->cfg.evaluator == 0 && n_leaves > 0) {
-                rc = sc_eval_submit(sp->eng, G.count, G.pos, G.moves, G.cnt, G.priors, G.value, nullptr, &G.ticket);
+                sc_engine *use = sp->arena && (sp->group_ply[g] & 1) ? sp->eng_black : sp->eng;
+                rc = sc_eval_submit(use, G.count, G.pos, G.moves, G.cnt, G.priors, G.value, nullptr, &G.ticket);
                 G.inflight = rc == SC_OK;
+                G.eng = use;
                 sp->batches++;
                 any = true;
             }
@@ -725,7 +921,7 @@ int sc_selfplay_run(sc_selfplay *sp, int64_t max_games, int64_t max_moves, doubl
             for (auto &t : sp->trees) t.active = false;
             for (int g = 0; g < sp->n_groups; g++)
                 if (sp->groups[g].inflight) {
-                    sc_eval_wait(sp->eng, sp->groups[g].ticket);
+                    sc_eval_wait(sp->groups[g].eng ? sp->groups[g].eng : sp->eng, sp->groups[g].ticket);
                     sp->groups[g].inflight = false;
                 }
             break;
@@ -808,7 +1004,7 @@ int sc_selfplay_destroy(sc_selfplay *sp)
     for (int g = 0; g < sp->n_groups; g++) {
         sc_selfplay::Group &G = sp->groups[g];
         if (sp->cfg.evaluator == 0) {
-            if (G.inflight && sp->eng) sc_eval_wait(sp->eng, G.ticket);
+            if (G.inflight && G.eng) sc_eval_wait(G.eng, G.ticket);
             cudaFreeHost(G.pos);
             cudaFreeHost(G.moves);
             cudaFreeHost(G.cnt);

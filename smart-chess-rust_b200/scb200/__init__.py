@@ -7,6 +7,8 @@ CPU box), but creating an Engine without an sm_100 device raises.
 from .binding import (  # noqa: F401
     Engine,
     SelfPlay,
+    Arena,
+    elo,
     rules_probe,
     SCError,
     SC_MODE_BF16,

@@ -22,7 +22,7 @@ DECLARED_SYMBOLS = [
     "sc_create", "sc_destroy", "sc_last_error", "sc_info", "sc_eval", "sc_eval_device", "sc_encode_only",
     "sc_move_index_only", "sc_forward_only", "sc_launch_count", "sc_last_timing", "sc_set_timing", "sc_kernel_timing",
     "sc_eval_submit", "sc_eval_wait", "sc_selfplay_create", "sc_selfplay_run", "sc_selfplay_trace_json",
-    "sc_selfplay_destroy", "sc_rules_probe",
+    "sc_selfplay_destroy", "sc_rules_probe", "sc_arena_create",
 ]
 
 
@@ -86,6 +86,7 @@ def load_library():
         L.sc_selfplay_trace_json.restype = C.c_int64
         L.sc_selfplay_trace_json.argtypes = [C.c_void_p, C.c_int64, C.c_char_p, C.c_int64]
         L.sc_selfplay_destroy.argtypes = [C.c_void_p]
+        L.sc_arena_create.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(SelfPlayConfig), C.POINTER(C.c_void_p)]
         L.sc_rules_probe.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.c_void_p,
                                      C.POINTER(C.c_int), C.POINTER(C.c_int)]
         _LIB = L
@@ -222,7 +223,7 @@ class SelfPlay:
 
     def __init__(self, engine, n_trees=2048, rollout_num=180, num_steps=150, cpuct=2.5, epsilon=0.15,
                  with_noise=True, temperature_switch=4, temperature=0.0, seed=0, n_threads=0, evaluator="engine",
-                 pipeline_groups=2, keep_traces=False):
+                 pipeline_groups=2, keep_traces=False, black_engine=None, arena=False):
         import json as _json
 
         self._json = _json
@@ -231,9 +232,14 @@ class SelfPlay:
                              temperature, seed, n_threads, 0 if evaluator == "engine" else 1, pipeline_groups,
                              int(keep_traces))
         h = C.c_void_p()
-        self._engine = engine  # keep alive
-        _check(L.sc_selfplay_create(engine.handle if engine is not None else None, C.byref(cfg), C.byref(h)),
-               "sc_selfplay_create")
+        self._engine = (engine, black_engine)  # keep alive
+        if arena:
+            _check(L.sc_arena_create(engine.handle if engine is not None else None,
+                                     black_engine.handle if black_engine is not None else None, C.byref(cfg),
+                                     C.byref(h)), "sc_arena_create")
+        else:
+            _check(L.sc_selfplay_create(engine.handle if engine is not None else None, C.byref(cfg), C.byref(h)),
+                   "sc_selfplay_create")
         self._h = h
 
     def run(self, max_games=0, max_moves=0, max_seconds=0.0):
@@ -274,3 +280,22 @@ def rules_probe(history):
                                          C.byref(term), C.byref(win)), "sc_rules_probe")
     mv = np.stack([legal["from"][: n.value], legal["to"][: n.value], legal["promo"][: n.value]], axis=1)
     return mv, pos[0], (term.value, win.value)
+
+
+class Arena(SelfPlay):
+    """`play --black-type nn` for n_trees games at once (src/play.rs:241-343): `white` moves on even plies."""
+
+    def __init__(self, white, black, n_trees=256, rollout=100, cpuct=1.5, temperature=0.0, temperature_switch=8,
+                 max_plies=200, seed=0, n_threads=0, evaluator="engine", pipeline_groups=2, keep_traces=False):
+        super().__init__(white, n_trees=n_trees, rollout_num=rollout, num_steps=max_plies, cpuct=cpuct,
+                         with_noise=False, temperature_switch=temperature_switch, temperature=temperature, seed=seed,
+                         n_threads=n_threads, evaluator=evaluator, pipeline_groups=pipeline_groups,
+                         keep_traces=keep_traces, black_engine=black, arena=True)
+
+
+def elo(total: int, wins: int, losses: int) -> float:
+    """scripts/elo.py:17-19: Elo difference from a Total/Win/Loss tally."""
+    import math
+
+    s = (wins + (total - wins - losses) / 2) / total
+    return 400 * math.log(s / (1 - s), 10)

@@ -109,3 +109,52 @@ def test_selfplay_config2_shape_smoke(co, small_net):
     assert len(openings) > 3
     sp.close()
     eng.close()
+
+
+def test_arena_two_networks(co, small_net, tmp_path):
+    """BASELINE configs[4] shape on small nets: two different networks, both colour assignments; each
+    ply's batch must come from the network of the side to move."""
+    import net
+    import scb200
+
+    sd_a, blob_a = small_net
+    sd_b = net.perturb_norm_params(net.init_state_dict(2, 11), 99)
+    blob_b = str(tmp_path / "b.scw")
+    scb200.write_blob(sd_b, blob_b)
+    ea = scb200.Engine(blob_a, 0, scb200.SC_MODE_BF16, 64)
+    eb = scb200.Engine(blob_b, 0, scb200.SC_MODE_BF16, 64)
+
+    def first_plies(white, black):
+        a = scb200.Arena(white, black, n_trees=16, rollout=20, cpuct=1.5, temperature=0.0, temperature_switch=0,
+                         max_plies=6, seed=1, keep_traces=True, n_threads=2)
+        st = a.run(max_games=16)
+        assert st["games_finished"] == 16 and st["moves"] == 16 * 6
+        trs = [a.trace(k) for k in range(16)]
+        a.close()
+        return trs
+
+    def selfplay_root(engine):
+        sp = scb200.SelfPlay(engine, n_trees=1, rollout_num=20, num_steps=1, cpuct=1.5, with_noise=False,
+                             temperature_switch=0, temperature=0.0, keep_traces=True, pipeline_groups=1)
+        sp.run(max_games=1)
+        tr = sp.trace(0)
+        sp.close()
+        return tr["steps"][0][2]
+
+    ab, ba = first_plies(ea, eb), first_plies(eb, ea)
+    root_a, root_b = selfplay_root(ea), selfplay_root(eb)
+    assert root_a != root_b
+    for tr in ab:
+        assert tr["steps"][0][2] == root_a           # White's search used network A
+    for tr in ba:
+        assert tr["steps"][0][2] == root_b           # ... and network B after the swap
+    # ply 1 is searched by the other network: same position => same stats as that network's own search
+    by_first = {}
+    for tr in ab:
+        by_first.setdefault(tr["steps"][0][0], []).append(tr["steps"][1][2])
+    for tr in first_plies(eb, eb):
+        mv = tr["steps"][0][0]
+        if mv in by_first:
+            assert tr["steps"][1][2] in by_first[mv]
+    ea.close()
+    eb.close()

@@ -163,3 +163,30 @@ def test_native_rules_probe_random_play_with_repetitions(co):
             g.push(m)
     with pytest.raises(scb200.SCError):
         scb200.rules_probe([(0, 63, 0)])
+
+
+def test_arena_rounds_hash_evaluator(co):
+    """play.rs semantics on the hash evaluator: rounds of n_trees games, outcome checked after every
+    ply, 200-ply cap, tally consistent, every trace replays legally and ends where the oracle says."""
+    import scb200
+
+    a = scb200.Arena(None, None, n_trees=6, rollout=10, cpuct=1.5, temperature=0.0, temperature_switch=8,
+                     max_plies=200, seed=2, evaluator="hash", keep_traces=True, n_threads=2)
+    st = a.run(max_games=9)
+    assert st["games_finished"] == 9
+    assert st["white_wins"] + st["black_wins"] + st["draws"] + st["unfinished"] == 9
+    for k in range(9):
+        tr = a.trace(k)
+        g = co.Game()
+        for i, (mv, q, ch) in enumerate(tr["steps"]):
+            assert g.outcome(claim_draw=True) is None        # the game would have stopped earlier
+            assert mv in g.legal_uci()
+            assert sum(c[1] for c in ch) == 9
+            g.push(mv)
+        oc = g.outcome(claim_draw=True)
+        if tr["outcome"] is None:
+            assert oc is None and len(tr["steps"]) == 200
+        else:
+            assert oc is not None and {1: "White", 0: "Black", -1: None}[oc[1]] == tr["outcome"]["winner"]
+    a.close()
+    assert abs(scb200.elo(200, 120, 60) - 107.538) < 1e-2     # scripts/elo.py

@@ -91,6 +91,69 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
         "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+// ---- cta_group::2 (CTA pair) variants -------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster addresses carry the CTA rank in bit 24; clearing it addresses the even (leader) CTA
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1,
+                                             int c2, int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
+            "r"(dst),
+        "l"(map), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            dst),
+        "l"(map), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc2_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the barrier at the same shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc2_commit_mc(uint32_t bar)
+{
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+        "h"((uint16_t)3)
+        : "memory");
+}
+// arrive on a barrier of the leader CTA (rank 0) of the pair
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+        "}" ::"r"(bar)
+        : "memory");
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -276,27 +339,35 @@ __device__ __forceinline__ void staged_gather_64B(uint8_t *stg, int lane, const 
     __syncwarp();
 }
 
-template <int BN> struct TcCfg {
-    static constexpr int B_BYTES = BN * TC_BK * 2;
+template <int BN, bool CTA2 = false> struct TcCfg {
+    // cta_group::2: the pair computes a 256-row tile; each CTA stages its own 128 rows of A and HALF of
+    // the weight rows, so a stage is 32 KB instead of 48 KB and six of them fit
+    static constexpr int STAGES = CTA2 ? 6 : TC_STAGES;
+    static constexpr int B_BYTES = (CTA2 ? BN / 2 : BN) * TC_BK * 2;
     static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
     static constexpr int SMEM_EPI = 3 * 256 * 4 /*bias,gamma,beta*/ + (4 * 256 + 2 * 256 + 2 * 128 + 2 * 256) * 4 /*SE*/ +
                                     (2 * 256 + 4 * 128) * 4 /*LN partials, FC1 partials*/ + 8 * 2048 /*store staging*/;
-    static constexpr int SMEM_BYTES = TC_STAGES * STAGE_BYTES + SMEM_EPI + 256;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SMEM_EPI + 256;
 };
 
-template <int BN, int EPI, bool A4D>
+template <int BN, int EPI, bool A4D, bool CTA2 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                const TcArgs args)
 {
-    using Cfg = TcCfg<BN>;
+    using Cfg = TcCfg<BN, CTA2>;
     constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
+    constexpr int NSTAGES = Cfg::STAGES;
+    static_assert(!CTA2 || (A4D && BN == 256 && (EPI == EPI_LN || EPI == EPI_LN_SE)), "pair mode: tower convs only");
+    const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
+    const int work0 = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int work_stride = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     // Dynamic shared memory is the only shared allocation of this kernel, so it starts at offset 0 of
     // the CTA window and is 1024-byte aligned (required by the 128B swizzle); checked below.  Deriving
     // the pointers directly from the __shared__ symbol keeps every access an LDS/STS (a pointer
     // laundered through an integer cast degrades to generic LD/ST).
     extern __shared__ __align__(1024) uint8_t smem[];
-    float *s_bias = reinterpret_cast<float *>(smem + TC_STAGES * STAGE_BYTES);
+    float *s_bias = reinterpret_cast<float *>(smem + NSTAGES * STAGE_BYTES);
     float *s_gamma = s_bias + 256;
     float *s_beta = s_gamma + 256;
     float *s_pool = s_beta + 256;   // [4 quads][256]
@@ -307,16 +378,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     float *s_hidp = s_stat + 512;   // [2 channel halves][2 boards][128]
     uint8_t *s_stage = reinterpret_cast<uint8_t *>(s_hidp + 512);  // [8 epilogue warps][32 rows][64 B]
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_stage + 8 * 2048);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TC_STAGES + 4);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * NSTAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = smem_u32(smem);
     if (smem_base & 1023u) __trap();
     const uint32_t bar_base = smem_u32(bars);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
-    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * TC_STAGES + s); };
-    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * TC_STAGES + 2 + s); };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (NSTAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * NSTAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * NSTAGES + 2 + s); };
 
     if (EPI != EPI_RAW) {
         constexpr int NV = EPI == EPI_LN73 ? C_POLICY : BN;
@@ -327,28 +398,36 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     }
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; s++) {
+        for (int s = 0; s < NSTAGES; s++) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
         for (int s = 0; s < 2; s++) {
             mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), (EPI == EPI_LN || EPI == EPI_LN_SE) ? 256 : 128);
+            mbar_init(tempty_bar(s), ((EPI == EPI_LN || EPI == EPI_LN_SE) ? 256 : 128) * (CTA2 ? 2 : 1));
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"(512u)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CTA2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"(512u)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"(512u)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (CTA2) cluster_sync_all();  // the peer's barriers are initialised before any remote arrive / complete_tx
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int nkb = args.taps * args.kchunks;
-    const int n_work = EPI == EPI_RAW ? args.n_tiles * args.n_splits : args.n_tiles;
+    const int n_work = EPI == EPI_RAW ? args.n_tiles * args.n_splits : (CTA2 ? (args.n_tiles + 1) / 2 : args.n_tiles);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -357,8 +436,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0;
             long long pc_wait_empty = 0;
-            for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
-                const int tile = EPI == EPI_RAW ? work / args.n_splits : work;
+            for (int work = work0; work < n_work; work += work_stride) {
+                const int tile = EPI == EPI_RAW ? work / args.n_splits : (CTA2 ? work * 2 + (int)cta_rank : work);
                 const int split = EPI == EPI_RAW ? work % args.n_splits : 0;
                 for (int tap = 0; tap < args.taps; tap++) {
                     const int dy = args.taps == 9 ? tap / 3 - 1 : 0;
@@ -369,16 +448,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         if (args.prof) pc_wait_empty += clock64() - t0;
                         const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
                         const uint32_t b_dst = a_dst + TC_A_BYTES;
-                        mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-                        if (A4D) {
+                        if (CTA2) {
+                            // both CTAs load into their own shared memory and complete on the LEADER's barrier,
+                            // which the leader alone arms with the bytes of both
+                            if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+                            tma2_load_4d(a_dst, &map_a, full_bar(stage), kc * TC_BK, dx, dy, tile * 2);
+                            tma2_load_2d(b_dst, &map_w, full_bar(stage), kc * TC_BK, tap * BN + (int)cta_rank * (BN / 2));
+                        } else if (A4D) {
+                            mbar_expect_tx(full_bar(stage), STAGE_BYTES);
                             tma_load_4d(a_dst, &map_a, full_bar(stage), kc * TC_BK, dx, dy, tile * 2);
                             tma_load_2d(b_dst, &map_w, full_bar(stage), kc * TC_BK, tap * BN);
                         } else {
+                            mbar_expect_tx(full_bar(stage), STAGE_BYTES);
                             const int k0 = (split * args.kchunks + kc) * TC_BK;
                             tma_load_2d(a_dst, &map_a, full_bar(stage), k0, tile * TC_BM);
                             tma_load_2d(b_dst, &map_w, full_bar(stage), k0, 0);
                         }
-                        if (++stage == TC_STAGES) {
+                        if (++stage == NSTAGES) {
                             stage = 0;
                             phase ^= 1u;
                         }
@@ -388,13 +474,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (args.prof) args.prof[blockIdx.x * 16 + 0] = pc_wait_empty;
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, BN);
+        if (lane == 0 && cta_rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(CTA2 ? 2 * TC_BM : TC_BM, BN);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
             long long pc_wait_tempty = 0, pc_wait_full = 0, pc_total = args.prof ? clock64() : 0;
-            for (int work = blockIdx.x; work < n_work; work += gridDim.x, it++) {
+            for (int work = work0; work < n_work; work += work_stride, it++) {
                 const int as = it & 1;
                 const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
                 long long t0 = args.prof ? clock64() : 0;
@@ -413,16 +499,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                     for (int k = 0; k < TC_BK / 16; k++) {
                         // +32 bytes per K=16 slice inside the 128-byte swizzle row
-                        tc_mma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
-                                    (uint32_t)((kb | k) != 0));
+                        if (CTA2)
+                            tc2_mma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                                         (uint32_t)((kb | k) != 0));
+                        else
+                            tc_mma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                                        (uint32_t)((kb | k) != 0));
                     }
-                    tc_commit(empty_bar(stage));
-                    if (++stage == TC_STAGES) {
+                    if (CTA2) tc2_commit_mc(empty_bar(stage));
+                    else tc_commit(empty_bar(stage));
+                    if (++stage == NSTAGES) {
                         stage = 0;
                         phase ^= 1u;
                     }
                 }
-                tc_commit(tfull_bar(as));
+                if (CTA2) tc2_commit_mc(tfull_bar(as));
+                else tc_commit(tfull_bar(as));
             }
             if (args.prof) {
                 args.prof[blockIdx.x * 16 + 1] = pc_wait_tempty;
@@ -439,8 +531,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         int it = 0;
         long long pe_wait = 0, pe_work = 0, pe_stats = 0, pe_pool = 0, pe_fc = 0, pe_final = 0;
         const bool prof = args.prof != nullptr && te == 0;
-        for (int work = blockIdx.x; work < n_work; work += gridDim.x, it++) {
-            const int tile = EPI == EPI_RAW ? work / args.n_splits : work;
+        for (int work = work0; work < n_work; work += work_stride, it++) {
+            const int tile = EPI == EPI_RAW ? work / args.n_splits : (CTA2 ? work * 2 + (int)cta_rank : work);
             const int split = EPI == EPI_RAW ? work % args.n_splits : 0;
             const int as = it & 1;
             const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
@@ -449,6 +541,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             long long tp1 = prof ? clock64() : 0;
             pe_wait += tp1 - tp0;
             tc_fence_after();
+            if (CTA2 && tile >= args.n_tiles) {
+                // odd tile count: the second half of the last pair computes on zero-filled boards; nothing to store
+                tc_fence_before();
+                mbar_arrive_leader(tempty_bar(as));
+                continue;
+            }
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256);
 
             if constexpr (EPI == EPI_RAW) {
@@ -698,7 +796,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 if (prof) pe_final += clock64() - tp2;
             }
             tc_fence_before();
-            mbar_arrive(tempty_bar(as));
+            if (CTA2) mbar_arrive_leader(tempty_bar(as));
+            else mbar_arrive(tempty_bar(as));
             if (prof) pe_work += clock64() - tp1;
         }
         if (prof) {
@@ -713,9 +812,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     tc_fence_before();
     __syncthreads();
+    if (CTA2) cluster_sync_all();  // neither CTA may leave while the pair's MMAs / remote arrives can touch it
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        if (CTA2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -745,6 +848,8 @@ struct ActMap {
 
 struct TcConv {
     CUtensorMap map_w;
+    CUtensorMap map_w_half;  // box {64, 128}: the half of the weight rows one CTA of a pair stages
+    bool pair_ok = false;
     int taps, k_per_tap, bn, epi;
     const float *bias, *gamma, *beta;
     const uint4 *se_w1p = nullptr, *se_w2p = nullptr;
@@ -816,10 +921,23 @@ int tc_conv_create(TcConv **out, const __nv_bfloat16 *w, int taps, int k_per_tap
         delete c;
         return rc;
     }
+    if (bn == 256 && (epi == EPI_LN || epi == EPI_LN_SE)) {
+        cuuint32_t box2[2] = {TC_BK, 128};
+        rc = encode_map(&c->map_w_half, w, 2, dims, strides, box2, "weights (pair half)");
+        if (rc != SC_OK) {
+            delete c;
+            return rc;
+        }
+        c->pair_ok = true;
+    }
     static bool attr_set = false;
     if (!attr_set) {
         SCB_CHECK((set_smem_attr<256, EPI_LN, true>()));
         SCB_CHECK((set_smem_attr<256, EPI_LN_SE, true>()));
+        SCB_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<256, EPI_LN, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      TcCfg<256, true>::SMEM_BYTES));
+        SCB_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<256, EPI_LN_SE, true, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256, true>::SMEM_BYTES));
         SCB_CHECK((set_smem_attr<LD_POLICY, EPI_LN73, true>()));
         SCB_CHECK((set_smem_attr<N_VALUE_HIDDEN, EPI_RAW, false>()));
         attr_set = true;
@@ -890,6 +1008,36 @@ int tc_conv_launch(TcConv *c, const __nv_bfloat16 *in, int rows_alloc, int n_uni
     }
     const int n_work = a4d ? a.n_tiles : a.n_tiles * a.n_splits;
     const int grid = n_work < num_sms ? n_work : num_sms;
+    // CTA-pair (cta_group::2) path for the 256-wide tower convolutions: clusters of two CTAs, each pair
+    // owns a 256-row tile (4 boards).  SCB200_CTA_PAIR=0 selects the single-CTA kernel.
+    static const bool pair_enabled = !(getenv("SCB200_CTA_PAIR") && getenv("SCB200_CTA_PAIR")[0] == '0');
+    if (pair_enabled && c->pair_ok && a.n_tiles >= 2) {
+        const int n_pairs = (a.n_tiles + 1) / 2;
+        int g2 = 2 * n_pairs;
+        if (g2 > (num_sms & ~1)) g2 = num_sms & ~1;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(g2);
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = TcCfg<256, true>::SMEM_BYTES;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (c->epi == EPI_LN)
+            SCB_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<256, EPI_LN, true, true>, *ma, c->map_w_half, a));
+        else {
+            if (!c->se_w1p || !resid) {
+                set_error("tc_conv_launch: SE epilogue without SE weights / residual");
+                return SC_E_INVAL;
+            }
+            SCB_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<256, EPI_LN_SE, true, true>, *ma, c->map_w_half, a));
+        }
+        goto launched;
+    }
     switch (c->epi) {
     case EPI_LN:
         tc_gemm_kernel<256, EPI_LN, true><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, st>>>(*ma, c->map_w, a);
@@ -912,6 +1060,7 @@ int tc_conv_launch(TcConv *c, const __nv_bfloat16 *in, int rows_alloc, int n_uni
         set_error("tc_conv_launch: bad epilogue");
         return SC_E_INVAL;
     }
+launched:
     SCB_CUDA(cudaGetLastError());
     if (want_prof) {
         // debugging aid: per-phase SM-cycle counters of this launch, averaged over CTAs (synchronous!)

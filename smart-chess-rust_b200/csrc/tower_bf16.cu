@@ -339,15 +339,17 @@ __device__ __forceinline__ void staged_gather_64B(uint8_t *stg, int lane, const 
     __syncwarp();
 }
 
-template <int BN, bool CTA2 = false> struct TcCfg {
+template <int BN, bool CTA2 = false, bool YSMEM = false> struct TcCfg {
     // cta_group::2: the pair computes a 256-row tile; each CTA stages its own 128 rows of A and HALF of
-    // the weight rows, so a stage is 32 KB instead of 48 KB and six of them fit
-    static constexpr int STAGES = CTA2 ? 6 : TC_STAGES;
+    // the weight rows, so a stage is 32 KB instead of 48 KB and six of them fit.  The SE variant spends
+    // two of those stages on a 64 KB bf16 copy of the tile's LayerNorm output (YSMEM), see the epilogue.
+    static constexpr int STAGES = CTA2 ? (YSMEM ? 4 : 6) : TC_STAGES;
+    static constexpr int Y_BYTES = YSMEM ? TC_BM * 256 * 2 : 0;
     static constexpr int B_BYTES = (CTA2 ? BN / 2 : BN) * TC_BK * 2;
     static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
     static constexpr int SMEM_EPI = 3 * 256 * 4 /*bias,gamma,beta*/ + (4 * 256 + 2 * 256 + 2 * 128 + 2 * 256) * 4 /*SE*/ +
                                     (2 * 256 + 4 * 128) * 4 /*LN partials, FC1 partials*/ + 8 * 2048 /*store staging*/;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SMEM_EPI + 256;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SMEM_EPI + Y_BYTES + 256;
 };
 
 template <int BN, int EPI, bool A4D, bool CTA2 = false>
@@ -355,7 +357,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                const TcArgs args)
 {
-    using Cfg = TcCfg<BN, CTA2>;
+    constexpr bool YSMEM = CTA2 && EPI == EPI_LN_SE;
+    using Cfg = TcCfg<BN, CTA2, YSMEM>;
     constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
     constexpr int NSTAGES = Cfg::STAGES;
     static_assert(!CTA2 || (A4D && BN == 256 && (EPI == EPI_LN || EPI == EPI_LN_SE)), "pair mode: tower convs only");
@@ -377,7 +380,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     float *s_stat = s_gate + 512;   // [2 column halves][128 rows][sum, sumsq]
     float *s_hidp = s_stat + 512;   // [2 channel halves][2 boards][128]
     uint8_t *s_stage = reinterpret_cast<uint8_t *>(s_hidp + 512);  // [8 epilogue warps][32 rows][64 B]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(s_stage + 8 * 2048);
+    uint8_t *s_y = s_stage + 8 * 2048;  // YSMEM: [128 rows][32 chunks of 16 B], chunk index XOR (row & 7)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_y + Cfg::Y_BYTES);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * NSTAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -676,8 +680,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             const int c = c0 + ch * 32 + j;
                             y[j] = (__uint_as_float(cur[j]) + s_bias[c] - mean) * rstd * s_gamma[c] + s_beta[c];
                         }
+                        if constexpr (YSMEM) {
+                            // keep LN(acc) as bf16 in shared memory: the final pass then needs neither TMEM nor
+                            // the LayerNorm arithmetic again, and the accumulator can be handed back early
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                uint32_t pw[4];
+#pragma unroll
+                                for (int i = 0; i < 4; i++) {
+                                    __nv_bfloat162 h = __floats2bfloat162_rn(y[8 * q + 2 * i], y[8 * q + 2 * i + 1]);
+                                    pw[i] = *reinterpret_cast<uint32_t *>(&h);
+                                }
+                                const int chunk = (c0 + ch * 32) / 8 + q;
+                                *reinterpret_cast<uint4 *>(s_y + row * 512 + ((chunk ^ (row & 7)) << 4)) =
+                                    make_uint4(pw[0], pw[1], pw[2], pw[3]);
+                            }
+                        }
                         s_pool[quad * 256 + c0 + ch * 32 + lane] = warp_transpose_reduce(y, lane);
                         if (ch < 3) tmem_wait_ld();
+                    }
+                    if constexpr (YSMEM) {
+                        tc_fence_before();
+                        mbar_arrive_leader(tempty_bar(as));  // the accumulator is no longer needed
                     }
                     {
                         // second half of the FC1 weights (the register file holds 10 warps at <= 168 registers,
@@ -721,7 +745,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     // consumed two barriers later
 #pragma unroll
                     for (int u = 0; u < 16; u++) w2v[u] = __ldg(args.se_w2p + u * 256 + te);
-                    {
+                    if constexpr (!YSMEM) {
                         const uint4 *xw = reinterpret_cast<const uint4 *>(args.resid + (wrow0 + (lane >> 2)) * BN + c0) + (lane & 3);
 #pragma unroll
                         for (int ch = 0; ch < 4; ch++)
@@ -757,6 +781,49 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (prof) { const long long t = clock64(); pe_fc += t - tp2; tp2 = t; }
                 }
 
+                if constexpr (YSMEM) {
+                    // ---- final pass, elementwise and fully coalesced: thread te owns 16-byte chunk te % 32 of
+                    //      rows te / 32 + 8 i; y from shared memory, x from global, out = relu(gate * y + x)
+                    const int chunk = te & 31, r0 = te >> 5;
+                    float g0[8], g1[8];
+                    {
+                        const float4 a0 = *reinterpret_cast<const float4 *>(s_gate + chunk * 8);
+                        const float4 a1 = *reinterpret_cast<const float4 *>(s_gate + chunk * 8 + 4);
+                        const float4 b0 = *reinterpret_cast<const float4 *>(s_gate + 256 + chunk * 8);
+                        const float4 b1 = *reinterpret_cast<const float4 *>(s_gate + 256 + chunk * 8 + 4);
+                        g0[0] = a0.x; g0[1] = a0.y; g0[2] = a0.z; g0[3] = a0.w; g0[4] = a1.x; g0[5] = a1.y; g0[6] = a1.z; g0[7] = a1.w;
+                        g1[0] = b0.x; g1[1] = b0.y; g1[2] = b0.z; g1[3] = b0.w; g1[4] = b1.x; g1[5] = b1.y; g1[6] = b1.z; g1[7] = b1.w;
+                    }
+                    const size_t tile_row0 = (size_t)tile * TC_BM;
+                    const uint4 *xg = reinterpret_cast<const uint4 *>(args.resid + tile_row0 * BN) + chunk;
+                    uint4 *og = reinterpret_cast<uint4 *>(static_cast<__nv_bfloat16 *>(args.out) + tile_row0 * BN) + chunk;
+#pragma unroll
+                    for (int i0 = 0; i0 < 16; i0 += 8) {
+                        uint4 xv[8];
+#pragma unroll
+                        for (int u = 0; u < 8; u++) xv[u] = xg[(size_t)(r0 + 8 * (i0 + u)) * (BN / 8)];
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            const int rr = r0 + 8 * (i0 + u);
+                            const uint4 yv = *reinterpret_cast<const uint4 *>(s_y + rr * 512 + ((chunk ^ (rr & 7)) << 4));
+                            const float *g = (i0 + u) < 8 ? g0 : g1;  // rows 0..63 are the tile's first board
+                            const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w};
+                            const uint32_t xw[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+                            uint32_t ow[4];
+#pragma unroll
+                            for (int k = 0; k < 4; k++) {
+                                const float o0 = fmaxf(fmaf(g[2 * k], __uint_as_float(yw[k] << 16), __uint_as_float(xw[k] << 16)), 0.f);
+                                const float o1 = fmaxf(fmaf(g[2 * k + 1], __uint_as_float(yw[k] & 0xffff0000u),
+                                                            __uint_as_float(xw[k] & 0xffff0000u)), 0.f);
+                                __nv_bfloat162 h = __floats2bfloat162_rn(o0, o1);
+                                ow[k] = *reinterpret_cast<uint32_t *>(&h);
+                            }
+                            og[(size_t)rr * (BN / 8)] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                        }
+                    }
+                    if (prof) pe_final += clock64() - tp2;
+                    continue;  // the accumulator was released after the pooling pass
+                }
                 // ---- final pass: y (recomputed from TMEM), [gate * y + x], ReLU, bf16 store ------
                 const float *gate = s_gate + (quad >> 1) * 256;
                 uint8_t *gout = reinterpret_cast<uint8_t *>(static_cast<__nv_bfloat16 *>(args.out) + wrow0 * BN + c0);
@@ -937,7 +1004,7 @@ int tc_conv_create(TcConv **out, const __nv_bfloat16 *w, int taps, int k_per_tap
         SCB_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<256, EPI_LN, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       TcCfg<256, true>::SMEM_BYTES));
         SCB_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<256, EPI_LN_SE, true, true>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256, true>::SMEM_BYTES));
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256, true, true>::SMEM_BYTES));
         SCB_CHECK((set_smem_attr<LD_POLICY, EPI_LN73, true>()));
         SCB_CHECK((set_smem_attr<N_VALUE_HIDDEN, EPI_RAW, false>()));
         attr_set = true;
@@ -1011,14 +1078,14 @@ int tc_conv_launch(TcConv *c, const __nv_bfloat16 *in, int rows_alloc, int n_uni
     // CTA-pair (cta_group::2) path for the 256-wide tower convolutions: clusters of two CTAs, each pair
     // owns a 256-row tile (4 boards).  SCB200_CTA_PAIR=0 selects the single-CTA kernel.
     static const bool pair_enabled = !(getenv("SCB200_CTA_PAIR") && getenv("SCB200_CTA_PAIR")[0] == '0');
-    if (pair_enabled && c->pair_ok && a.n_tiles >= 2) {
+    if (pair_enabled && c->pair_ok) {  // also for a single tile: the arithmetic must not depend on the batch size
         const int n_pairs = (a.n_tiles + 1) / 2;
         int g2 = 2 * n_pairs;
         if (g2 > (num_sms & ~1)) g2 = num_sms & ~1;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(g2);
         cfg.blockDim = dim3(TC_THREADS);
-        cfg.dynamicSmemBytes = TcCfg<256, true>::SMEM_BYTES;
+        cfg.dynamicSmemBytes = c->epi == EPI_LN_SE ? TcCfg<256, true, true>::SMEM_BYTES : TcCfg<256, true>::SMEM_BYTES;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;

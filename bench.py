@@ -373,9 +373,15 @@ def main():
         roof = None
         if conv_avg_ms and conv_avg_ms > 0 and args.mode == "bf16":
             ach = B * FLOP_PER_LEAF_CONV3 / (conv_avg_ms * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": "tc_conv_ln_kernel (3x3 256->256, bias+LN fused)",
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture in
+            # profiles/r01d_conv_full_raw.csv at this workload: 95.4 MB (conv1) and 161.0 MB (conv2 + SE +
+            # residual); one of each per residual block -> average per timed launch
+            traffic = (95.4e6 + 161.0e6) / 2 if B == 2048 else None
+            roof = {"bound": "tensor",
+                    "kernel": "tc_gemm_kernel<256, EPI_LN | EPI_LN_SE, pair> (3x3 256->256 conv, bias+LN[+SE+residual] fused)",
                     "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
-                    "peak_kind": f"bf16_tflops_sustained ({peaks['src']})", "traffic": None,
+                    "peak_kind": f"bf16_tflops_sustained ({peaks['src']})", "traffic": traffic,
+                    "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01d_summary.md)",
                     "launches_timed_per_step": conv_n, "avg_launch_ms": conv_avg_ms,
                     "flops_per_launch": B * FLOP_PER_LEAF_CONV3,
                     "whole_step_tflops": value / world * FLOP_PER_LEAF / 1e12}

@@ -105,6 +105,21 @@ int sc_encode_only(sc_engine *e, int n, const sc_position *pos, int8_t *planes_o
 int sc_move_index_only(sc_engine *e, int n, const sc_position *pos, const sc_move *moves,
                        const int32_t *move_off, int32_t *index_out);
 
+/* -------- training-data batch encoder: `chess_encode_steps` (src/lib.rs:47-128), the call
+ * py/dataset.py:47-87 makes once per trace.  The game is replayed from the start position with the
+ * native rules; for every ply i the outputs are what the reference returns for that step:
+ *   planes_out  int8 [n][8][8][112]   `history.view(...)` (identical with and without apply_mirror)
+ *   meta_out    int32 [n][7]          `step.encode_meta()`; with apply_mirror it is the ROTATED board's
+ *                                     meta (turn flipped, fullmove+1 on White's plies, castling pairs swapped)
+ *   dist_out    float [n][4672]       visit counts / (sum + 1e-5) scattered at the move indices
+ *   index_out   int32 CSR             move indices of the LEGAL moves in generation order; index_off[n+1]
+ * `played[i]` is the move made at ply i, children (CSR by child_off) are the (move, visit count) pairs of
+ * the trace row.  Like the reference (which panics) the call fails with SC_E_INVAL if the children of a
+ * ply are not exactly its legal moves or the played move is not among them. n <= max_batch. */
+int sc_encode_steps(sc_engine *e, int n, const sc_move *played, const sc_move *child_moves,
+                    const uint32_t *child_counts, const int32_t *child_off, int apply_mirror, int8_t *planes_out,
+                    int32_t *meta_out, float *dist_out, int32_t *index_out, int32_t *index_off);
+
 /* -------- tolerance gate: ChessModule.forward (py/module.py:135-154) -------------------------
  * planes float [n][112][8][8] (NCHW, what the backends feed), meta float [n][7];
  * logp_out float [n][4672] in the reference's flatten order, value_out float [n]. Host pointers. */

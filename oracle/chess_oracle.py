@@ -314,3 +314,70 @@ def random_play_positions(n: int, seed: int = 1, max_ply: int = 150):
         out.append(g.dup())
         g.push(mv[rng.randint(len(mv))])
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# `chess_encode_steps` (/root/reference/src/lib.rs:47-128), restated LITERALLY: per step the board
+# is extracted (`Board::extract`, chess.rs:356-412), optionally rotated (`Board::rotate`,
+# chess.rs:594-621), pushed to the FRONT of an 8-deep history, and the whole history is viewed with
+# `rotate = (step.turn == Black)` (`BoardHistory::view`, chess.rs:828-842) -- so with apply_mirror
+# boards may be rotated twice.  Pure Python on purpose (small cases only).
+# ----------------------------------------------------------------------------------------------
+def _extract_board(g: "Game") -> dict:
+    pm = {}
+    for sq in range(64):
+        p = g.piece_at(sq)
+        if p:
+            pm[(sq >> 3, sq & 7)] = (abs(p), 1 if p > 0 else 0)
+    _, meta, _ = g.pack()
+    return {"piece_map": pm, "turn": int(meta[0]), "fullmove": int(meta[1]), "K": (int(meta[2]), int(meta[4])),
+            "Q": (int(meta[3]), int(meta[5])), "halfmove": int(meta[6]), "rep2": g.is_repetition(2),
+            "rep3": g.is_repetition(3)}
+
+
+def _rotate_board(b: dict) -> dict:
+    return {"piece_map": {(7 - r, f): (pt, 1 - c) for (r, f), (pt, c) in b["piece_map"].items()},
+            "turn": 1 - b["turn"], "fullmove": b["fullmove"] + (1 if b["turn"] == 1 else 0),
+            "K": (b["K"][1], b["K"][0]), "Q": (b["Q"][1], b["Q"][0]), "halfmove": b["halfmove"], "rep2": b["rep2"],
+            "rep3": b["rep3"]}
+
+
+def _encode_pieces(b: dict) -> np.ndarray:
+    a = np.zeros((8, 8, 14), dtype=np.int8)
+    for (r, f), (pt, c) in b["piece_map"].items():
+        a[r, f, (pt - 1) + (0 if c == 1 else 6)] = 1
+    a[:, :, 12] = int(b["rep2"])
+    a[:, :, 13] = int(b["rep3"])
+    return a
+
+
+def encode_steps(steps, apply_mirror: bool):
+    """steps: [((from,to,promo), [((from,to,promo), count), ...]), ...] -> list of
+    (planes int8[8,8,112], meta int32[7], dist float32[4672], [legal move indices])."""
+    from collections import deque
+
+    g = Game()
+    hist = deque(maxlen=8)
+    out = []
+    for mv, children in steps:
+        legal = g.legal_moves()
+        assert {tuple(int(x) for x in m) for m in legal} == {tuple(int(x) for x in m) for m, _ in children}, "inconsistent moves"
+        assert tuple(int(x) for x in mv) in {tuple(int(x) for x in m) for m in legal}
+        b = _extract_board(g)
+        step = _rotate_board(b) if apply_mirror else b
+        ori_turn = (1 - step["turn"]) if apply_mirror else step["turn"]
+        hist.appendleft(step)
+        rot = step["turn"] == 0
+        planes = np.zeros((8, 8, 112), dtype=np.int8)
+        for i, hb in enumerate(hist):
+            planes[:, :, 14 * i:14 * i + 14] = _encode_pieces(_rotate_board(hb) if rot else hb)
+        meta = np.array([step["turn"], step["fullmove"], step["K"][0], step["Q"][0], step["K"][1], step["Q"][1],
+                         step["halfmove"]], dtype=np.int32)
+        idx = [move_index(m, ori_turn) for m in legal]
+        total = np.float32(sum(int(c) for _, c in children))
+        dist = np.zeros(4672, dtype=np.float32)
+        for m, c in children:
+            dist[move_index(m, ori_turn)] = np.float32(c) / (total + np.float32(1e-5))
+        out.append((planes, meta, dist, idx))
+        g.push(mv)
+    return out

@@ -55,6 +55,9 @@ int launch_move_index(const sc_position *d_pos, const sc_move *d_moves, const in
 // [b*SC_MAX_MOVES, +d_cnt[b]) of d_moves and d_priors)
 int launch_policy_gather(const float *logits, const sc_position *d_pos, const sc_move *d_moves,
                          const int32_t *d_off, const int32_t *d_cnt, int n, float *d_priors, cudaStream_t st);
+// visit counts -> training target: dist[b][move_index(m_k)] = cnt_k / (sum_k cnt_k + 1e-5) (src/lib.rs:104-112)
+int launch_dist_scatter(const sc_position *d_pos, const sc_move *d_moves, const uint32_t *d_counts,
+                        const int32_t *d_off, int n, float *d_dist /*[n][4672]*/, cudaStream_t st);
 int launch_policy_logp_full(const float *logits, int n, float *d_logp /*[n][4672]*/, cudaStream_t st);
 
 // ---- tower_f32.cu -------------------------------------------------------------------------

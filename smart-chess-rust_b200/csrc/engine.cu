@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "host/chess_rules.hpp"
 
 namespace scb {
 
@@ -680,6 +681,114 @@ int sc_move_index_only(sc_engine *e, int n, const sc_position *pos, const sc_mov
     e->launches += 1;
     SCB_CUDA(cudaMemcpyAsync(index_out, e->d_index, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, st));
     SCB_CUDA(cudaStreamSynchronize(st));
+    return SC_OK;
+}
+
+int sc_encode_steps(sc_engine *e, int n, const sc_move *played, const sc_move *child_moves,
+                    const uint32_t *child_counts, const int32_t *child_off, int apply_mirror, int8_t *planes_out,
+                    int32_t *meta_out, float *dist_out, int32_t *index_out, int32_t *index_off)
+{
+    if (!e || n < 0 || n > e->max_batch ||
+        (n > 0 && (!played || !child_moves || !child_counts || !child_off || !planes_out || !meta_out || !dist_out ||
+                   !index_out || !index_off))) {
+        set_error("sc_encode_steps: bad argument");
+        return SC_E_INVAL;
+    }
+    if (n == 0) return SC_OK;
+    // ---- host: replay with the native rules (the reference replays through python-chess) -------------
+    chess::Game g;
+    std::vector<sc_position> pos((size_t)n);
+    std::vector<sc_move> legal;
+    std::vector<int32_t> loff((size_t)n + 1, 0);
+    for (int i = 0; i < n; i++) {
+        chess::MoveList l;
+        g.cur.legal_moves(l);
+        const int cb = child_off[i], ce = child_off[i + 1];
+        bool ok = (ce - cb) == l.n;
+        for (int k = cb; ok && k < ce; k++) {
+            bool found = false;
+            for (int j = 0; j < l.n; j++)
+                found = found || (l.m[j].from == child_moves[k].from && l.m[j].to == child_moves[k].to &&
+                                  l.m[j].promo == child_moves[k].promo);
+            ok = found;
+        }
+        if (!ok) {
+            set_error("sc_encode_steps: inconsistent moves at ply " + std::to_string(i));
+            return SC_E_INVAL;
+        }
+        chess::Move mv{played[i].from, played[i].to, played[i].promo};
+        bool in = false;
+        for (int j = 0; j < l.n; j++) in = in || (l.m[j] == mv);
+        if (!in) {
+            set_error("sc_encode_steps: num_act table doesn't include the next move at ply " + std::to_string(i));
+            return SC_E_INVAL;
+        }
+        // the packed leaf of ply i: full history back to the start (BoardHistory of lib.rs:52, capacity 8)
+        sc_position &p = pos[i];
+        memset(&p, 0, sizeof(p));
+        int nh = std::min(SC_LOOKBACK, g.ply() + 1);
+        for (int t = 0; t < nh; t++) {
+            const chess::Position &q = g.pos_at(g.ply() - t);
+            for (int c = 0; c < 6; c++) p.slot[t][c] = q.pt[c + 1];
+            p.slot[t][6] = q.occ[chess::WHITE];
+            p.slot[t][7] = g.rep_at(g.ply() - t);
+        }
+        const chess::Position &c = g.cur;
+        p.meta[0] = c.turn;
+        p.meta[1] = c.fullmove;
+        p.meta[2] = c.has_kingside(c.turn);
+        p.meta[3] = c.has_queenside(c.turn);
+        p.meta[4] = c.has_kingside(!c.turn);
+        p.meta[5] = c.has_queenside(!c.turn);
+        p.meta[6] = c.halfmove;
+        p.n_hist = nh;
+        for (int j = 0; j < l.n; j++) legal.push_back(sc_move{l.m[j].from, l.m[j].to, l.m[j].promo, 0});
+        loff[i + 1] = (int32_t)legal.size();
+        g.push(mv);
+    }
+    const int n_child = child_off[n], n_legal = loff[n];
+    if (n_child > e->max_moves_total || n_legal > e->max_moves_total) {
+        set_error("sc_encode_steps: too many moves");
+        return SC_E_INVAL;
+    }
+    // ---- device: planes, move indices of the legal moves, scattered visit distribution ---------------
+    cudaStream_t st = e->stream;
+    SCB_CUDA(cudaSetDevice(e->device));
+    int8_t *d_planes = static_cast<int8_t *>(e->d_scratch);
+    const size_t planes_bytes = ((size_t)n * 64 * SC_N_PLANES + 255) & ~(size_t)255;
+    int32_t *d_meta = reinterpret_cast<int32_t *>(d_planes + planes_bytes);
+    float *d_dist = reinterpret_cast<float *>(d_planes + planes_bytes + (((size_t)n * SC_N_META * 4 + 255) & ~(size_t)255));
+    uint32_t *d_counts = reinterpret_cast<uint32_t *>(e->d_priors);  // reuse: same element size and capacity
+    SCB_CUDA(cudaMemcpyAsync(e->d_pos, pos.data(), sizeof(sc_position) * (size_t)n, cudaMemcpyHostToDevice, st));
+    SCB_CHECK(launch_encode_i8(e->d_pos, n, d_planes, d_meta, st));
+    SCB_CUDA(cudaMemcpyAsync(e->d_moves, legal.data(), sizeof(sc_move) * (size_t)n_legal, cudaMemcpyHostToDevice, st));
+    SCB_CUDA(cudaMemcpyAsync(e->d_off, loff.data(), sizeof(int32_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+    SCB_CHECK(launch_move_index(e->d_pos, e->d_moves, e->d_off, n, e->d_index, st));
+    SCB_CUDA(cudaMemcpyAsync(index_out, e->d_index, sizeof(int32_t) * (size_t)n_legal, cudaMemcpyDeviceToHost, st));
+    // children (trace order) -> dist
+    SCB_CUDA(cudaMemcpyAsync(e->d_moves, child_moves, sizeof(sc_move) * (size_t)n_child, cudaMemcpyHostToDevice, st));
+    SCB_CUDA(cudaMemcpyAsync(e->d_off, child_off, sizeof(int32_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+    SCB_CUDA(cudaMemcpyAsync(d_counts, child_counts, sizeof(uint32_t) * (size_t)n_child, cudaMemcpyHostToDevice, st));
+    SCB_CHECK(launch_dist_scatter(e->d_pos, e->d_moves, d_counts, e->d_off, n, d_dist, st));
+    e->launches += 3;
+    SCB_CUDA(cudaMemcpyAsync(planes_out, d_planes, (size_t)n * 64 * SC_N_PLANES, cudaMemcpyDeviceToHost, st));
+    SCB_CUDA(cudaMemcpyAsync(meta_out, d_meta, (size_t)n * SC_N_META * 4, cudaMemcpyDeviceToHost, st));
+    SCB_CUDA(cudaMemcpyAsync(dist_out, d_dist, (size_t)n * SC_N_POLICY * 4, cudaMemcpyDeviceToHost, st));
+    SCB_CUDA(cudaStreamSynchronize(st));
+    memcpy(index_off, loff.data(), sizeof(int32_t) * (size_t)(n + 1));
+    if (apply_mirror) {
+        // `board_state.to_board().rotate()` (src/chess.rs:594-621) changes the meta, not the planes
+        for (int i = 0; i < n; i++) {
+            int32_t *m = meta_out + (size_t)i * SC_N_META;
+            const int32_t t = m[0], k0 = m[2], q0 = m[3];
+            m[1] += t == 1 ? 1 : 0;
+            m[0] = !t;
+            m[2] = m[4];
+            m[3] = m[5];
+            m[4] = k0;
+            m[5] = q0;
+        }
+    }
     return SC_OK;
 }
 

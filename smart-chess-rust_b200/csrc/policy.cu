@@ -172,6 +172,46 @@ __global__ void __launch_bounds__(POL_WARPS * 32) policy_logp_full_kernel(const 
     for (int i = lane; i < SC_N_POLICY; i += 32) o[i] = (lg[(i & 63) * LD_POLICY + (i >> 6)] - mx) - lsum;
 }
 
+// training target of `chess_encode_steps` (src/lib.rs:104-112): one warp per ply
+__global__ void __launch_bounds__(POL_WARPS * 32) dist_scatter_kernel(const sc_position *__restrict__ pos,
+                                                                      const sc_move *__restrict__ moves,
+                                                                      const uint32_t *__restrict__ counts,
+                                                                      const int32_t *__restrict__ off, int n,
+                                                                      float *__restrict__ dist)
+{
+    __shared__ int8_t s_q[9], s_k[25];
+    if (threadIdx.x < 9) s_q[threadIdx.x] = c_queen_dir[threadIdx.x];
+    if (threadIdx.x >= 32 && threadIdx.x < 57) s_k[threadIdx.x - 32] = c_knight_type[threadIdx.x - 32];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * POL_WARPS + warp;
+    if (b >= n) return;
+    float4 *o4 = reinterpret_cast<float4 *>(dist + (size_t)b * SC_N_POLICY);
+    for (int i = lane; i < SC_N_POLICY / 4; i += 32) o4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int beg = off[b], end = off[b + 1];
+    uint32_t sum = 0;
+    for (int k = beg + lane; k < end; k += 32) sum += counts[k];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float denom = (float)sum + 1e-5f;
+    const int turn = pos[b].meta[0];
+    __syncwarp();
+    for (int k = beg + lane; k < end; k += 32) {
+        int idx = move_index_dev(moves[k], turn, s_q, s_k);
+        if (idx >= 0) dist[(size_t)b * SC_N_POLICY + idx] = __fdiv_rn((float)counts[k], denom);
+    }
+}
+
+int launch_dist_scatter(const sc_position *d_pos, const sc_move *d_moves, const uint32_t *d_counts,
+                        const int32_t *d_off, int n, float *d_dist, cudaStream_t st)
+{
+    if (n <= 0) return SC_OK;
+    dist_scatter_kernel<<<(n + POL_WARPS - 1) / POL_WARPS, POL_WARPS * 32, 0, st>>>(d_pos, d_moves, d_counts, d_off, n,
+                                                                                     d_dist);
+    SCB_CUDA(cudaGetLastError());
+    return SC_OK;
+}
+
 int launch_move_index(const sc_position *d_pos, const sc_move *d_moves, const int32_t *d_off, int n,
                       int32_t *d_index, cudaStream_t st)
 {

@@ -22,7 +22,7 @@ DECLARED_SYMBOLS = [
     "sc_create", "sc_destroy", "sc_last_error", "sc_info", "sc_eval", "sc_eval_device", "sc_encode_only",
     "sc_move_index_only", "sc_forward_only", "sc_launch_count", "sc_last_timing", "sc_set_timing", "sc_kernel_timing",
     "sc_eval_submit", "sc_eval_wait", "sc_selfplay_create", "sc_selfplay_run", "sc_selfplay_trace_json",
-    "sc_selfplay_destroy", "sc_rules_probe", "sc_arena_create",
+    "sc_selfplay_destroy", "sc_rules_probe", "sc_arena_create", "sc_encode_steps",
 ]
 
 
@@ -74,6 +74,7 @@ def load_library():
         L.sc_encode_only.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.sc_move_index_only.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.sc_forward_only.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sc_encode_steps.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 5
         L.sc_launch_count.restype = C.c_int64
         L.sc_launch_count.argtypes = [C.c_void_p]
         L.sc_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
@@ -198,6 +199,32 @@ class Engine:
         _check(load_library().sc_forward_only(self._h, n, _ptr(planes), _ptr(meta), _ptr(logp), _ptr(value)),
                "sc_forward_only")
         return logp, value
+
+    def encode_steps(self, steps, apply_mirror: bool = False):
+        """`libsmartchess.chess_encode_steps(steps, apply_mirror)` (src/lib.rs:47-128): steps is the list
+        [((from, to, promo), [((from, to, promo), visit_count), ...]), ...] a trace yields (py/dataset.py:70-77).
+        Returns a list of (planes int8[8,8,112], meta int32[7], dist float32[4672], [move indices])."""
+        n = len(steps)
+        played = np.zeros(n, dtype=MOVE_DTYPE)
+        off = np.zeros(n + 1, dtype=np.int32)
+        cm, cc = [], []
+        for i, (mv, children) in enumerate(steps):
+            played[i] = (int(mv[0]), int(mv[1]), int(mv[2]), 0)
+            for m, c in children:
+                cm.append((int(m[0]), int(m[1]), int(m[2]), 0))
+                cc.append(int(c))
+            off[i + 1] = len(cm)
+        cm = np.array(cm, dtype=MOVE_DTYPE) if cm else np.zeros(1, dtype=MOVE_DTYPE)
+        cc = np.array(cc, dtype=np.uint32) if cc else np.zeros(1, dtype=np.uint32)
+        planes = np.zeros((n, 8, 8, SC_N_PLANES), dtype=np.int8)
+        meta = np.zeros((n, SC_N_META), dtype=np.int32)
+        dist = np.zeros((n, SC_N_POLICY), dtype=np.float32)
+        index = np.zeros(max(1, n * 256), dtype=np.int32)
+        ioff = np.zeros(n + 1, dtype=np.int32)
+        _check(load_library().sc_encode_steps(self._h, n, _ptr(played), _ptr(cm), _ptr(cc), _ptr(off), int(apply_mirror),
+                                              _ptr(planes), _ptr(meta), _ptr(dist), _ptr(index), _ptr(ioff)),
+               "sc_encode_steps")
+        return [(planes[i], meta[i], dist[i], index[ioff[i]:ioff[i + 1]].tolist()) for i in range(n)]
 
     def launch_count(self) -> int:
         return int(load_library().sc_launch_count(self._h))

@@ -309,3 +309,28 @@ def test_full_size_properties(co, nets):
         assert val[0] == val[2] and np.array_equal(pri[o3[0]:o3[1]], pri[o3[2]:o3[3]])
     finally:
         e.close()
+
+
+def test_encode_steps_matches_reference_restatement(co, eng_f32_small):
+    """Training-data batch encoder vs the literal restatement of `chess_encode_steps` on a real trace
+    produced by the self-play driver (hash evaluator), with and without apply_mirror."""
+    import scb200
+
+    sp = scb200.SelfPlay(None, n_trees=2, rollout_num=24, num_steps=60, cpuct=2.5, with_noise=True,
+                         temperature_switch=10, evaluator="hash", keep_traces=True, seed=4)
+    sp.run(max_games=2)
+    for k in range(2):
+        tr = sp.trace(k)
+        steps = [(co.parse_uci(s[0]), [(co.parse_uci(c[0]), c[1]) for c in s[2]]) for s in tr["steps"]]
+        for mirror in (False, True):
+            got = eng_f32_small.encode_steps(steps, mirror)
+            ref = co.encode_steps(steps, mirror)
+            assert len(got) == len(ref) == len(steps)
+            for (p, m, d, i), (rp, rm, rd, ri) in zip(got, ref):
+                assert np.array_equal(p, rp) and np.array_equal(m, rm)
+                assert i == ri
+                assert np.array_equal(d, rd)          # same f32 division, bit-exact
+    sp.close()
+    bad = [((12, 28, 0), [((12, 28, 0), 3)])]          # children are not the full legal-move set
+    with pytest.raises(scb200.SCError):
+        eng_f32_small.encode_steps(bad, False)

@@ -232,3 +232,28 @@ def test_sequential_search_invariants(co):
     t2 = co.Tree()
     t2.search(40, 2.5)
     assert (t2.root_children()[1] == before).all()
+
+
+def test_encode_steps_literal_restatement(co):
+    """`chess_encode_steps` restated literally (double rotation under apply_mirror): its planes equal
+    `_encode`'s with and without the mirror; only the meta differs (rotated board's meta)."""
+    g = co.Game()
+    steps = []
+    rng = np.random.RandomState(3)
+    for _ in range(30):
+        mv = g.legal_moves()
+        m = mv[rng.randint(len(mv))]
+        steps.append((tuple(int(x) for x in m), [(tuple(int(x) for x in c), int(rng.randint(0, 9))) for c in mv]))
+        g.push(m)
+    plain = co.encode_steps(steps, False)
+    mirr = co.encode_steps(steps, True)
+    g = co.Game()
+    for (mv, _), (p0, m0, d0, i0), (p1, m1, d1, i1) in zip(steps, plain, mirr):
+        planes, meta = g.encode()
+        assert np.array_equal(p0, planes) and np.array_equal(m0, meta)
+        assert np.array_equal(p1, planes) and i0 == i1 and np.array_equal(d0, d1)
+        assert m1[0] == 1 - meta[0] and m1[1] == meta[1] + (1 if meta[0] == 1 else 0)
+        assert list(m1[2:6]) == [meta[4], meta[5], meta[2], meta[3]] and m1[6] == meta[6]
+        assert i0 == [int(x) for x in g.move_indices()]
+        assert abs(d0.sum() - 1.0) < 1e-4 or d0.sum() == 0
+        g.push(mv)

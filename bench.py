@@ -316,11 +316,12 @@ def main():
             ev1.synchronize()
             step_ms.append(ev0.elapsed_time(ev1))
             a, n = eng.kernel_timing()
-            conv_ms.append(a)
+            conv_ms.append(a * n)   # device time of all timed tower-convolution launches of this step
             conv_n = n
         barrier()
         t_wall = time.perf_counter() - t_wall0
         launches = eng.launch_count() - launches0
+        eng_timed_flops = eng.timed_flops_per_leaf()
         clocks = sampler.stop()
         eng.set_timing(0)
     total_ms = float(sum(step_ms))
@@ -369,21 +370,26 @@ def main():
 
     if rank == 0:
         peaks = _peaks()
-        conv_avg_ms = float(np.mean(conv_ms)) if conv_ms else None
+        conv_tot_ms = float(np.mean(conv_ms)) if conv_ms else None
+        conv_avg_ms = conv_tot_ms / conv_n if conv_tot_ms and conv_n else None
+        timed_flops = eng_timed_flops
         roof = None
         if conv_avg_ms and conv_avg_ms > 0 and args.mode == "bf16":
-            ach = B * FLOP_PER_LEAF_CONV3 / (conv_avg_ms * 1e-3) / 1e12
+            ach = B * timed_flops / (conv_tot_ms * 1e-3) / 1e12
             # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture in
             # profiles/r01d_conv_full_raw.csv at this workload: 95.4 MB (conv1) and 161.0 MB (conv2 + SE +
             # residual); one of each per residual block -> average per timed launch
-            traffic = (95.4e6 + 161.0e6) / 2 if B == 2048 else None
+            # one launch of each per residual block; the whole-tower launch contains all of them
+            traffic = ((95.4e6 + 161.0e6) / 2 if conv_n > 1 else 19 * (95.4e6 + 161.0e6)) if B == 2048 else None
             roof = {"bound": "tensor",
-                    "kernel": "tc_gemm_kernel<256, EPI_LN | EPI_LN_SE, pair> (3x3 256->256 conv, bias+LN[+SE+residual] fused)",
+                    "kernel": ("tc_gemm_kernel<256, pair, TOWER>: stem + 19 x (conv3x3+LN+ReLU, conv3x3+LN+SE+residual+ReLU) in one launch"
+                               if conv_n == 1 else
+                               "tc_gemm_kernel<256, EPI_LN | EPI_LN_SE, pair> (3x3 256->256 conv, bias+LN[+SE+residual] fused)"),
                     "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
                     "peak_kind": f"bf16_tflops_sustained ({peaks['src']})", "traffic": traffic,
                     "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01d_summary.md)",
                     "launches_timed_per_step": conv_n, "avg_launch_ms": conv_avg_ms,
-                    "flops_per_launch": B * FLOP_PER_LEAF_CONV3,
+                    "flops_per_launch": B * timed_flops / conv_n,
                     "whole_step_tflops": value / world * FLOP_PER_LEAF / 1e12}
         cpu = None
         if world == 1 and args.cpu_budget > 0:

@@ -135,9 +135,12 @@ int sc_last_timing(sc_engine *e, float *tower_ms, float *total_ms);
 /* per-call event timing: 0 off, 1 = tower/total of a call (two event records + one sync per
  * call), 2 = additionally one event pair around every 3x3 tower convolution launch */
 int sc_set_timing(sc_engine *e, int enabled);
-/* level 2: average device time (ms) of the 3x3 256->256 tower convolution launches of the
- * most recent call and how many there were (the roofline kernel of bench.py) */
+/* level 2: average device time (ms) of the timed tower-convolution launches of the most recent call and
+ * how many there were (the roofline kernel of bench.py): one launch of the whole-tower kernel, or the 38
+ * per-layer 3x3 256->256 launches with SCB200_TOWER=0; sc_timed_flops_per_leaf = algorithmic FLOPs per
+ * leaf those launches cover together */
 int sc_kernel_timing(sc_engine *e, float *conv3x3_avg_ms, int *n_launches);
+double sc_timed_flops_per_leaf(const sc_engine *e);
 
 /* ===================== batched self-play driver (host side, C++) ================================
  * Replaces the single-tree loop of the `selfplay` binary (src/main.rs:153-238) and `mcts::mcts` /

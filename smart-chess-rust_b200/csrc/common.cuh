@@ -86,4 +86,17 @@ void tc_conv_destroy(TcConv *c);
 int tc_conv_launch(TcConv *c, const __nv_bfloat16 *in, int rows_alloc, int n_units, void *out,
                    const __nv_bfloat16 *resid, int relu, int n_splits, int num_sms, cudaStream_t st);
 
+// whole-tower kernel: every 256-wide convolution of the residual tower in ONE launch (layers in order)
+struct TcTower;
+struct TcTowerLayerDesc {
+    TcConv *conv;
+    const __nv_bfloat16 *in;     // bf16 NHWC [boards_alloc][64][conv k_per_tap]
+    void *out;                   // bf16 NHWC [boards_alloc][64][256]
+    const __nv_bfloat16 *resid;  // SE layers: block input (may alias out)
+    int relu;
+};
+int tc_tower_create(TcTower **out, const TcTowerLayerDesc *descs, int n, int boards_alloc);
+int tc_tower_launch(TcTower *t, int n_boards, int num_sms, cudaStream_t st);
+void tc_tower_destroy(TcTower *t);
+
 }  // namespace scb

@@ -5,6 +5,7 @@
 // policy/value network, move-index gather + renormalisation, D2H of priors and values.
 // There is no CPU fallback: without an sm_100 device sc_create() fails with SC_E_NOGPU.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -118,6 +119,8 @@ struct sc_engine {
     ConvW pol1, pol2, val1;
     float *vfc_w_f32 = nullptr;           // fp32 mode: [16384][128]
     TcConv *vfc_tc = nullptr;             // bf16 mode: value FC as a split-K tcgen05 GEMM
+    TcTower *tower = nullptr;             // bf16 mode: stem + all residual blocks in one launch
+    double timed_flops_per_leaf = 0.0;    // FLOPs per leaf covered by the level-2 timed launches
     float *v_wmeta = nullptr, *v_b1 = nullptr, *v_w2 = nullptr, *v_b2 = nullptr;
     // io
     sc_position *d_pos = nullptr;
@@ -410,17 +413,34 @@ static int run_network(sc_engine *e, int n, cudaStream_t st)
         e->launches += 3;
     } else {
         const int nb = e->alloc_boards;
-        SCB_CHECK(tc_conv_launch(e->stem.tc, e->h_planes, nb, n, e->h_x, nullptr, 1, 1, e->num_sms, st));
-        e->launches += 1;
-        for (int i = 0; i < e->n_blocks; i++) {
+        static const bool tower_enabled = !(getenv("SCB200_TOWER") && getenv("SCB200_TOWER")[0] == '0');
+        int trc = SC_E_STATE;
+        if (tower_enabled && e->tower) {
             SCB_CHECK(kev_mark(e, st));
-            SCB_CHECK(tc_conv_launch(e->conv1[i].tc, e->h_x, nb, n, e->h_t, nullptr, 1, 1, e->num_sms, st));
-            SCB_CHECK(kev_mark(e, st));
-            SCB_CHECK(kev_mark(e, st));
-            // conv2 + LN + squeeze-excitation + residual + ReLU, in place on the block input x
-            SCB_CHECK(tc_conv_launch(e->conv2[i].tc, e->h_t, nb, n, e->h_x, e->h_x, 0, 1, e->num_sms, st));
-            SCB_CHECK(kev_mark(e, st));
-            e->launches += 2;
+            trc = tc_tower_launch(e->tower, n, e->num_sms, st);
+            if (trc == SC_OK) {
+                SCB_CHECK(kev_mark(e, st));
+                e->launches += 1;
+                e->timed_flops_per_leaf = 2.0 * 64 * 256 * (9.0 * C_IN + e->n_blocks * (2 * 9.0 * 256 + 2.0 * C_SE / 64));
+            } else if (trc != SC_E_STATE)
+                return trc;
+            else
+                e->kev_used = 0;
+        }
+        if (trc != SC_OK) {
+            SCB_CHECK(tc_conv_launch(e->stem.tc, e->h_planes, nb, n, e->h_x, nullptr, 1, 1, e->num_sms, st));
+            e->launches += 1;
+            for (int i = 0; i < e->n_blocks; i++) {
+                SCB_CHECK(kev_mark(e, st));
+                SCB_CHECK(tc_conv_launch(e->conv1[i].tc, e->h_x, nb, n, e->h_t, nullptr, 1, 1, e->num_sms, st));
+                SCB_CHECK(kev_mark(e, st));
+                SCB_CHECK(kev_mark(e, st));
+                // conv2 + LN + squeeze-excitation + residual + ReLU, in place on the block input x
+                SCB_CHECK(tc_conv_launch(e->conv2[i].tc, e->h_t, nb, n, e->h_x, e->h_x, 0, 1, e->num_sms, st));
+                SCB_CHECK(kev_mark(e, st));
+                e->launches += 2;
+            }
+            e->timed_flops_per_leaf = 2.0 * 64 * 256 * 9.0 * 256 * 2 * e->n_blocks;
         }
         if (e->timing) SCB_CUDA(cudaEventRecord(e->ev[2], st));
         SCB_CHECK(tc_conv_launch(e->pol1.tc, e->h_x, nb, n, e->h_t, nullptr, 0, 1, e->num_sms, st));
@@ -502,6 +522,15 @@ int sc_create(const char *weights_blob_path, int device, int mode, int max_batch
         if (rc) break;
         if ((rc = load_weights(e, blob)) != SC_OK) break;
         if ((rc = alloc_buffers(e)) != SC_OK) break;
+        if (mode == SC_MODE_BF16) {
+            std::vector<TcTowerLayerDesc> d;
+            d.push_back(TcTowerLayerDesc{e->stem.tc, e->h_planes, e->h_x, nullptr, 1});
+            for (int i = 0; i < e->n_blocks; i++) {
+                d.push_back(TcTowerLayerDesc{e->conv1[i].tc, e->h_x, e->h_t, nullptr, 1});
+                d.push_back(TcTowerLayerDesc{e->conv2[i].tc, e->h_t, e->h_x, e->h_x, 0});
+            }
+            if ((rc = tc_tower_create(&e->tower, d.data(), (int)d.size(), e->alloc_boards)) != SC_OK) break;
+        }
         if (cudaDeviceSynchronize() != cudaSuccess) { rc = SC_E_CUDA; set_error("sync after weight upload failed"); break; }
     } while (0);
     if (rc != SC_OK) {
@@ -520,6 +549,7 @@ int sc_destroy(sc_engine *e)
     auto kill = [](ConvW &c) { if (c.tc) tc_conv_destroy(c.tc); c.tc = nullptr; };
     kill(e->stem); kill(e->pol1); kill(e->pol2); kill(e->val1);
     if (e->vfc_tc) tc_conv_destroy(e->vfc_tc);
+    if (e->tower) tc_tower_destroy(e->tower);
     for (auto &c : e->conv1) kill(c);
     for (auto &c : e->conv2) kill(c);
     for (void *p : e->allocs) cudaFree(p);
@@ -831,6 +861,8 @@ int sc_set_timing(sc_engine *e, int enabled)
     e->timing = enabled < 0 ? 0 : (enabled > 2 ? 2 : enabled);
     return SC_OK;
 }
+
+double sc_timed_flops_per_leaf(const sc_engine *e) { return e ? e->timed_flops_per_leaf : 0.0; }
 
 int sc_kernel_timing(sc_engine *e, float *conv3x3_avg_ms, int *n_launches)
 {

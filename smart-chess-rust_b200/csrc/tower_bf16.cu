@@ -23,6 +23,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -219,6 +220,18 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N)
 //   EPI_RAW    split-K partial sums of the value FC               -> fp32 [split][M][128]
 enum { EPI_LN = 0, EPI_LN_SE = 1, EPI_LN73 = 2, EPI_RAW = 3 };
 
+// One convolution layer of the whole-tower kernel (device array, written once at engine creation)
+struct alignas(64) TowerLayer {
+    CUtensorMap map_a;                   // activations of the layer's input buffer (4-D, box of two boards)
+    CUtensorMap map_w;                   // this layer's weights, box {64, 128} (one CTA's half)
+    void *out;
+    const __nv_bfloat16 *resid;
+    const float *bias, *gamma, *beta;
+    const uint4 *se_w1p, *se_w2p;
+    const float *se_b1, *se_b2;
+    int taps, kchunks, relu, se;
+};
+
 struct TcArgs {
     void *out;
     const __nv_bfloat16 *resid;          // EPI_LN_SE: block input x (may alias out)
@@ -231,6 +244,8 @@ struct TcArgs {
     int n_splits;                        // EPI_RAW: work items = n_tiles * n_splits
     int m_rows;                          // EPI_RAW: valid rows
     long long *prof;                     // optional [grid][16] phase cycle counters (SCB200_PHASE_PROFILE=1)
+    const TowerLayer *layers;            // TOWER: all conv layers of the residual tower, run back to back
+    int n_layers;
 };
 
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32])
@@ -349,14 +364,21 @@ template <int BN, bool CTA2 = false, bool YSMEM = false> struct TcCfg {
     static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
     static constexpr int SMEM_EPI = 3 * 256 * 4 /*bias,gamma,beta*/ + (4 * 256 + 2 * 256 + 2 * 128 + 2 * 256) * 4 /*SE*/ +
                                     (2 * 256 + 4 * 128) * 4 /*LN partials, FC1 partials*/ + 8 * 2048 /*store staging*/;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SMEM_EPI + Y_BYTES + 256;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SMEM_EPI + Y_BYTES + 768;
 };
 
-template <int BN, int EPI, bool A4D, bool CTA2 = false>
+constexpr int TC_MAX_SLOTS = 32;  // TOWER: tiles per CTA whose layer-to-layer hand-over is tracked
+
+template <int BN, int EPI, bool A4D, bool CTA2 = false, bool TOWER = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                const TcArgs args)
 {
+    // TOWER: one launch runs every convolution of the residual tower.  Boards never interact inside the
+    // tower, so layer l+1 of a tile depends only on layer l of the SAME tile, which the same CTA
+    // produced: the hand-over is a per-tile mbarrier inside the CTA, there is no grid-wide barrier, no
+    // per-layer launch gap and no per-layer tail.
+    static_assert(!TOWER || (CTA2 && EPI == EPI_LN_SE), "tower kernel = pair mode with both epilogues compiled in");
     constexpr bool YSMEM = CTA2 && EPI == EPI_LN_SE;
     using Cfg = TcCfg<BN, CTA2, YSMEM>;
     constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
@@ -382,7 +404,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint8_t *s_stage = reinterpret_cast<uint8_t *>(s_hidp + 512);  // [8 epilogue warps][32 rows][64 B]
     uint8_t *s_y = s_stage + 8 * 2048;  // YSMEM: [128 rows][32 chunks of 16 B], chunk index XOR (row & 7)
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_y + Cfg::Y_BYTES);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * NSTAGES + 4);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * NSTAGES + 4 + TC_MAX_SLOTS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = smem_u32(smem);
@@ -392,8 +414,31 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     auto empty_bar = [&](int s) { return bar_base + 8u * (NSTAGES + s); };
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * NSTAGES + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * NSTAGES + 2 + s); };
+    auto ready_bar = [&](int s) { return bar_base + 8u * (2 * NSTAGES + 4 + s); };  // TOWER: tile s written by layer l
 
-    if (EPI != EPI_RAW) {
+    struct LayerView {
+        const CUtensorMap *ma, *mw;
+        void *out;
+        const __nv_bfloat16 *resid;
+        const float *bias, *gamma, *beta;
+        const uint4 *w1p, *w2p;
+        const float *b1, *b2;
+        int taps, kchunks, relu;
+        bool se;
+    };
+    auto layer_view = [&](int l) -> LayerView {
+        if constexpr (TOWER) {
+            const TowerLayer &T = args.layers[l];
+            return LayerView{&T.map_a, &T.map_w, T.out, T.resid, T.bias, T.gamma, T.beta, T.se_w1p, T.se_w2p, T.se_b1, T.se_b2,
+                             T.taps, T.kchunks, T.relu, T.se != 0};
+        } else {
+            return LayerView{&map_a, &map_w, args.out, args.resid, args.bias, args.gamma, args.beta, args.se_w1p, args.se_w2p,
+                             args.se_b1, args.se_b2, args.taps, args.kchunks, args.relu, EPI == EPI_LN_SE};
+        }
+    };
+    const int n_layers = TOWER ? args.n_layers : 1;
+
+    if (EPI != EPI_RAW && !TOWER) {
         constexpr int NV = EPI == EPI_LN73 ? C_POLICY : BN;
         for (int i = threadIdx.x; i < 256; i += TC_THREADS) {
             s_bias[i] = i < NV ? args.bias[i] : 0.f;
@@ -406,6 +451,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
+        if (TOWER)
+            for (int s = 0; s < TC_MAX_SLOTS; s++) mbar_init(ready_bar(s), 256);
         for (int s = 0; s < 2; s++) {
             mbar_init(tfull_bar(s), 1);
             mbar_init(tempty_bar(s), ((EPI == EPI_LN || EPI == EPI_LN_SE) ? 256 : 128) * (CTA2 ? 2 : 1));
@@ -430,7 +477,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (CTA2) cluster_sync_all();  // the peer's barriers are initialised before any remote arrive / complete_tx
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int nkb = args.taps * args.kchunks;
     const int n_work = EPI == EPI_RAW ? args.n_tiles * args.n_splits : (CTA2 ? (args.n_tiles + 1) / 2 : args.n_tiles);
 
     if (warp == 0) {
@@ -440,13 +486,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0;
             long long pc_wait_empty = 0;
-            for (int work = work0; work < n_work; work += work_stride) {
+            for (int layer = 0; layer < n_layers; layer++) {
+            const LayerView P = layer_view(layer);
+            int slot = 0;
+            for (int work = work0; work < n_work; work += work_stride, slot++) {
+                if (TOWER && layer > 0) mbar_wait(ready_bar(slot), (uint32_t)(layer - 1) & 1u);  // this tile's input is written
                 const int tile = EPI == EPI_RAW ? work / args.n_splits : (CTA2 ? work * 2 + (int)cta_rank : work);
                 const int split = EPI == EPI_RAW ? work % args.n_splits : 0;
-                for (int tap = 0; tap < args.taps; tap++) {
-                    const int dy = args.taps == 9 ? tap / 3 - 1 : 0;
-                    const int dx = args.taps == 9 ? tap % 3 - 1 : 0;
-                    for (int kc = 0; kc < args.kchunks; kc++) {
+                for (int tap = 0; tap < P.taps; tap++) {
+                    const int dy = P.taps == 9 ? tap / 3 - 1 : 0;
+                    const int dx = P.taps == 9 ? tap % 3 - 1 : 0;
+                    for (int kc = 0; kc < P.kchunks; kc++) {
                         const long long t0 = args.prof ? clock64() : 0;
                         mbar_wait(empty_bar(stage), phase ^ 1u);
                         if (args.prof) pc_wait_empty += clock64() - t0;
@@ -456,15 +506,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             // both CTAs load into their own shared memory and complete on the LEADER's barrier,
                             // which the leader alone arms with the bytes of both
                             if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
-                            tma2_load_4d(a_dst, &map_a, full_bar(stage), kc * TC_BK, dx, dy, tile * 2);
-                            tma2_load_2d(b_dst, &map_w, full_bar(stage), kc * TC_BK, tap * BN + (int)cta_rank * (BN / 2));
+                            tma2_load_4d(a_dst, P.ma, full_bar(stage), kc * TC_BK, dx, dy, tile * 2);
+                            tma2_load_2d(b_dst, P.mw, full_bar(stage), kc * TC_BK, tap * BN + (int)cta_rank * (BN / 2));
                         } else if (A4D) {
                             mbar_expect_tx(full_bar(stage), STAGE_BYTES);
                             tma_load_4d(a_dst, &map_a, full_bar(stage), kc * TC_BK, dx, dy, tile * 2);
                             tma_load_2d(b_dst, &map_w, full_bar(stage), kc * TC_BK, tap * BN);
                         } else {
                             mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-                            const int k0 = (split * args.kchunks + kc) * TC_BK;
+                            const int k0 = (split * P.kchunks + kc) * TC_BK;
                             tma_load_2d(a_dst, &map_a, full_bar(stage), k0, tile * TC_BM);
                             tma_load_2d(b_dst, &map_w, full_bar(stage), k0, 0);
                         }
@@ -475,6 +525,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                 }
             }
+            }
             if (args.prof) args.prof[blockIdx.x * 16 + 0] = pc_wait_empty;
         }
     } else if (warp == 1) {
@@ -484,6 +535,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             uint32_t phase = 0;
             int it = 0;
             long long pc_wait_tempty = 0, pc_wait_full = 0, pc_total = args.prof ? clock64() : 0;
+            for (int layer = 0; layer < n_layers; layer++) {
+            const LayerView P = layer_view(layer);
+            const int nkb = P.taps * P.kchunks;
             for (int work = work0; work < n_work; work += work_stride, it++) {
                 const int as = it & 1;
                 const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
@@ -520,6 +574,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 if (CTA2) tc2_commit_mc(tfull_bar(as));
                 else tc_commit(tfull_bar(as));
             }
+            }
             if (args.prof) {
                 args.prof[blockIdx.x * 16 + 1] = pc_wait_tempty;
                 args.prof[blockIdx.x * 16 + 2] = pc_wait_full;
@@ -535,7 +590,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         int it = 0;
         long long pe_wait = 0, pe_work = 0, pe_stats = 0, pe_pool = 0, pe_fc = 0, pe_final = 0;
         const bool prof = args.prof != nullptr && te == 0;
-        for (int work = work0; work < n_work; work += work_stride, it++) {
+        for (int layer = 0; layer < n_layers; layer++) {
+        const LayerView P = layer_view(layer);
+        const bool is_se = P.se;
+        if constexpr (TOWER) {
+            // this layer's bias / LayerNorm parameters replace the previous layer's in shared memory
+            epi_bar_sync();
+            s_bias[te] = P.bias[te];
+            s_gamma[te] = P.gamma[te];
+            s_beta[te] = P.beta[te];
+            epi_bar_sync();
+        }
+        int slot = 0;
+        // end of a tile in the tower kernel: the tile's output (generic-proxy stores) is handed to the TMA
+        // loads (async proxy) of the next layer through a per-tile mbarrier
+        auto tile_done = [&](int sl) {
+            if constexpr (TOWER) {
+                asm volatile("fence.proxy.async;" ::: "memory");
+                mbar_arrive(ready_bar(sl));
+            }
+        };
+        for (int work = work0; work < n_work; work += work_stride, it++, slot++) {
             const int tile = EPI == EPI_RAW ? work / args.n_splits : (CTA2 ? work * 2 + (int)cta_rank : work);
             const int split = EPI == EPI_RAW ? work % args.n_splits : 0;
             const int as = it & 1;
@@ -549,6 +624,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 // odd tile count: the second half of the last pair computes on zero-filled boards; nothing to store
                 tc_fence_before();
                 mbar_arrive_leader(tempty_bar(as));
+                tile_done(slot);
                 continue;
             }
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256);
@@ -660,12 +736,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 // FC1 weights do not depend on anything computed here: request them before the pooling pass
                 // so their L2 latency is hidden (thread = (hidden unit j, channel half hc))
                 uint4 w1v[16];
-                if constexpr (EPI == EPI_LN_SE) {
+                if (is_se) {
                     const int j = te & 127, hc = te >> 7;
 #pragma unroll
-                    for (int u = 0; u < 8; u++) w1v[u] = __ldg(args.se_w1p + (hc * 16 + u) * 128 + j);
+                    for (int u = 0; u < 8; u++) w1v[u] = __ldg(P.w1p + (hc * 16 + u) * 128 + j);
                 }
-                if constexpr (EPI == EPI_LN_SE) {
+                if (is_se) {
                     // ---- squeeze: per-board channel means of y = LN(conv) (fp32) -------------------
                     uint32_t rn[32];
                     tmem_ld32(tcol, r);
@@ -708,7 +784,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         // so only half of them could be requested before the pooling pass)
                         const int j = te & 127, hc = te >> 7;
 #pragma unroll
-                        for (int u = 8; u < 16; u++) w1v[u] = __ldg(args.se_w1p + (hc * 16 + u) * 128 + j);
+                        for (int u = 8; u < 16; u++) w1v[u] = __ldg(P.w1p + (hc * 16 + u) * 128 + j);
                     }
                     epi_bar_sync();
                     if (prof) { const long long t = clock64(); pe_pool += t - tp2; tp2 = t; }
@@ -744,9 +820,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     // FC2 weights (thread = channel te) and the residual rows are requested now; both are
                     // consumed two barriers later
 #pragma unroll
-                    for (int u = 0; u < 16; u++) w2v[u] = __ldg(args.se_w2p + u * 256 + te);
+                    for (int u = 0; u < 16; u++) w2v[u] = __ldg(P.w2p + u * 256 + te);
                     if constexpr (!YSMEM) {
-                        const uint4 *xw = reinterpret_cast<const uint4 *>(args.resid + (wrow0 + (lane >> 2)) * BN + c0) + (lane & 3);
+                        const uint4 *xw = reinterpret_cast<const uint4 *>(P.resid + (wrow0 + (lane >> 2)) * BN + c0) + (lane & 3);
 #pragma unroll
                         for (int ch = 0; ch < 4; ch++)
 #pragma unroll
@@ -755,12 +831,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     epi_bar_sync();
                     {
                         const int b = te >> 7, j = te & 127;  // [board][hidden unit]
-                        s_hid[te] = fmaxf(args.se_b1[j] + s_hidp[b * 128 + j] + s_hidp[(2 + b) * 128 + j], 0.f);
+                        s_hid[te] = fmaxf(P.b1[j] + s_hidp[b * 128 + j] + s_hidp[(2 + b) * 128 + j], 0.f);
                     }
                     epi_bar_sync();
                     // ---- FC2 (128 -> 256) + sigmoid: thread te owns channel te for both boards
                     {
-                        float g0 = args.se_b2[te], g1 = g0;
+                        float g0 = P.b2[te], g1 = g0;
 #pragma unroll
                         for (int q = 0; q < 16; q++) {
                             float wf[8];
@@ -781,7 +857,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (prof) { const long long t = clock64(); pe_fc += t - tp2; tp2 = t; }
                 }
 
-                if constexpr (YSMEM) {
+                if (YSMEM && is_se) {
                     // ---- final pass, elementwise and fully coalesced: thread te owns 16-byte chunk te % 32 of
                     //      rows te / 32 + 8 i; y from shared memory, x from global, out = relu(gate * y + x)
                     const int chunk = te & 31, r0 = te >> 5;
@@ -795,8 +871,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         g1[0] = b0.x; g1[1] = b0.y; g1[2] = b0.z; g1[3] = b0.w; g1[4] = b1.x; g1[5] = b1.y; g1[6] = b1.z; g1[7] = b1.w;
                     }
                     const size_t tile_row0 = (size_t)tile * TC_BM;
-                    const uint4 *xg = reinterpret_cast<const uint4 *>(args.resid + tile_row0 * BN) + chunk;
-                    uint4 *og = reinterpret_cast<uint4 *>(static_cast<__nv_bfloat16 *>(args.out) + tile_row0 * BN) + chunk;
+                    const uint4 *xg = reinterpret_cast<const uint4 *>(P.resid + tile_row0 * BN) + chunk;
+                    uint4 *og = reinterpret_cast<uint4 *>(static_cast<__nv_bfloat16 *>(P.out) + tile_row0 * BN) + chunk;
 #pragma unroll
                     for (int i0 = 0; i0 < 16; i0 += 8) {
                         uint4 xv[8];
@@ -822,11 +898,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         }
                     }
                     if (prof) pe_final += clock64() - tp2;
+                    tile_done(slot);
                     continue;  // the accumulator was released after the pooling pass
                 }
                 // ---- final pass: y (recomputed from TMEM), [gate * y + x], ReLU, bf16 store ------
                 const float *gate = s_gate + (quad >> 1) * 256;
-                uint8_t *gout = reinterpret_cast<uint8_t *>(static_cast<__nv_bfloat16 *>(args.out) + wrow0 * BN + c0);
+                uint8_t *gout = reinterpret_cast<uint8_t *>(static_cast<__nv_bfloat16 *>(P.out) + wrow0 * BN + c0);
                 uint32_t rm[32];
                 tmem_ld32(tcol, r);
 #pragma unroll
@@ -834,19 +911,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (ch < 3) tmem_ld32_nowait(tcol + (ch + 1) * 32, (ch & 1) ? r : rm);
                     const uint32_t(&cur)[32] = (ch & 1) ? rm : r;
                     uint4 xr[4];
-                    if constexpr (EPI == EPI_LN_SE) staged_gather_64B(stg, lane, xa + ch * 4, xr);
+                    if (!YSMEM && is_se) staged_gather_64B(stg, lane, xa + ch * 4, xr);
                     uint4 pk[4];
 #pragma unroll
                     for (int j = 0; j < 16; j++) {
                         const int c = c0 + ch * 32 + 2 * j;
                         float y0 = (__uint_as_float(cur[2 * j]) + s_bias[c] - mean) * rstd * s_gamma[c] + s_beta[c];
                         float y1 = (__uint_as_float(cur[2 * j + 1]) + s_bias[c + 1] - mean) * rstd * s_gamma[c + 1] + s_beta[c + 1];
-                        if constexpr (EPI == EPI_LN_SE) {
+                        if (!YSMEM && is_se) {
                             const uint4 xq = xr[j >> 2];
                             const uint32_t xw = (j & 3) == 0 ? xq.x : ((j & 3) == 1 ? xq.y : ((j & 3) == 2 ? xq.z : xq.w));
                             y0 = fmaxf(fmaf(gate[c], y0, __uint_as_float(xw << 16)), 0.f);
                             y1 = fmaxf(fmaf(gate[c + 1], y1, __uint_as_float(xw & 0xffff0000u)), 0.f);
-                        } else if (args.relu) {
+                        } else if (P.relu) {
                             y0 = fmaxf(y0, 0.f);
                             y1 = fmaxf(y1, 0.f);
                         }
@@ -865,7 +942,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tc_fence_before();
             if (CTA2) mbar_arrive_leader(tempty_bar(as));
             else mbar_arrive(tempty_bar(as));
+            tile_done(slot);
             if (prof) pe_work += clock64() - tp1;
+        }
         }
         if (prof) {
             args.prof[blockIdx.x * 16 + 5] = pe_wait;
@@ -1022,6 +1101,98 @@ void tc_conv_set_se(TcConv *c, const void *w1p, const float *b1, const void *w2p
 }
 
 void tc_conv_destroy(TcConv *c) { delete c; }
+
+// ---- whole-tower kernel --------------------------------------------------------------------------------
+struct TcTower {
+    TowerLayer *d_layers = nullptr;
+    int n_layers = 0;
+};
+
+int tc_tower_create(TcTower **out, const TcTowerLayerDesc *descs, int n, int boards_alloc)
+{
+    std::vector<TowerLayer> h((size_t)n);
+    for (int i = 0; i < n; i++) {
+        const TcConv *c = descs[i].conv;
+        if (!c || !c->pair_ok || c->bn != 256 || (c->epi != EPI_LN && c->epi != EPI_LN_SE)) {
+            set_error("tc_tower_create: layer is not a 256-wide tower convolution");
+            return SC_E_INVAL;
+        }
+        memset(&h[i], 0, sizeof(TowerLayer));
+        SCB_CHECK(make_act_map_4d(descs[i].in, boards_alloc, c->k_per_tap, &h[i].map_a));
+        h[i].map_w = c->map_w_half;
+        h[i].out = descs[i].out;
+        h[i].resid = descs[i].resid;
+        h[i].bias = c->bias;
+        h[i].gamma = c->gamma;
+        h[i].beta = c->beta;
+        h[i].se_w1p = c->se_w1p;
+        h[i].se_w2p = c->se_w2p;
+        h[i].se_b1 = c->se_b1;
+        h[i].se_b2 = c->se_b2;
+        h[i].taps = c->taps;
+        h[i].kchunks = c->k_per_tap / TC_BK;
+        h[i].relu = descs[i].relu;
+        h[i].se = c->epi == EPI_LN_SE;
+        if (h[i].se && (!c->se_w1p || !descs[i].resid)) {
+            set_error("tc_tower_create: SE layer without SE weights / residual");
+            return SC_E_INVAL;
+        }
+    }
+    TcTower *t = new TcTower();
+    t->n_layers = n;
+    if (cudaMalloc(&t->d_layers, sizeof(TowerLayer) * (size_t)n) != cudaSuccess ||
+        cudaMemcpy(t->d_layers, h.data(), sizeof(TowerLayer) * (size_t)n, cudaMemcpyHostToDevice) != cudaSuccess) {
+        delete t;
+        set_error("tc_tower_create: device allocation failed");
+        return SC_E_CUDA;
+    }
+    SCB_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<256, EPI_LN_SE, true, true, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256, true, true>::SMEM_BYTES));
+    *out = t;
+    return SC_OK;
+}
+
+void tc_tower_destroy(TcTower *t)
+{
+    if (!t) return;
+    cudaFree(t->d_layers);
+    delete t;
+}
+
+// returns SC_E_STATE (without an error message) when the batch needs more tile slots per CTA than the
+// kernel tracks; the caller then runs the layers one launch at a time
+int tc_tower_launch(TcTower *t, int n_boards, int num_sms, cudaStream_t st)
+{
+    if (n_boards <= 0) return SC_OK;
+    const int n_tiles = (n_boards + 1) / 2;
+    const int n_pairs = (n_tiles + 1) / 2;
+    int g2 = 2 * n_pairs;
+    if (g2 > (num_sms & ~1)) g2 = num_sms & ~1;
+    const int slots = (n_pairs + g2 / 2 - 1) / (g2 / 2);
+    if (slots > TC_MAX_SLOTS) return SC_E_STATE;
+    TcArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_tiles = n_tiles;
+    a.n_splits = 1;
+    a.layers = t->d_layers;
+    a.n_layers = t->n_layers;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(g2);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = TcCfg<256, true, true>::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    static CUtensorMap dummy;  // the layer array carries the tensor maps
+    SCB_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<256, EPI_LN_SE, true, true, true>, dummy, dummy, a));
+    SCB_CUDA(cudaGetLastError());
+    return SC_OK;
+}
 
 int tc_conv_launch(TcConv *c, const __nv_bfloat16 *in, int rows_alloc, int n_units, void *out,
                    const __nv_bfloat16 *resid, int relu, int n_splits, int num_sms, cudaStream_t st)

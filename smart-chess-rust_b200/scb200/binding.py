@@ -22,7 +22,7 @@ DECLARED_SYMBOLS = [
     "sc_create", "sc_destroy", "sc_last_error", "sc_info", "sc_eval", "sc_eval_device", "sc_encode_only",
     "sc_move_index_only", "sc_forward_only", "sc_launch_count", "sc_last_timing", "sc_set_timing", "sc_kernel_timing",
     "sc_eval_submit", "sc_eval_wait", "sc_selfplay_create", "sc_selfplay_run", "sc_selfplay_trace_json",
-    "sc_selfplay_destroy", "sc_rules_probe", "sc_arena_create", "sc_encode_steps",
+    "sc_selfplay_destroy", "sc_rules_probe", "sc_arena_create", "sc_encode_steps", "sc_timed_flops_per_leaf",
 ]
 
 
@@ -75,6 +75,8 @@ def load_library():
         L.sc_move_index_only.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.sc_forward_only.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.sc_encode_steps.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 5
+        L.sc_timed_flops_per_leaf.restype = C.c_double
+        L.sc_timed_flops_per_leaf.argtypes = [C.c_void_p]
         L.sc_launch_count.restype = C.c_int64
         L.sc_launch_count.argtypes = [C.c_void_p]
         L.sc_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
@@ -237,6 +239,9 @@ class Engine:
         a, n = C.c_float(), C.c_int()
         _check(load_library().sc_kernel_timing(self._h, C.byref(a), C.byref(n)), "sc_kernel_timing")
         return a.value, n.value
+
+    def timed_flops_per_leaf(self) -> float:
+        return float(load_library().sc_timed_flops_per_leaf(self._h))
 
     def last_timing(self):
         a, b = C.c_float(), C.c_float()

@@ -421,7 +421,8 @@ static int run_network(sc_engine *e, int n, cudaStream_t st)
             if (trc == SC_OK) {
                 SCB_CHECK(kev_mark(e, st));
                 e->launches += 1;
-                e->timed_flops_per_leaf = 2.0 * 64 * 256 * (9.0 * C_IN + e->n_blocks * (2 * 9.0 * 256 + 2.0 * C_SE / 64));
+                e->timed_flops_per_leaf =
+                    2.0 * 64 * 256 * (9.0 * C_IN + e->n_blocks * (2 * 9.0 * 256 + 2.0 * C_SE / 64) + 2 * 256.0);
             } else if (trc != SC_E_STATE)
                 return trc;
             else
@@ -443,11 +444,14 @@ static int run_network(sc_engine *e, int n, cudaStream_t st)
             e->timed_flops_per_leaf = 2.0 * 64 * 256 * 9.0 * 256 * 2 * e->n_blocks;
         }
         if (e->timing) SCB_CUDA(cudaEventRecord(e->ev[2], st));
-        SCB_CHECK(tc_conv_launch(e->pol1.tc, e->h_x, nb, n, e->h_t, nullptr, 0, 1, e->num_sms, st));
+        if (trc != SC_OK) {
+            SCB_CHECK(tc_conv_launch(e->pol1.tc, e->h_x, nb, n, e->h_t, nullptr, 0, 1, e->num_sms, st));
+            SCB_CHECK(tc_conv_launch(e->val1.tc, e->h_x, nb, n, e->h_y, nullptr, 1, 1, e->num_sms, st));
+            e->launches += 2;
+        }
         SCB_CHECK(tc_conv_launch(e->pol2.tc, e->h_t, nb, n, e->logits, nullptr, 0, 1, e->num_sms, st));
-        SCB_CHECK(tc_conv_launch(e->val1.tc, e->h_x, nb, n, e->h_y, nullptr, 1, 1, e->num_sms, st));
         SCB_CHECK(tc_conv_launch(e->vfc_tc, e->h_y, nb, n, e->vpre, nullptr, 0, e->vsplit, e->num_sms, st));
-        e->launches += 4;
+        e->launches += 2;
     }
     SCB_CHECK(launch_value_finish(e->vpre, e->vsplit, n, e->d_meta, e->v_wmeta, e->v_b1, e->v_w2, e->v_b2,
                                   e->d_value, st));
@@ -529,6 +533,9 @@ int sc_create(const char *weights_blob_path, int device, int mode, int max_batch
                 d.push_back(TcTowerLayerDesc{e->conv1[i].tc, e->h_x, e->h_t, nullptr, 1});
                 d.push_back(TcTowerLayerDesc{e->conv2[i].tc, e->h_t, e->h_x, e->h_x, 0});
             }
+            // the two 256-wide 1x1 head convolutions read the tower output tile by tile as well
+            d.push_back(TcTowerLayerDesc{e->pol1.tc, e->h_x, e->h_t, nullptr, 0});
+            d.push_back(TcTowerLayerDesc{e->val1.tc, e->h_x, e->h_y, nullptr, 1});
             if ((rc = tc_tower_create(&e->tower, d.data(), (int)d.size(), e->alloc_boards)) != SC_OK) break;
         }
         if (cudaDeviceSynchronize() != cudaSuccess) { rc = SC_E_CUDA; set_error("sync after weight upload failed"); break; }

@@ -334,3 +334,26 @@ def test_encode_steps_matches_reference_restatement(co, eng_f32_small):
     bad = [((12, 28, 0), [((12, 28, 0), 3)])]          # children are not the full legal-move set
     with pytest.raises(scb200.SCError):
         eng_f32_small.encode_steps(bad, False)
+
+
+def test_large_batch_falls_back_to_per_layer_launches_bit_identically(co, nets):
+    """The whole-tower launch tracks at most 32 tiles per CTA (9472 boards on 148 SMs); larger batches run
+    the same kernels one layer per launch.  Both paths must give bit-identical priors and values."""
+    import scb200
+
+    games = co.random_play_positions(97, seed=21)
+    reps = 100
+    big = games * reps                                   # 9700 leaves > 9472
+    pos, moves, off, _ = games_to_batch(big)
+    e = scb200.Engine(nets["n2"][1], 0, scb200.SC_MODE_BF16, len(big))
+    try:
+        pri_big, val_big = e.eval(pos, moves, off)
+        pri_big, val_big = pri_big.copy(), val_big.copy()
+        p1, m1, o1, _ = games_to_batch(games)
+        pri, val = e.eval(p1, m1, o1)                    # 97 leaves: whole-tower launch
+        n1 = int(o1[-1])
+        for r in (0, 37, reps - 1):
+            assert np.array_equal(val_big[r * 97:(r + 1) * 97], val)
+            assert np.array_equal(pri_big[r * n1:(r + 1) * n1], pri)
+    finally:
+        e.close()

@@ -246,6 +246,7 @@ struct TcArgs {
     long long *prof;                     // optional [grid][16] phase cycle counters (SCB200_PHASE_PROFILE=1)
     const TowerLayer *layers;            // TOWER: all conv layers of the residual tower, run back to back
     int n_layers;
+    int group;                           // TOWER: tiles per CTA carried through all layers together (0 = all)
 };
 
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32])
@@ -478,6 +479,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int n_work = EPI == EPI_RAW ? args.n_tiles * args.n_splits : (CTA2 ? (args.n_tiles + 1) / 2 : args.n_tiles);
+    // This CTA's work items are visited group by group; a group of tiles goes through ALL layers before the
+    // next group starts (TOWER), so a tile's output is re-read while it is still in L2.  Groups have >= 2 tiles
+    // whenever possible: with the double-buffered accumulator the epilogue of one tile overlaps the MMAs of
+    // the next tile of the group.  Outside the tower kernel there is one layer and one group.
+    const int n_slots = work0 < n_work ? (n_work - work0 + work_stride - 1) / work_stride : 0;
+    const int gsz_req = (TOWER && args.group > 0) ? args.group : (n_slots > 0 ? n_slots : 1);
+    int n_groups = (2 * n_slots + gsz_req) / (2 * gsz_req);  // round(n_slots / gsz_req)
+    if (n_groups < 1) n_groups = 1;
+    auto group_begin = [&](int gi) { return (int)(((long long)gi * n_slots) / n_groups); };
 
     if (warp == 0) {
         if (lane == 0) {
@@ -486,10 +496,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0;
             long long pc_wait_empty = 0;
+            for (int gi = 0; gi < n_groups; gi++)
             for (int layer = 0; layer < n_layers; layer++) {
             const LayerView P = layer_view(layer);
-            int slot = 0;
-            for (int work = work0; work < n_work; work += work_stride, slot++) {
+            for (int slot = group_begin(gi); slot < group_begin(gi + 1); slot++) {
+                const int work = work0 + slot * work_stride;
                 if (TOWER && layer > 0) mbar_wait(ready_bar(slot), (uint32_t)(layer - 1) & 1u);  // this tile's input is written
                 const int tile = EPI == EPI_RAW ? work / args.n_splits : (CTA2 ? work * 2 + (int)cta_rank : work);
                 const int split = EPI == EPI_RAW ? work % args.n_splits : 0;
@@ -535,10 +546,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             uint32_t phase = 0;
             int it = 0;
             long long pc_wait_tempty = 0, pc_wait_full = 0, pc_total = args.prof ? clock64() : 0;
+            for (int gi = 0; gi < n_groups; gi++)
             for (int layer = 0; layer < n_layers; layer++) {
             const LayerView P = layer_view(layer);
             const int nkb = P.taps * P.kchunks;
-            for (int work = work0; work < n_work; work += work_stride, it++) {
+            for (int slot = group_begin(gi); slot < group_begin(gi + 1); slot++, it++) {
                 const int as = it & 1;
                 const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
                 long long t0 = args.prof ? clock64() : 0;
@@ -590,6 +602,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         int it = 0;
         long long pe_wait = 0, pe_work = 0, pe_stats = 0, pe_pool = 0, pe_fc = 0, pe_final = 0;
         const bool prof = args.prof != nullptr && te == 0;
+        for (int gi = 0; gi < n_groups; gi++)
         for (int layer = 0; layer < n_layers; layer++) {
         const LayerView P = layer_view(layer);
         const bool is_se = P.se;
@@ -601,7 +614,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             s_beta[te] = P.beta[te];
             epi_bar_sync();
         }
-        int slot = 0;
         // end of a tile in the tower kernel: the tile's output (generic-proxy stores) is handed to the TMA
         // loads (async proxy) of the next layer through a per-tile mbarrier
         auto tile_done = [&](int sl) {
@@ -610,7 +622,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 mbar_arrive(ready_bar(sl));
             }
         };
-        for (int work = work0; work < n_work; work += work_stride, it++, slot++) {
+        for (int slot = group_begin(gi); slot < group_begin(gi + 1); slot++, it++) {
+            const int work = work0 + slot * work_stride;
             const int tile = EPI == EPI_RAW ? work / args.n_splits : (CTA2 ? work * 2 + (int)cta_rank : work);
             const int split = EPI == EPI_RAW ? work % args.n_splits : 0;
             const int as = it & 1;
@@ -1176,6 +1189,8 @@ int tc_tower_launch(TcTower *t, int n_boards, int num_sms, cudaStream_t st)
     a.n_splits = 1;
     a.layers = t->d_layers;
     a.n_layers = t->n_layers;
+    static const int group = getenv("SCB200_TOWER_GROUP") ? atoi(getenv("SCB200_TOWER_GROUP")) : 3;
+    a.group = group;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(g2);
     cfg.blockDim = dim3(TC_THREADS);
@@ -1189,8 +1204,27 @@ int tc_tower_launch(TcTower *t, int n_boards, int num_sms, cudaStream_t st)
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     static CUtensorMap dummy;  // the layer array carries the tensor maps
+    static long long *d_prof = nullptr;
+    static const bool want_prof = getenv("SCB200_PHASE_PROFILE") != nullptr;
+    if (want_prof) {
+        if (!d_prof) SCB_CUDA(cudaMalloc(&d_prof, 148 * 16 * sizeof(long long)));
+        SCB_CUDA(cudaMemsetAsync(d_prof, 0, 148 * 16 * sizeof(long long), st));
+        a.prof = d_prof;
+    }
     SCB_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<256, EPI_LN_SE, true, true, true>, dummy, dummy, a));
     SCB_CUDA(cudaGetLastError());
+    if (want_prof) {
+        static long long h[148 * 16];
+        SCB_CUDA(cudaStreamSynchronize(st));
+        SCB_CUDA(cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost));
+        double acc[16] = {0};
+        for (int b = 0; b < g2; b += 2)  // leader CTAs carry the MMA counters
+            for (int k = 0; k < 16; k++) acc[k] += (double)h[b * 16 + k] / (g2 / 2);
+        fprintf(stderr,
+                "[tower layers=%d grid=%d] tiles/cta %.2f | producer wait_empty %.0f | mma: total %.0f wait_tmem_empty %.0f "
+                "wait_full %.0f | epilogue: wait_tmem_full %.0f work %.0f (stats %.0f pool %.0f fc %.0f final %.0f)\n",
+                t->n_layers, g2, acc[4], acc[0], acc[3], acc[1], acc[2], acc[5], acc[6], acc[7], acc[8], acc[9], acc[10]);
+    }
     return SC_OK;
 }
 
@@ -1215,7 +1249,7 @@ int tc_conv_launch(TcConv *c, const __nv_bfloat16 *in, int rows_alloc, int n_uni
         ma = &c->act_maps.back().map;
     }
     TcArgs a;
-    a.prof = nullptr;
+    memset(&a, 0, sizeof(a));
     static long long *d_prof = nullptr;
     static const bool want_prof = getenv("SCB200_PHASE_PROFILE") != nullptr;
     if (want_prof) {

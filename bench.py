@@ -50,29 +50,32 @@ def _peaks():
 
 
 # ------------------------------------------------------------------------------------------
-# synthetic workload (uses the oracle's rules engine only to GENERATE positions; nothing of the
-# oracle is on the timed path of our arm)
+# synthetic workload of OUR arm: positions from the driver's native rules (sc_random_positions), weights
+# from scb200.random_init -- nothing under oracle/ is imported on this arm.  The cpu_baseline leg and the
+# --impl reference arm draw their own bounded sample of the same workload from the oracle.
 # ------------------------------------------------------------------------------------------
 def make_workload(n_leaves: int, seed: int):
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import chess_oracle as co
-    from conftest import games_to_batch
+    import scb200
 
-    games = co.random_play_positions(n_leaves, seed=seed)
-    pos, moves, off, _ = games_to_batch(games)
-    return games, pos, moves, off
+    pos, moves, off = scb200.random_positions(n_leaves, seed=seed, max_ply=150)
+    return pos, moves, off
 
 
 def make_blob(tmpdir: str, n_blocks: int = N_BLOCKS):
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import net
     import scb200
 
-    sd = net.init_state_dict(n_blocks, 0)   # == load_model(n_res_blocks=19) seed-0 init (py/module.py:184-212)
+    sd = scb200.random_init_state_dict(n_blocks, 0)   # == load_model(n_res_blocks=19) seed-0 init (py/module.py:184-212)
     path = os.path.join(tmpdir, f"seed0_{n_blocks}.scw")
     scb200.write_blob(sd, path)
     return sd, path
+
+
+def oracle_sample(n: int, seed: int):
+    """bounded sample of the same workload for the CPU legs (seeded random play with true history)"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import chess_oracle as co
+
+    return co.random_play_positions(n, seed=seed)
 
 
 class ClockSampler:
@@ -180,7 +183,7 @@ def reference_arm(args):
 
     torch.set_num_threads(os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1; use every host core
     sd = net.init_state_dict(N_BLOCKS, 0)
-    games, _, _, _ = make_workload(256, seed=1000)
+    games = oracle_sample(256, seed=1000)
     batch = 64
     steps, warm = args.steps, args.warmup
     import numpy as np
@@ -265,7 +268,7 @@ def main():
     sd, blob = make_blob(tmp)
     from scb200 import shard
 
-    games, pos, moves, off = make_workload(B, seed=shard.rank_seed(1000, rank) % (2**31 - 1))
+    pos, moves, off = make_workload(B, seed=shard.rank_seed(1000, rank))
     n_moves = int(off[B])
     eng = scb200.Engine(blob, local_rank, mode, B)
 
@@ -394,7 +397,7 @@ def main():
                     "whole_step_tflops": value / world * FLOP_PER_LEAF / 1e12}
         cpu = None
         if world == 1 and args.cpu_budget > 0:
-            b, b1, n, thr = cpu_reference_throughput(sd, games, args.cpu_budget, 64)
+            b, b1, n, thr = cpu_reference_throughput(sd, oracle_sample(512, seed=1000), args.cpu_budget, 64)
             cpu = {"value": b, "unit": "leaf evals/s", "cores": thr, "kind": "port",
                    "sample": f"{n} leaves of the same workload in batches of 64 (fp32 libtorch CPU oracle)",
                    "batch1_value": b1, "host_cpus": os.cpu_count()}

@@ -201,6 +201,12 @@ int sc_selfplay_destroy(sc_selfplay *sp);
  * engines exchanged, as scripts/leader-board:49-54 does. */
 int sc_arena_create(sc_engine *white, sc_engine *black, const sc_selfplay_config *cfg, sc_selfplay **out);
 
+/* Synthetic workload: seeded uniform random play from the start position with the driver's
+ * native rules, restart on mate/stalemate or at `max_ply`; every non-terminal position met is emitted
+ * with its true history (packed leaf, node depth = ply) and its legal moves (CSR).  Fills exactly n. */
+int sc_random_positions(int n, uint64_t seed, int max_ply, sc_position *pos_out, sc_move *moves_out,
+                        int32_t *move_off /* n+1 */, int max_moves_total);
+
 /* Host rules probe: replays `n_history` moves from the start position with the driver's native rules
  * (the replacement of the python-chess calls at src/chess.rs:665-788) and reports what the reference
  * would see there: legal moves in python-chess generation order, the packed leaf `_encode` would be

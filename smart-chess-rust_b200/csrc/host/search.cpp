@@ -958,6 +958,39 @@ int64_t sc_selfplay_trace_json(sc_selfplay *sp, int64_t k, char *buf, int64_t ca
     return (int64_t)s.size() + 1;
 }
 
+int sc_random_positions(int n, uint64_t seed, int max_ply, sc_position *pos_out, sc_move *moves_out, int32_t *move_off,
+                        int max_moves_total)
+{
+    if (n < 0 || (n > 0 && (!pos_out || !moves_out || !move_off)) || max_ply <= 0) {
+        set_error("sc_random_positions: bad argument");
+        return SC_E_INVAL;
+    }
+    Rng rng;
+    rng.seed(seed);
+    Tree t;
+    t.new_game(0);
+    int k = 0, total = 0;
+    if (move_off) move_off[0] = 0;
+    while (k < n) {
+        MoveList l;
+        t.game.cur.legal_moves(l);
+        if (l.n == 0 || t.game.ply() >= max_ply) {
+            t.new_game(0);
+            continue;
+        }
+        if (total + l.n > max_moves_total) {
+            set_error("sc_random_positions: move buffer too small");
+            return SC_E_INVAL;
+        }
+        pack_leaf(t, t.game.ply(), pos_out + k);
+        for (int i = 0; i < l.n; i++) moves_out[total + i] = sc_move{l.m[i].from, l.m[i].to, l.m[i].promo, 0};
+        total += l.n;
+        move_off[++k] = total;
+        t.game.push(l.m[(int)(rng.next() % (uint64_t)l.n)]);
+    }
+    return SC_OK;
+}
+
 int sc_rules_probe(const sc_move *history, int n_history, sc_move *legal_out, int *n_legal, sc_position *packed_out,
                    int *termination, int *winner)
 {

@@ -10,6 +10,7 @@ from .binding import (  # noqa: F401
     Arena,
     elo,
     rules_probe,
+    random_positions,
     SCError,
     SC_MODE_BF16,
     SC_MODE_FP32,
@@ -21,3 +22,4 @@ from .binding import (  # noqa: F401
     DECLARED_SYMBOLS,
 )
 from .export import write_blob, export_checkpoint  # noqa: F401
+from .random_init import random_init_state_dict  # noqa: F401

@@ -23,6 +23,7 @@ DECLARED_SYMBOLS = [
     "sc_move_index_only", "sc_forward_only", "sc_launch_count", "sc_last_timing", "sc_set_timing", "sc_kernel_timing",
     "sc_eval_submit", "sc_eval_wait", "sc_selfplay_create", "sc_selfplay_run", "sc_selfplay_trace_json",
     "sc_selfplay_destroy", "sc_rules_probe", "sc_arena_create", "sc_encode_steps", "sc_timed_flops_per_leaf",
+    "sc_random_positions",
 ]
 
 
@@ -90,6 +91,7 @@ def load_library():
         L.sc_selfplay_trace_json.argtypes = [C.c_void_p, C.c_int64, C.c_char_p, C.c_int64]
         L.sc_selfplay_destroy.argtypes = [C.c_void_p]
         L.sc_arena_create.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(SelfPlayConfig), C.POINTER(C.c_void_p)]
+        L.sc_random_positions.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.sc_rules_probe.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.c_void_p,
                                      C.POINTER(C.c_int), C.POINTER(C.c_int)]
         _LIB = L
@@ -331,3 +333,13 @@ def elo(total: int, wins: int, losses: int) -> float:
 
     s = (wins + (total - wins - losses) / 2) / total
     return 400 * math.log(s / (1 - s), 10)
+
+
+def random_positions(n: int, seed: int = 1, max_ply: int = 150):
+    """Synthetic workload from the driver's native rules: (sc_position[n], sc_move[total], move_off[n+1])."""
+    pos = np.zeros(n, dtype=POSITION_DTYPE)
+    moves = np.zeros(max(1, n * 64), dtype=MOVE_DTYPE)
+    off = np.zeros(n + 1, dtype=np.int32)
+    _check(load_library().sc_random_positions(n, seed, max_ply, _ptr(pos), _ptr(moves), _ptr(off), len(moves)),
+           "sc_random_positions")
+    return pos, moves[: int(off[n])].copy(), off

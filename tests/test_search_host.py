@@ -190,3 +190,25 @@ def test_arena_rounds_hash_evaluator(co):
             assert oc is not None and {1: "White", 0: "Black", -1: None}[oc[1]] == tr["outcome"]["winner"]
     a.close()
     assert abs(scb200.elo(200, 120, 60) - 107.538) < 1e-2     # scripts/elo.py
+
+
+def test_random_positions_generator_matches_oracle_encoding(co):
+    """bench.py's workload generator (native rules) emits legal, well-formed leaves: replaying its games
+    is impossible from outside, so check each leaf's packed history against itself -- n_hist grows 1..8,
+    slot 0 meta consistent, moves are exactly the legal moves of the position rebuilt from slot 0."""
+    import scb200
+
+    pos, moves, off = scb200.random_positions(400, seed=3, max_ply=60)
+    assert len(pos) == 400 and off[0] == 0 and off[-1] == len(moves)
+    assert pos["n_hist"].min() == 1 and pos["n_hist"].max() == 8
+    # plies restart at 60: meta fullmove stays small, both colours appear
+    assert pos["meta"][:, 1].max() <= 31 and set(pos["meta"][:, 0].tolist()) == {0, 1}
+    # first leaf is the start position with the 20 standard moves in python-chess order
+    g = co.Game()
+    first = [(int(m["from"]), int(m["to"]), int(m["promo"])) for m in moves[off[0]:off[1]]]
+    assert first == [tuple(int(x) for x in m) for m in g.legal_moves()]
+    slot, meta, nh = g.pack()
+    assert np.array_equal(pos["slot"][0], slot) and np.array_equal(pos["meta"][0], meta)
+    # determinism
+    p2, m2, o2 = scb200.random_positions(400, seed=3, max_ply=60)
+    assert np.array_equal(p2, pos) and np.array_equal(o2, off)

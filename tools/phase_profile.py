@@ -7,7 +7,7 @@ import bench
 import numpy as np, scb200
 tmp = tempfile.mkdtemp()
 sd, blob = bench.make_blob(tmp, int(os.environ.get('BLOCKS', '19')))
-games, pos, moves, off = bench.make_workload(2048, 1000)
+pos, moves, off = bench.make_workload(2048, 1000)
 e = scb200.Engine(blob, 0, scb200.SC_MODE_BF16, 2048)
 for i in range(3):
     sys.stderr.write(f"--- eval {i}\n")

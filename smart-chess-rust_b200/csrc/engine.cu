@@ -645,10 +645,14 @@ int sc_eval_submit(sc_engine *e, int n, const sc_position *pos, const sc_move *m
     e->next_ticket = (t + 1) % SC_MAX_INFLIGHT;
     if (!e->tickets[t]) SCB_CUDA(cudaEventCreateWithFlags(&e->tickets[t], cudaEventDisableTiming));
     if (n > 0) {
-        const size_t nm = (size_t)n * SC_MAX_MOVES;
         SCB_CUDA(cudaMemcpyAsync(e->d_pos, pos, sizeof(sc_position) * (size_t)n, cudaMemcpyHostToDevice, st));
         SCB_CUDA(cudaMemcpyAsync(e->d_cnt, move_cnt, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
-        SCB_CUDA(cudaMemcpyAsync(e->d_moves, moves_strided, sizeof(sc_move) * nm, cudaMemcpyHostToDevice, st));
+        // strided by SC_MAX_MOVES on both sides, but only the first max(move_cnt) moves of every leaf travel
+        int wmax = 1;
+        for (int i = 0; i < n; i++) wmax = move_cnt[i] > wmax ? move_cnt[i] : wmax;
+        if (wmax > SC_MAX_MOVES) wmax = SC_MAX_MOVES;
+        SCB_CUDA(cudaMemcpy2DAsync(e->d_moves, sizeof(sc_move) * SC_MAX_MOVES, moves_strided, sizeof(sc_move) * SC_MAX_MOVES,
+                                   sizeof(sc_move) * (size_t)wmax, (size_t)n, cudaMemcpyHostToDevice, st));
         SCB_CHECK(encode_for_mode(e, e->d_pos, n, st));
         const int saved_timing = e->timing;
         e->timing = 0;  // asynchronous path never synchronises
@@ -657,7 +661,8 @@ int sc_eval_submit(sc_engine *e, int n, const sc_position *pos, const sc_move *m
         SCB_CHECK(rc);
         SCB_CHECK(launch_policy_gather(e->logits, e->d_pos, e->d_moves, nullptr, e->d_cnt, n, e->d_priors, st));
         e->launches += 1;
-        SCB_CUDA(cudaMemcpyAsync(priors_out_strided, e->d_priors, sizeof(float) * nm, cudaMemcpyDeviceToHost, st));
+        SCB_CUDA(cudaMemcpy2DAsync(priors_out_strided, sizeof(float) * SC_MAX_MOVES, e->d_priors, sizeof(float) * SC_MAX_MOVES,
+                                   sizeof(float) * (size_t)wmax, (size_t)n, cudaMemcpyDeviceToHost, st));
         SCB_CUDA(cudaMemcpyAsync(value_out, e->d_value, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, st));
     }
     SCB_CUDA(cudaEventRecord(e->tickets[t], st));

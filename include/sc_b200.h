@@ -207,6 +207,10 @@ int sc_arena_create(sc_engine *white, sc_engine *black, const sc_selfplay_config
 int sc_random_positions(int n, uint64_t seed, int max_ply, sc_position *pos_out, sc_move *moves_out,
                         int32_t *move_off /* n+1 */, int max_moves_total);
 
+/* Test hook: one Dirichlet(alpha) sample of size n from the driver's root-noise sampler (src/mcts.rs:123-130
+ * uses rand_distr::Dirichlet(0.3)); lets the tests check its moments. */
+int sc_test_dirichlet(uint64_t seed, float alpha, int n, float *out);
+
 /* Host rules probe: replays `n_history` moves from the start position with the driver's native rules
  * (the replacement of the python-chess calls at src/chess.rs:665-788) and reports what the reference
  * would see there: legal moves in python-chess generation order, the packed leaf `_encode` would be

@@ -571,8 +571,12 @@ struct Game {
 
     bool is_repetition(int count) const
     {
+        // python-chess pre-filters on equal occupancy over the whole stack; the exact walk below stops at
+        // the first irreversible move, and every zeroing move is irreversible, so only the last
+        // `halfmove` plies can hold a real repetition -- scanning just those gives the same answer
         int maybe = 1;
-        for (int k = ply() - 1; k >= 0; k--)
+        const int lo = ply() - cur.halfmove > 0 ? ply() - cur.halfmove : 0;
+        for (int k = ply() - 1; k >= lo; k--)
             if (stack[k].pos.all == cur.all && ++maybe >= count) break;
         if (maybe < count) return false;
         const TKey key = tkey(cur);
@@ -591,7 +595,8 @@ struct Game {
         stack.push_back(Entry{cur, cur_rep});
         moves.push_back(m);
         cur.push(m);
-        cur_rep = (uint8_t)((is_repetition(2) ? 1 : 0) | (is_repetition(3) ? 2 : 0));
+        // three occurrences imply two
+        cur_rep = is_repetition(2) ? (uint8_t)(1 | (is_repetition(3) ? 2 : 0)) : (uint8_t)0;
     }
     void pop()
     {

@@ -58,28 +58,43 @@ struct Rng {
         return r;
     }
     double uniform() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
-    double normal()
+    // single-precision stream for the Dirichlet noise (thousands of gamma draws per move and tree)
+    float uniformf() { return ((float)(next() >> 40) + 0.5f) * (1.0f / 16777216.0f); }  // (0, 1)
+    bool have_spare = false;
+    float spare = 0.f;
+    float normalf()
     {
-        double u1 = uniform(), u2 = uniform();
-        if (u1 < 1e-300) u1 = 1e-300;
-        return std::sqrt(-2.0 * std::log(u1)) * std::cos(6.283185307179586 * u2);
+        if (have_spare) {
+            have_spare = false;
+            return spare;
+        }
+        // Box-Muller, both outputs used
+        const float u1 = uniformf(), u2 = uniformf();
+        const float r = sqrtf(-2.0f * logf(u1));
+        float sn, cs;
+        sincosf(6.2831853f * u2, &sn, &cs);
+        spare = r * sn;
+        have_spare = true;
+        return r * cs;
     }
     // Marsaglia-Tsang; alpha < 1 handled by the boost gamma(a) = gamma(a+1) * U^(1/a)
-    double gamma(double alpha)
+    float gammaf(float alpha)
     {
-        if (alpha < 1.0) {
-            double u = uniform();
-            if (u < 1e-300) u = 1e-300;
-            return gamma(alpha + 1.0) * std::pow(u, 1.0 / alpha);
+        float boost = 1.0f;
+        if (alpha < 1.0f) {
+            boost = expf(logf(uniformf()) / alpha);
+            alpha += 1.0f;
         }
-        const double d = alpha - 1.0 / 3.0, c = 1.0 / std::sqrt(9.0 * d);
+        const float d = alpha - 1.0f / 3.0f, c = 1.0f / sqrtf(9.0f * d);
         for (;;) {
-            double x = normal(), v = 1.0 + c * x;
-            if (v <= 0) continue;
+            const float x = normalf();
+            float v = 1.0f + c * x;
+            if (v <= 0.f) continue;
             v = v * v * v;
-            double u = uniform();
-            if (u < 1.0 - 0.0331 * x * x * x * x) return d * v;
-            if (std::log(u) < 0.5 * x * x + d * (1.0 - v + std::log(v))) return d * v;
+            const float u = uniformf();
+            const float x2 = x * x;
+            if (u < 1.0f - 0.0331f * x2 * x2) return d * v * boost;
+            if (logf(u) < 0.5f * x2 + d * (1.0f - v + logf(v))) return d * v * boost;
         }
     }
 };
@@ -388,14 +403,15 @@ bool descend(sc_selfplay *sp, Tree &t)
             if (is_root && cfg.with_noise && nd.n_children >= 2) {
                 // fresh Dirichlet(0.3) sample on every rollout (src/mcts.rs:123-130, 171-184)
                 t.noisy.resize(nd.n_children);
-                double tot_g = 0.0;
-                std::vector<double> g(nd.n_children);
+                float g[256];
+                float tot_g = 0.f;
                 for (int i = 0; i < nd.n_children; i++) {
-                    g[i] = t.rng.gamma(0.3);
+                    g[i] = t.rng.gammaf(0.3f);
                     tot_g += g[i];
                 }
+                const float inv = tot_g > 0.f ? 1.0f / tot_g : 0.f;
                 for (int i = 0; i < nd.n_children; i++)
-                    t.noisy[i] = ch[i].prior * (1.0f - cfg.epsilon) + (float)(g[i] / tot_g) * cfg.epsilon;
+                    t.noisy[i] = ch[i].prior * (1.0f - cfg.epsilon) + (g[i] * inv) * cfg.epsilon;
                 pri = t.noisy.data();
             }
             int bi = 0;
@@ -988,6 +1004,20 @@ int sc_random_positions(int n, uint64_t seed, int max_ply, sc_position *pos_out,
         move_off[++k] = total;
         t.game.push(l.m[(int)(rng.next() % (uint64_t)l.n)]);
     }
+    return SC_OK;
+}
+
+int sc_test_dirichlet(uint64_t seed, float alpha, int n, float *out)
+{
+    if (n <= 0 || !out || !(alpha > 0.f)) return SC_E_INVAL;
+    Rng rng;
+    rng.seed(seed);
+    float tot = 0.f;
+    for (int i = 0; i < n; i++) {
+        out[i] = rng.gammaf(alpha);
+        tot += out[i];
+    }
+    for (int i = 0; i < n; i++) out[i] /= tot;
     return SC_OK;
 }
 

@@ -212,3 +212,23 @@ def test_random_positions_generator_matches_oracle_encoding(co):
     # determinism
     p2, m2, o2 = scb200.random_positions(400, seed=3, max_ply=60)
     assert np.array_equal(p2, pos) and np.array_equal(o2, off)
+
+
+def test_root_noise_sampler_moments():
+    """Dirichlet(0.3) root noise (mcts.rs:123-130): components sum to 1, mean 1/n, and the variance of a
+    component is (1/n)(1-1/n)/(n*alpha+1)."""
+    import ctypes
+
+    import scb200
+
+    L = scb200.load_library()
+    n, alpha, reps = 30, 0.3, 4000
+    xs = np.zeros((reps, n), dtype=np.float32)
+    for r in range(reps):
+        assert L.sc_test_dirichlet(1000 + r, ctypes.c_float(alpha), n, xs[r].ctypes.data) == 0
+    assert np.allclose(xs.sum(1), 1.0, atol=1e-4) and (xs >= 0).all()
+    assert abs(xs.mean() - 1.0 / n) < 1e-6
+    var_expected = (1 / n) * (1 - 1 / n) / (n * alpha + 1)
+    assert abs(xs.var(axis=0).mean() / var_expected - 1.0) < 0.1
+    # sparse, as alpha < 1 demands: the largest component usually carries a big share
+    assert np.median(xs.max(1)) > 0.25

@@ -342,7 +342,7 @@ def main():
     # ---- batched self-play at 180 rollouts (BASELINE configs[2]: 2048 concurrent trees) ---------------
     sp_stats = None
     if args.selfplay_moves > 0:
-        nthr = args.threads or max(1, (os.cpu_count() or 8) // max(world, 1) - 1)
+        nthr = args.threads or max(1, (os.cpu_count() or 8) // max(world, 1))
         eng_sp = scb200.Engine(blob, local_rank, mode, B)
         sp = scb200.SelfPlay(eng_sp, n_trees=B, rollout_num=180, num_steps=150, cpuct=2.5, epsilon=0.15,
                              with_noise=True, temperature_switch=4, temperature=0.0, seed=shard.rank_seed(100, rank),

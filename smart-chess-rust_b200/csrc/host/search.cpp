@@ -735,7 +735,7 @@ void worker_main(sc_selfplay *sp, int worker, int n_workers)
             seen = sp->job_gen;
             g = sp->job_group;
         }
-        run_group_slice(sp, g, worker, n_workers);
+        run_group_slice(sp, g, worker + 1, n_workers + 1);
         {
             std::lock_guard<std::mutex> lk(sp->mu);
             if (--sp->job_pending == 0) sp->cv_done.notify_one();
@@ -743,6 +743,7 @@ void worker_main(sc_selfplay *sp, int worker, int n_workers)
     }
 }
 
+// n_threads = T: the calling thread takes slice 0, T - 1 pool threads take the others
 void parallel_advance(sc_selfplay *sp, int g)
 {
     const int nw = (int)sp->workers.size();
@@ -757,6 +758,7 @@ void parallel_advance(sc_selfplay *sp, int g)
         sp->job_gen++;
     }
     sp->cv_start.notify_all();
+    run_group_slice(sp, g, 0, nw + 1);
     std::unique_lock<std::mutex> lk(sp->mu);
     sp->cv_done.wait(lk, [&] { return sp->job_pending == 0; });
 }
@@ -825,7 +827,7 @@ int sc_selfplay_create(sc_engine *e, const sc_selfplay_config *cfg, sc_selfplay 
         }
         memset(G.cnt, 0, sizeof(int32_t) * G.count);
     }
-    const int nt = cfg->n_threads > 1 ? cfg->n_threads : 0;
+    const int nt = cfg->n_threads > 1 ? cfg->n_threads - 1 : 0;  // pool threads next to the calling thread
     for (int w = 0; w < nt; w++) sp->workers.emplace_back(worker_main, sp, w, nt);
     *out = sp;
     return SC_OK;

@@ -56,9 +56,6 @@ __device__ __forceinline__ void build_masks(const sc_position *p, uint64_t *slot
     __syncwarp();
 }
 
-template <typename T> struct One;
-template <> struct One<int8_t> { static __device__ __forceinline__ uint32_t bits() { return 1u; } };
-
 __global__ void __launch_bounds__(ENC_WARPS * 32) encode_i8_kernel(const sc_position *__restrict__ pos, int n,
                                                                    int8_t *__restrict__ out,
                                                                    int32_t *__restrict__ meta_out)

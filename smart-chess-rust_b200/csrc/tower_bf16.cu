@@ -1,8 +1,10 @@
 // bf16 throughput mode of the policy/value network: tcgen05 / TMEM / TMA implicit-GEMM
-// convolutions with the bias + LayerNorm(C) (+ReLU) epilogue fused in, for sm_100a.
+// convolutions with bias + LayerNorm(C) (+ReLU | + squeeze-excitation + residual + ReLU)
+// fused into the epilogue, for sm_100a.
 //
 // Network arithmetic restated from py/module.py:120-126 (stem), :38-46 (ResBlockSE),
-// :70-76 / :89-93 (head 1x1 convs); LayerNorm2d = LN over channels, eps 1e-6 (timm).
+// :70-76 / :89-93 (head 1x1 convs); LayerNorm2d = LN over channels, eps 1e-6 (timm);
+// SqueezeExcitation(256, 128) = sigmoid(fc2(relu(fc1(avgpool)))) * x (torchvision).
 //
 // GEMM view of one 3x3 layer: M = 64 * boards, N = 256 output channels, K = 9 taps x Cin.
 //   A (activations, bf16 NHWC [board][rank][file][C]) is never materialised as im2col: for
@@ -10,15 +12,22 @@
 //   2 boards} at coordinates (64*kc, dx, dy, board0); ranks/files outside [0,8) are
 //   zero-filled by the TMA unit, which IS the conv padding.  The box lands in shared memory
 //   as 128 rows x 128 bytes, 128B-swizzled = the canonical K-major UMMA operand layout.
-//   B (weights, bf16 [tap][cout][cin]) is a plain 2-D box {64, 256}.
+//   B (weights, bf16 [tap][cout][cin]) is a plain 2-D box.
 //   D accumulates in TMEM (128 lanes x 256 fp32 columns per tile, two tiles = all 512
 //   columns, so the epilogue of tile i overlaps the MMAs of tile i+1).
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (each owns the TMEM lane quadrant warp_id % 4; one thread = one
-// (board, square) row, so LayerNorm over channels is a per-thread reduction).
-// The same kernel, with other template arguments, runs the 1x1 head convolutions, the
-// 256->73 policy convolution (N = 80) with its LayerNorm(73), and the 16384->128 value FC
-// as a split-K GEMM whose rows are boards.
+// One kernel template, tc_gemm_kernel<BN, EPI, A4D, CTA2, TOWER>:
+//   * CTA2: clusters of two CTAs issue tcgen05.mma.cta_group::2 (256-row tiles, each CTA
+//     stages its 128 rows of A and half of the weight rows);
+//   * TOWER: the stem, all residual blocks and the two 256-wide head 1x1 convolutions run
+//     in ONE persistent launch; a tile's layers are chained by a per-tile mbarrier inside
+//     the CTA (boards never interact inside the tower), tiles are carried through all
+//     layers in groups of 3-4 so that layer outputs are re-read from L2;
+//   * the narrow head GEMMs (256->73 with LayerNorm(73); value FC 16384->128 as a split-K
+//     GEMM whose rows are boards) are single-CTA instantiations of the same kernel.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..9 = epilogue (two warps per TMEM lane quadrant, each owning 128 of the 256
+// columns of its 32 rows; one thread = one (board, square) row, so LayerNorm over channels
+// is a per-thread reduction plus one exchange with the sibling warp).
 #include <cuda.h>
 
 #include <cstdio>
@@ -35,11 +44,7 @@ constexpr int TC_BN = 256;
 constexpr int TC_BK = 64;
 constexpr int TC_STAGES = 4;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KB
-constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;  // 32 KB
-constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 constexpr int TC_THREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
-constexpr int TC_SMEM_PARAMS = 3 * TC_BN * 4;
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_SMEM_PARAMS + 256 + 1024;
 
 // ---- PTX wrappers ------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }

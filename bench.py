@@ -237,6 +237,9 @@ def main():
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline work (rank 0, N=1)")
     ap.add_argument("--selfplay-moves", type=int, default=4096, help="plies of batched self-play to time (0 = skip)")
+    ap.add_argument("--leaves-per-tree", type=int, default=1,
+                    help="self-play leg: leaves per tree per batch (1 = the reference's sequential search; "
+                         ">1 = virtual loss, leaves/K trees)")
     ap.add_argument("--threads", type=int, default=0, help="host worker threads for self-play (0 = cores / ranks)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -344,12 +347,14 @@ def main():
     if args.selfplay_moves > 0:
         nthr = args.threads or max(1, (os.cpu_count() or 8) // max(world, 1))
         eng_sp = scb200.Engine(blob, local_rank, mode, B)
-        sp = scb200.SelfPlay(eng_sp, n_trees=B, rollout_num=180, num_steps=150, cpuct=2.5, epsilon=0.15,
+        kl = max(1, args.leaves_per_tree)
+        sp = scb200.SelfPlay(eng_sp, n_trees=max(2, B // kl), leaves_per_tree=kl, rollout_num=180, num_steps=150, cpuct=2.5, epsilon=0.15,
                              with_noise=True, temperature_switch=4, temperature=0.0, seed=shard.rank_seed(100, rank),
                              n_threads=nthr, pipeline_groups=2)
         barrier()
         sp_stats = sp.run(max_moves=args.selfplay_moves)
         sp_stats["threads"] = nthr
+        sp_stats["trees"] = max(2, B // kl)
         sp.close()
         eng_sp.close()
 
@@ -414,8 +419,11 @@ def main():
         if sp_stats:
             line["selfplay"] = {
                 "moves_per_s": sp_moves / sp_secs, "leaf_evals_per_s": sp_evals / sp_secs, "unit": "plies/s at 180 rollouts/move",
-                "config": "2048 concurrent trees per GPU, rollout-num 180, cpuct 2.5, temperature-switch 4, epsilon 0.15 noise on, "
-                          "two pipeline groups of 1024 leaves, host threads = %d per GPU" % sp_stats["threads"],
+                "config": "%d concurrent trees per GPU x %d leaves per tree per batch%s, rollout-num 180, cpuct 2.5, "
+                          "temperature-switch 4, epsilon 0.15 noise on, two pipeline groups, host threads = %d per GPU"
+                          % (sp_stats["trees"], max(1, args.leaves_per_tree),
+                             "" if args.leaves_per_tree <= 1 else " (virtual loss; not the reference's visit counts)",
+                             sp_stats["threads"]),
                 "plies": sp_moves, "seconds": sp_secs, "device_wait_frac_rank0": sp_stats["wait_seconds"] / sp_stats["seconds"],
                 "games_finished_rank0": sp_stats["games_finished"],
             }

@@ -164,6 +164,9 @@ typedef struct sc_selfplay_config {
     int32_t evaluator;          /* 0 = the engine (GPU); 1 = position-hash stand-in (test hook, no engine) */
     int32_t pipeline_groups;    /* 1 or 2: trees are split in groups that alternate between host and device */
     int32_t keep_traces;        /* keep the traces of finished games in memory (sc_selfplay_trace_json) */
+    int32_t leaves_per_tree;    /* 0/1: one leaf per tree per batch, the reference's exact sequential search.
+                                   K > 1: up to K leaves per tree per batch; in-flight paths carry a virtual loss
+                                   (one visit lost by the mover).  Not visit-count identical to the reference. */
 } sc_selfplay_config;
 
 typedef struct sc_selfplay_stats {

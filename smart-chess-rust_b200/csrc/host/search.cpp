@@ -148,6 +148,7 @@ struct Node {
     int32_t parent;
     int32_t first_child;
     int32_t n_children;
+    uint8_t pending;     // an evaluation of this (unexpanded) node is in flight
 };
 
 struct TraceStep {
@@ -171,10 +172,20 @@ struct Tree {
     Game game;         // state at the search root + scratch pushes along the current path
     int root_ply = 0;
     Rng rng;
-    // current rollout
-    std::vector<int> path;
-    int pending_leaf = -1;   // node waiting for the network
-    MoveList pending_moves;
+    // rollouts whose leaf is waiting for the network: one per step in the reference-exact mode,
+    // up to leaves_per_tree with virtual loss
+    struct Pending {
+        int leaf = -1;
+        std::vector<int> path;
+        MoveList moves;
+        int child_color = 0;
+        int slot = -1;     // row of the group's batch buffers
+        bool vloss = false;
+        float value = 0.f;  // hash evaluator: result computed at collection time
+        float pri[256];
+    };
+    std::vector<Pending> pend;
+    int n_pend = 0;
     // current search / game
     int rollouts_done = 0;
     int move_index = 0;      // `i` of the self-play loop (main.rs:168)
@@ -196,7 +207,7 @@ struct Tree {
         root_ply = 0;
         rollouts_done = 0;
         move_index = 0;
-        pending_leaf = -1;
+        n_pend = 0;
         game_over = false;
         trace = TraceRec();
         (void)seed;
@@ -222,6 +233,8 @@ struct sc_selfplay {
         int ticket = -1;
         bool inflight = false;
         sc_engine *eng = nullptr;  // engine the in-flight batch was submitted to
+        std::atomic<int> n_used{0};  // rows of the batch buffers filled by the current step (dense)
+        int capacity = 0;            // trees of the group x leaves_per_tree
     } groups[2];
     int n_groups = 1;
     // stats
@@ -342,20 +355,32 @@ void pack_leaf(const Tree &t, int node_depth, sc_position *out)
     out->n_hist = n_hist;
 }
 
-// expansion (src/mcts.rs:269-283) + backward (src/mcts.rs:90-98) for the pending leaf
-void finish_rollout(sc_selfplay *sp, Tree &t, const float *priors, float value)
+// virtual loss: while an evaluation is in flight every node of its path (below the root) looks like one more
+// visit that ended in a loss for the player who chose it, so the next descent of the same step goes elsewhere
+inline void apply_vloss(Tree &t, const std::vector<int> &path, float sign)
 {
-    const int leaf = t.pending_leaf;
-    const int n = t.pending_moves.n;
+    for (size_t i = 1; i < path.size(); i++) {
+        Node &c = t.nodes[path[i]];
+        c.n += (int)sign;
+        c.q += sign * (c.step_color == WHITE ? 1.f : -1.f);  // mover was Black iff White is to move after it
+    }
+}
+
+// expansion (src/mcts.rs:269-283) + backward (src/mcts.rs:90-98) for one pending leaf
+void finish_rollout(sc_selfplay *sp, Tree &t, Tree::Pending &P, const float *priors, float value)
+{
+    const int leaf = P.leaf;
+    const int n = P.moves.n;
+    if (P.vloss) apply_vloss(t, P.path, -1.f);
+    t.nodes[leaf].pending = 0;
     if (n > 0) {
         const int first = (int)t.nodes.size();
-        const int child_color = !t.game.cur.turn;
         const int depth = t.nodes[leaf].depth + 1;
         t.nodes.resize(first + n);
         for (int i = 0; i < n; i++) {
             Node &c = t.nodes[first + i];
-            c.mv = t.pending_moves.m[i];
-            c.step_color = (uint8_t)child_color;
+            c.mv = P.moves.m[i];
+            c.step_color = (uint8_t)P.child_color;
             c.depth = depth;
             c.q = 0.f;
             c.n = 0;
@@ -364,28 +389,28 @@ void finish_rollout(sc_selfplay *sp, Tree &t, const float *priors, float value)
             c.parent = leaf;
             c.first_child = -1;
             c.n_children = 0;
+            c.pending = 0;
         }
         t.nodes[leaf].first_child = first;
         t.nodes[leaf].n_children = n;
     }
-    for (int idx : t.path) {
+    for (int idx : P.path) {
         t.nodes[idx].n += 1;
         t.nodes[idx].q += value;
     }
-    // unwind the scratch pushes back to the search root
-    while (t.game.ply() > t.root_ply) t.game.pop();
-    t.pending_leaf = -1;
     t.rollouts_done++;
     sp->rollouts.fetch_add(1, std::memory_order_relaxed);
 }
 
 // one `select` descent (src/mcts.rs:132-227). Returns true if the leaf needs the network.
-bool descend(sc_selfplay *sp, Tree &t)
+// Returns 1 if the leaf needs the network, 0 if the rollout finished at a terminal leaf, -1 if it ran into a
+// leaf whose evaluation is already in flight (virtual-loss mode only; nothing was changed).
+int descend(sc_selfplay *sp, Tree &t, Tree::Pending &P)
 {
     const sc_selfplay_config &cfg = sp->cfg;
-    t.path.clear();
+    P.path.clear();
     int node = t.root;
-    t.path.push_back(node);
+    P.path.push_back(node);
     for (;;) {
         Node &nd = t.nodes[node];
         if (nd.n_children == 0) break;  // leaf: unexplored or terminal
@@ -399,7 +424,7 @@ bool descend(sc_selfplay *sp, Tree &t)
             for (int i = 0; i < nd.n_children; i++) tot += ch[i].n;
             const float sq = std::sqrt((float)tot);
             const float *pri = nullptr;
-            const bool is_root = t.path.size() == 1;
+            const bool is_root = P.path.size() == 1;
             if (is_root && cfg.with_noise && nd.n_children >= 2) {
                 // fresh Dirichlet(0.3) sample on every rollout (src/mcts.rs:123-130, 171-184)
                 t.noisy.resize(nd.n_children);
@@ -428,20 +453,30 @@ bool descend(sc_selfplay *sp, Tree &t)
             best = nd.first_child + bi;
         }
         t.game.push(t.nodes[best].mv);
-        t.path.push_back(best);
+        P.path.push_back(best);
         node = best;
     }
     // `predict` at the leaf: legal moves; none -> terminal value without the network
-    t.pending_leaf = node;
-    t.game.cur.legal_moves(t.pending_moves);
-    if (t.pending_moves.n == 0) {
+    auto unwind = [&]() {
+        while (t.game.ply() > t.root_ply) t.game.pop();
+    };
+    if (t.nodes[node].pending) {
+        unwind();
+        return -1;
+    }
+    P.leaf = node;
+    P.vloss = false;
+    P.child_color = !t.game.cur.turn;
+    t.game.cur.legal_moves(P.moves);
+    if (P.moves.n == 0) {
         float v = 0.f;
         if (t.game.cur.in_check()) v = t.game.cur.turn == WHITE ? -1.f : 1.f;  // winner = side that mated
         sp->terminal_evals.fetch_add(1, std::memory_order_relaxed);
-        finish_rollout(sp, t, nullptr, v);
-        return false;
+        unwind();
+        finish_rollout(sp, t, P, nullptr, v);
+        return 0;
     }
-    return true;
+    return 1;  // the game is left AT the leaf: the caller packs the position, then unwinds
 }
 
 // the move choice of `mcts::step` (src/mcts.rs:292-328) + the loop body of main.rs:198-228.
@@ -629,47 +664,96 @@ void play_move_arena(sc_selfplay *sp, Tree &t)
     }
 }
 
-// arena: a tree only searches the ply its pipeline group is at, then waits for the others
-bool advance_tree_arena(sc_selfplay *sp, Tree &t, int group_ply, sc_position *pos, sc_move *moves, int32_t *cnt,
-                        const float *priors, const float *value)
+// Collects up to leaves_per_tree leaves of one tree into the group's batch buffers.  Returns the number
+// collected.  `may_search` is evaluated before every descent.
+struct BatchOut {
+    sc_position *pos;
+    sc_move *moves;
+    int32_t *cnt;
+    std::atomic<int> *n_used;
+};
+
+template <typename Ready>
+int collect_leaves(sc_selfplay *sp, Tree &t, const BatchOut &out, Ready finish_move)
 {
-    if (t.pending_leaf >= 0) finish_rollout(sp, t, priors, *value);
-    *cnt = 0;
+    const int K = sp->cfg.leaves_per_tree > 1 ? sp->cfg.leaves_per_tree : 1;
+    if ((int)t.pend.size() < K) t.pend.resize(K);
+    int collected = 0;
     for (;;) {
-        if (!t.active || t.game_over || t.move_index > group_ply) return false;
-        if (t.rollouts_done >= sp->cfg.rollout_num) {
-            play_move_arena(sp, t);
+        if (t.rollouts_done + collected >= sp->cfg.rollout_num) {
+            if (collected > 0) break;           // the move's last evaluations are in flight
+            if (!finish_move()) break;          // move played / game over / tree waits
             continue;
         }
-        if (descend(sp, t)) {
-            if (sp->cfg.evaluator == 1) {
-                float pri[256];
-                float v = hash_eval(t.game.cur, t.pending_moves.m, t.pending_moves.n, pri);
-                sp->leaf_evals.fetch_add(1, std::memory_order_relaxed);
-                finish_rollout(sp, t, pri, v);
-                continue;
-            }
-            pack_leaf(t, t.nodes[t.pending_leaf].depth, pos);
-            for (int i = 0; i < t.pending_moves.n; i++) moves[i] = sc_move{t.pending_moves.m[i].from, t.pending_moves.m[i].to, t.pending_moves.m[i].promo, 0};
-            *cnt = t.pending_moves.n;
-            sp->leaf_evals.fetch_add(1, std::memory_order_relaxed);
-            return true;
+        if (collected >= K) break;
+        Tree::Pending &P = t.pend[collected];
+        const int r = descend(sp, t, P);
+        if (r == 0) continue;                    // terminal leaf: rollout already backed up
+        if (r < 0) break;                        // ran into an in-flight leaf: wait for it
+        if (sp->cfg.evaluator == 1) {
+            P.value = hash_eval(t.game.cur, P.moves.m, P.moves.n, P.pri);
+        } else {
+            const int s = out.n_used->fetch_add(1, std::memory_order_relaxed);
+            P.slot = s;
+            pack_leaf(t, t.nodes[P.leaf].depth, out.pos + s);
+            sc_move *mv = out.moves + (size_t)s * SC_MAX_MOVES;
+            for (int i = 0; i < P.moves.n; i++) mv[i] = sc_move{P.moves.m[i].from, P.moves.m[i].to, P.moves.m[i].promo, 0};
+            out.cnt[s] = P.moves.n;
         }
+        while (t.game.ply() > t.root_ply) t.game.pop();
+        sp->leaf_evals.fetch_add(1, std::memory_order_relaxed);
+        t.nodes[P.leaf].pending = 1;
+        if (K > 1) {
+            apply_vloss(t, P.path, 1.f);
+            P.vloss = true;
+        }
+        collected++;
+        if (sp->cfg.evaluator == 1 && K == 1) {
+            // reference-exact mode on the stand-in evaluator: finish at once, keep going
+            finish_rollout(sp, t, P, P.pri, P.value);
+            collected = 0;
+        }
+    }
+    if (sp->cfg.evaluator == 1) {
+        for (int i = 0; i < collected; i++) finish_rollout(sp, t, t.pend[i], t.pend[i].pri, t.pend[i].value);
+        if (collected > 0) return -1;            // stand-in evaluator: call again, nothing is in flight
+        return 0;
+    }
+    t.n_pend = collected;
+    return collected;
+}
+
+void finish_pending(sc_selfplay *sp, Tree &t, const float *priors, const float *value)
+{
+    for (int i = 0; i < t.n_pend; i++) {
+        Tree::Pending &P = t.pend[i];
+        finish_rollout(sp, t, P, priors + (size_t)P.slot * SC_MAX_MOVES, value[P.slot]);
+    }
+    t.n_pend = 0;
+}
+
+// arena: a tree only searches the ply its pipeline group is at, then waits for the others
+void advance_tree_arena(sc_selfplay *sp, Tree &t, int group_ply, const BatchOut &out, const float *priors,
+                        const float *value)
+{
+    finish_pending(sp, t, priors, value);
+    for (;;) {
+        if (!t.active || t.game_over || t.move_index > group_ply) return;
+        const int r = collect_leaves(sp, t, out, [&]() {
+            play_move_arena(sp, t);
+            return t.active && !t.game_over && t.move_index <= group_ply;
+        });
+        if (r >= 0) return;
     }
 }
 
-// advance one tree until it has a leaf for the network (true) or has no more work (false)
-bool advance_tree(sc_selfplay *sp, Tree &t, sc_position *pos, sc_move *moves, int32_t *cnt, const float *priors,
-                  const float *value)
+// advance one tree until it has leaves for the network or has no more work
+void advance_tree(sc_selfplay *sp, Tree &t, const BatchOut &out, const float *priors, const float *value)
 {
-    if (t.pending_leaf >= 0) {
-        if (sp->cfg.evaluator == 0)
-            finish_rollout(sp, t, priors, *value);
-    }
-    *cnt = 0;
+    finish_pending(sp, t, priors, value);
     for (;;) {
-        if (!t.active) return false;
-        if (t.rollouts_done >= sp->cfg.rollout_num) {
+        if (!t.active) return;
+        const int r = collect_leaves(sp, t, out, [&]() {
             if (!play_move(sp, t)) {
                 // start the next game in this slot if the run still needs games
                 int64_t started = sp->games_started.fetch_add(1) + 1;
@@ -683,27 +767,9 @@ bool advance_tree(sc_selfplay *sp, Tree &t, sc_position *pos, sc_move *moves, in
                 t.active = false;
                 return false;
             }
-            continue;
-        }
-        if (descend(sp, t)) {
-            if (sp->cfg.evaluator == 1) {
-                float pri[256];
-                float v = hash_eval(t.game.cur, t.pending_moves.m, t.pending_moves.n, pri);
-                sp->leaf_evals.fetch_add(1, std::memory_order_relaxed);
-                finish_rollout(sp, t, pri, v);
-                continue;
-            }
-            pack_leaf(t, t.nodes[t.pending_leaf].depth, pos);
-            for (int i = 0; i < t.pending_moves.n; i++) {
-                moves[i].from = t.pending_moves.m[i].from;
-                moves[i].to = t.pending_moves.m[i].to;
-                moves[i].promo = t.pending_moves.m[i].promo;
-                moves[i].pad = 0;
-            }
-            *cnt = t.pending_moves.n;
-            sp->leaf_evals.fetch_add(1, std::memory_order_relaxed);
             return true;
-        }
+        });
+        if (r >= 0) return;
     }
 }
 
@@ -712,14 +778,13 @@ void run_group_slice(sc_selfplay *sp, int g, int worker, int n_workers)
     sc_selfplay::Group &G = sp->groups[g];
     const int per = (G.count + n_workers - 1) / n_workers;
     const int lo = worker * per, hi = std::min(G.count, lo + per);
+    const BatchOut out{G.pos, G.moves, G.cnt, &G.n_used};
     for (int i = lo; i < hi; i++) {
         Tree &t = sp->trees[G.first + i];
         if (sp->arena)
-            advance_tree_arena(sp, t, sp->group_ply[g], G.pos + i, G.moves + (size_t)i * SC_MAX_MOVES, G.cnt + i,
-                               G.priors + (size_t)i * SC_MAX_MOVES, G.value + i);
+            advance_tree_arena(sp, t, sp->group_ply[g], out, G.priors, G.value);
         else
-            advance_tree(sp, t, G.pos + i, G.moves + (size_t)i * SC_MAX_MOVES, G.cnt + i,
-                         G.priors + (size_t)i * SC_MAX_MOVES, G.value + i);
+            advance_tree(sp, t, out, G.priors, G.value);
     }
 }
 
@@ -774,6 +839,11 @@ int sc_selfplay_create(sc_engine *e, const sc_selfplay_config *cfg, sc_selfplay 
         set_error("sc_selfplay_create: bad argument");
         return SC_E_INVAL;
     }
+    if (cfg->leaves_per_tree < 0 || cfg->leaves_per_tree > 64) {
+        set_error("sc_selfplay_create: leaves_per_tree must be 0..64");
+        return SC_E_INVAL;
+    }
+    const int kleaves = cfg->leaves_per_tree > 1 ? cfg->leaves_per_tree : 1;
     sc_selfplay *sp = new sc_selfplay();
     sp->eng = e;
     sp->cfg = *cfg;
@@ -787,14 +857,14 @@ int sc_selfplay_create(sc_engine *e, const sc_selfplay_config *cfg, sc_selfplay 
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
         const int wave = 2 * sms;
-        if (size0 >= wave) size0 = size0 / wave * wave;
+        if (size0 * kleaves >= wave) size0 = std::max(1, size0 * kleaves / wave * wave / kleaves);
     }
     if (e) {
         int mb = 0;
         sc_info(e, nullptr, &mb, nullptr);
-        if (std::max(size0, cfg->n_trees - size0) > mb) {
+        if (std::max(size0, cfg->n_trees - size0) * kleaves > mb) {
             delete sp;
-            set_error("sc_selfplay_create: trees per pipeline group exceed the engine's max_batch");
+            set_error("sc_selfplay_create: trees per pipeline group x leaves_per_tree exceed the engine's max_batch");
             return SC_E_INVAL;
         }
     }
@@ -807,25 +877,26 @@ int sc_selfplay_create(sc_engine *e, const sc_selfplay_config *cfg, sc_selfplay 
         sc_selfplay::Group &G = sp->groups[g];
         G.first = g == 0 ? 0 : size0;
         G.count = sp->n_groups == 1 ? cfg->n_trees : (g == 0 ? size0 : cfg->n_trees - size0);
-        const size_t nm = (size_t)G.count * SC_MAX_MOVES;
+        G.capacity = G.count * kleaves;
+        const size_t nm = (size_t)G.capacity * SC_MAX_MOVES;
         if (cfg->evaluator == 0) {
-            if (cudaMallocHost(&G.pos, sizeof(sc_position) * G.count) != cudaSuccess ||
+            if (cudaMallocHost(&G.pos, sizeof(sc_position) * G.capacity) != cudaSuccess ||
                 cudaMallocHost(&G.moves, sizeof(sc_move) * nm) != cudaSuccess ||
-                cudaMallocHost(&G.cnt, sizeof(int32_t) * G.count) != cudaSuccess ||
+                cudaMallocHost(&G.cnt, sizeof(int32_t) * G.capacity) != cudaSuccess ||
                 cudaMallocHost(&G.priors, sizeof(float) * nm) != cudaSuccess ||
-                cudaMallocHost(&G.value, sizeof(float) * G.count) != cudaSuccess) {
+                cudaMallocHost(&G.value, sizeof(float) * G.capacity) != cudaSuccess) {
                 set_error("sc_selfplay_create: pinned allocation failed");
                 sc_selfplay_destroy(sp);
                 return SC_E_CUDA;
             }
         } else {
-            G.pos = new sc_position[G.count];
+            G.pos = new sc_position[G.capacity];
             G.moves = new sc_move[nm];
-            G.cnt = new int32_t[G.count];
+            G.cnt = new int32_t[G.capacity];
             G.priors = new float[nm];
-            G.value = new float[G.count];
+            G.value = new float[G.capacity];
         }
-        memset(G.cnt, 0, sizeof(int32_t) * G.count);
+        memset(G.cnt, 0, sizeof(int32_t) * G.capacity);
     }
     const int nt = cfg->n_threads > 1 ? cfg->n_threads - 1 : 0;  // pool threads next to the calling thread
     for (int w = 0; w < nt; w++) sp->workers.emplace_back(worker_main, sp, w, nt);
@@ -847,7 +918,7 @@ int sc_arena_create(sc_engine *white, sc_engine *black, const sc_selfplay_config
         int mb = 0;
         sc_info(black, nullptr, &mb, nullptr);
         int need = 0;
-        for (int g = 0; g < (*out)->n_groups; g++) need = std::max(need, (*out)->groups[g].count);
+        for (int g = 0; g < (*out)->n_groups; g++) need = std::max(need, (*out)->groups[g].capacity);
         if (need > mb) {
             sc_selfplay_destroy(*out);
             *out = nullptr;
@@ -887,9 +958,9 @@ int sc_selfplay_run(sc_selfplay *sp, int64_t max_games, int64_t max_moves, doubl
                 G.inflight = false;
                 if (rc != SC_OK) break;
             }
+            G.n_used.store(0, std::memory_order_relaxed);
             parallel_advance(sp, g);
-            int n_leaves = 0;
-            for (int i = 0; i < G.count; i++) n_leaves += G.cnt[i] > 0;
+            int n_leaves = G.n_used.load(std::memory_order_relaxed);
             if (sp->arena) {
                 // nobody produced a leaf: the whole group finished this ply -> next ply, or next round
                 for (int guard = 0; n_leaves == 0 && guard < 1000000; guard++) {
@@ -917,7 +988,7 @@ int sc_selfplay_run(sc_selfplay *sp, int64_t max_games, int64_t max_moves, doubl
                         sp->group_ply[g] = 0;
                     }
                     parallel_advance(sp, g);
-                    for (int i = 0; i < G.count; i++) n_leaves += G.cnt[i] > 0;
+                    n_leaves = G.n_used.load(std::memory_order_relaxed);
                     if (sp->cfg.evaluator == 1) {
                         // hash evaluator never leaves a leaf pending: keep stepping plies until the round is over
                         bool left = false;
@@ -928,7 +999,7 @@ int sc_selfplay_run(sc_selfplay *sp, int64_t max_games, int64_t max_moves, doubl
             }
             if (sp->cfg.evaluator == 0 && n_leaves > 0) {
                 sc_engine *use = sp->arena && (sp->group_ply[g] & 1) ? sp->eng_black : sp->eng;
-                rc = sc_eval_submit(use, G.count, G.pos, G.moves, G.cnt, G.priors, G.value, nullptr, &G.ticket);
+                rc = sc_eval_submit(use, n_leaves, G.pos, G.moves, G.cnt, G.priors, G.value, nullptr, &G.ticket);
                 G.inflight = rc == SC_OK;
                 G.eng = use;
                 sp->batches++;

@@ -32,7 +32,8 @@ class SelfPlayConfig(C.Structure):
     _fields_ = [("n_trees", C.c_int32), ("rollout_num", C.c_int32), ("num_steps", C.c_int32), ("cpuct", C.c_float),
                 ("epsilon", C.c_float), ("with_noise", C.c_int32), ("temperature_switch", C.c_int32),
                 ("temperature", C.c_float), ("seed", C.c_uint64), ("n_threads", C.c_int32), ("evaluator", C.c_int32),
-                ("pipeline_groups", C.c_int32), ("keep_traces", C.c_int32)]
+                ("pipeline_groups", C.c_int32), ("keep_traces", C.c_int32),
+                ("leaves_per_tree", C.c_int32)]
 
 
 class SelfPlayStats(C.Structure):
@@ -258,14 +259,14 @@ class SelfPlay:
 
     def __init__(self, engine, n_trees=2048, rollout_num=180, num_steps=150, cpuct=2.5, epsilon=0.15,
                  with_noise=True, temperature_switch=4, temperature=0.0, seed=0, n_threads=0, evaluator="engine",
-                 pipeline_groups=2, keep_traces=False, black_engine=None, arena=False):
+                 pipeline_groups=2, keep_traces=False, black_engine=None, arena=False, leaves_per_tree=1):
         import json as _json
 
         self._json = _json
         L = load_library()
         cfg = SelfPlayConfig(n_trees, rollout_num, num_steps, cpuct, epsilon, int(with_noise), temperature_switch,
                              temperature, seed, n_threads, 0 if evaluator == "engine" else 1, pipeline_groups,
-                             int(keep_traces))
+                             int(keep_traces), int(leaves_per_tree))
         h = C.c_void_p()
         self._engine = (engine, black_engine)  # keep alive
         if arena:
@@ -321,11 +322,12 @@ class Arena(SelfPlay):
     """`play --black-type nn` for n_trees games at once (src/play.rs:241-343): `white` moves on even plies."""
 
     def __init__(self, white, black, n_trees=256, rollout=100, cpuct=1.5, temperature=0.0, temperature_switch=8,
-                 max_plies=200, seed=0, n_threads=0, evaluator="engine", pipeline_groups=2, keep_traces=False):
+                 max_plies=200, seed=0, n_threads=0, evaluator="engine", pipeline_groups=2, keep_traces=False,
+                 leaves_per_tree=1):
         super().__init__(white, n_trees=n_trees, rollout_num=rollout, num_steps=max_plies, cpuct=cpuct,
                          with_noise=False, temperature_switch=temperature_switch, temperature=temperature, seed=seed,
                          n_threads=n_threads, evaluator=evaluator, pipeline_groups=pipeline_groups,
-                         keep_traces=keep_traces, black_engine=black, arena=True)
+                         keep_traces=keep_traces, black_engine=black, arena=True, leaves_per_tree=leaves_per_tree)
 
 
 def elo(total: int, wins: int, losses: int) -> float:

@@ -158,3 +158,44 @@ def test_arena_two_networks(co, small_net, tmp_path):
             assert tr["steps"][1][2] in by_first[mv]
     ea.close()
     eb.close()
+
+
+def test_virtual_loss_mode_on_engine(co, small_net):
+    """leaves_per_tree = 4: 64 trees fill a 256-row batch.  Same invariants as the CPU test, now with the
+    engine in the loop and dense batch rows handed out across host threads; the result must not
+    depend on the thread count (rows are assigned in a different order, results per row are not)."""
+    import scb200
+
+    sd, blob = small_net
+
+    def run(threads):
+        eng = scb200.Engine(blob, 0, scb200.SC_MODE_BF16, 256)
+        sp = scb200.SelfPlay(eng, n_trees=64, rollout_num=33, num_steps=12, cpuct=2.5, with_noise=False,
+                             temperature_switch=0, temperature=0.0, keep_traces=True, pipeline_groups=2,
+                             n_threads=threads, leaves_per_tree=4)
+        st = sp.run(max_games=64)
+        trs = [sp.trace(k) for k in range(64)]
+        sp.close()
+        eng.close()
+        return st, trs
+
+    st, trs = run(1)
+    assert st["games_finished"] == 64 and st["moves"] == 64 * 12
+    assert st["rollouts"] == 64 * 12 * 33 == st["leaf_evals"] + st["terminal_evals"]
+    assert st["batches"] < 64 * 12 * 33 / 64 / 2       # several leaves per tree per batch
+    for tr in trs[::7]:
+        g = co.Game()
+        for mv, q, ch in tr["steps"]:
+            assert [c[0] for c in ch] == g.legal_uci()
+            assert sum(c[1] for c in ch) == 32
+            assert all(c[1] >= 0 and abs(c[2]) <= c[1] + 1e-4 for c in ch)
+            g.push(mv)
+    st4, trs4 = run(4)
+    assert trs4 == trs
+
+    with pytest.raises(RuntimeError):
+        eng = scb200.Engine(blob, 0, scb200.SC_MODE_BF16, 64)
+        try:
+            scb200.SelfPlay(eng, n_trees=64, rollout_num=8, num_steps=2, pipeline_groups=1, leaves_per_tree=4)
+        finally:
+            eng.close()

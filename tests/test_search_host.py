@@ -234,3 +234,40 @@ def test_root_noise_sampler_moments():
     ref = np.random.RandomState(0).dirichlet([alpha] * n, size=reps)
     assert abs(np.median(xs.max(1)) - np.median(ref.max(1))) < 0.02
     assert abs(np.mean(xs < 1e-3) - np.mean(ref < 1e-3)) < 0.02
+
+
+def test_virtual_loss_mode_invariants(co):
+    """leaves_per_tree > 1 is not the reference's sequential search (in-flight paths carry a virtual
+    loss), so it is checked through invariants: every move still gets exactly rollout_num rollouts,
+    no virtual visit survives into the recorded statistics, |q| <= n, the children are the legal moves
+    in python-chess order, and the run is deterministic and independent of threads."""
+    import scb200
+
+    plies, rollouts = 16, 50
+
+    def run(k, threads, trees=4):
+        sp = scb200.SelfPlay(None, n_trees=trees, rollout_num=rollouts, num_steps=plies, cpuct=2.5, with_noise=False,
+                             temperature_switch=0, temperature=0.0, evaluator="hash", keep_traces=True,
+                             n_threads=threads, leaves_per_tree=k)
+        st = sp.run(max_games=trees)
+        tr = [sp.trace(i) for i in range(trees)]
+        sp.close()
+        return st, tr
+
+    st1, tr1 = run(1, 0)
+    for k in (2, 4, 8):
+        st, tr = run(k, 0)
+        assert st["games_finished"] == 4 and st["moves"] == 4 * plies
+        assert st["rollouts"] == 4 * plies * rollouts
+        for t in tr:
+            g = co.Game()
+            for mv, q, ch in t["steps"]:
+                assert [c[0] for c in ch] == g.legal_uci()
+                assert sum(c[1] for c in ch) == rollouts - 1        # first rollout expands the root
+                assert all(c[1] >= 0 and abs(c[2]) <= c[1] + 1e-4 for c in ch)
+                g.push(mv)
+        st_b, tr_b = run(k, 3)
+        assert tr_b == tr
+        # the search differs from K = 1 only through the order in which leaves are evaluated
+        same = sum(a["steps"][0][0] == b["steps"][0][0] for a, b in zip(tr1, tr))
+        assert same >= 1

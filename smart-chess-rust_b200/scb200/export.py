@@ -24,9 +24,23 @@ MAGIC = b"SCB2WTS1"
 
 
 def _normalise_state_dict(obj):
+    """Raw state_dict, Lightning checkpoint (py/module.py:172-177 chops the first name component),
+    or the state_dict of a torch.compile'd / scripted module (`_orig_mod.` prefix)."""
+    if hasattr(obj, "state_dict") and not isinstance(obj, dict):
+        obj = obj.state_dict()
     if isinstance(obj, dict) and "pytorch-lightning_version" in obj:
-        return {k.split(".", 1)[1]: v for k, v in obj["state_dict"].items()}
-    return obj
+        obj = {k.split(".", 1)[1]: v for k, v in obj["state_dict"].items()}
+    sd = {(k[len("_orig_mod."):] if k.startswith("_orig_mod.") else k): v for k, v in obj.items()}
+    if any(k.endswith("running_mean") for k in sd):
+        # NormTable["BatchNorm"] (py/module.py:6-9) is never built by load_model (py/module.py:199)
+        raise ValueError("BatchNorm checkpoints are not supported: the engine implements the LayerNorm network "
+                         "that the reference's load_model builds")
+    required = ["conv_block.0.weight", "conv_block.0.bias", "conv_block.1.weight", "policy_head.model.2.weight",
+                "value_head.ffn.0.weight", "value_head.ffn.2.weight"]
+    missing = [k for k in required if k not in sd]
+    if missing:
+        raise ValueError("not a ChessModule state_dict, missing: " + ", ".join(missing))
+    return sd
 
 
 def write_blob(state_dict, path: str) -> int:
@@ -66,7 +80,11 @@ def export_checkpoint(checkpoint_path: str, out_path: str) -> int:
     """`scripts/export_model.py -c ckpt` equivalent for the .scw blob."""
     import torch
 
-    ckpt = torch.load(checkpoint_path, weights_only=True, map_location="cpu")
+    try:
+        ckpt = torch.load(checkpoint_path, weights_only=True, map_location="cpu")
+    except Exception:
+        # a TorchScript export of the reference (py/export.py:36-65) carries the same parameter names
+        ckpt = torch.jit.load(checkpoint_path, map_location="cpu").state_dict()
     return write_blob(ckpt, out_path)
 
 

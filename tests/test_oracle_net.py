@@ -70,3 +70,20 @@ def test_blob_roundtrip(tmp_path):
     p2 = str(tmp_path / "w2.scw")
     scb200.write_blob(wrapped, p2)
     assert open(p2, "rb").read() == raw
+    # a torch.compile'd module's names carry `_orig_mod.` (load_model(compile=True), py/module.py:207-208)
+    p3 = str(tmp_path / "w3.scw")
+    scb200.write_blob({"_orig_mod." + k: v for k, v in sd.items()}, p3)
+    assert open(p3, "rb").read() == raw
+    # torch.save'd checkpoint through the CLI path
+    ck = str(tmp_path / "c.ckpt")
+    torch.save(wrapped, ck)
+    p4 = str(tmp_path / "w4.scw")
+    scb200.export_checkpoint(ck, p4)
+    assert open(p4, "rb").read() == raw
+    # inputs the engine cannot run are refused at export time, not at load time
+    bn = dict(sd)
+    bn["conv_block.1.running_mean"] = torch.zeros(256)
+    with pytest.raises(ValueError, match="BatchNorm"):
+        scb200.write_blob(bn, p3)
+    with pytest.raises(ValueError, match="missing"):
+        scb200.write_blob({"foo": torch.zeros(1)}, p3)

@@ -200,3 +200,47 @@ def test_virtual_loss_mode_on_engine(co, small_net):
             scb200.SelfPlay(eng, n_trees=64, rollout_num=8, num_steps=2, pipeline_groups=1, leaves_per_tree=4)
         finally:
             eng.close()
+
+
+def test_cfg1_game_reproduces_reference_visit_tables(tmp_path):
+    """BASELINE configs[0] (`--rollout-num 20 --num-steps 150 --cpuct 2.5`, noise off, temperature 0):
+    tests/golden/search_cfg1.json holds every root's visit table of the game the sequential CPU search
+    plays with the reference's own 19-block seed-0 network (oracle/make_golden_search.py).  The fp32
+    engine behind the batched driver must play the same game with the same tables."""
+    import json
+    import os
+
+    import net
+    import scb200
+
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "search_cfg1.json")))
+    cfg = gold["config"]
+    sd = scb200.random_init_state_dict(cfg["n_res_blocks"], 0)
+    d = net.state_dict_digest(sd)
+    assert d["numel"] == gold["weights_digest"]["numel"] and abs(d["sum"] - gold["weights_digest"]["sum"]) < 1e-6
+    blob = str(tmp_path / "seed0.scw")
+    scb200.write_blob(sd, blob)
+    eng = scb200.Engine(blob, 0, scb200.SC_MODE_FP32, 4)
+    sp = scb200.SelfPlay(eng, n_trees=2, rollout_num=cfg["rollout_num"], num_steps=cfg["num_steps"], cpuct=cfg["cpuct"],
+                         with_noise=False, temperature_switch=0, temperature=0.0, keep_traces=True, pipeline_groups=2)
+    sp.run(max_games=2)
+    tr = sp.trace(0)
+    assert sp.trace(1) == tr
+    sp.close()
+    eng.close()
+    first_div, max_dq = None, 0.0
+    for ply, (got, ref) in enumerate(zip(tr["steps"], gold["steps"])):
+        mv, q, ch = got
+        assert [c[0] for c in ch] == [c[0] for c in ref["children"]]           # legal moves, python-chess order
+        if mv != ref["move"] or [c[1] for c in ch] != [c[1] for c in ref["children"]]:
+            first_div = ply
+            break
+        max_dq = max(max_dq, max(abs(c[2] - r[2]) for c, r in zip(ch, ref["children"])), abs(q - ref["root_q"]))
+    print("plies compared:", min(len(tr["steps"]), len(gold["steps"])), "first divergence:", first_div, "max |dQ|:", max_dq)
+    assert max_dq < 1e-3
+    # uct near-ties may flip on the 1e-4 forward tolerance; the game must agree well into the middle game
+    assert first_div is None or first_div >= 20
+    if first_div is None:
+        assert len(tr["steps"]) == len(gold["steps"])
+        # the golden game ends with no legal moves: the driver must have seen the same terminal position
+        assert tr["outcome"] is not None or len(gold["steps"]) == cfg["num_steps"]

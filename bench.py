@@ -342,6 +342,20 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
 
+    # ---- small-batch latency of the same call (what the one-leaf `Game::predict` shim sees) -----------
+    latency = {}
+    if rank == 0:
+        pos_np = h_pos.numpy().view(scb200.POSITION_DTYPE)
+        for nb in (1, 8, 64):
+            if nb > B:
+                continue
+            for it in range(3 + 30):
+                if it == 3:
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                eng.eval(pos_np[:nb], h_moves[: int(h_off[nb])], h_off[: nb + 1], h_pri, h_val, sh)
+            latency["n%d_ms" % nb] = (time.perf_counter() - t0) / 30 * 1e3
+
     # ---- batched self-play at 180 rollouts (BASELINE configs[2]: 2048 concurrent trees) ---------------
     sp_stats = None
     if args.selfplay_moves > 0:
@@ -414,7 +428,7 @@ def main():
             "vs_baseline": None, "dtype": args.mode, "data": "synthetic", "config": workload_config(B),
             "e2e": {"value": e2e, "unit": "leaf evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-            "wall_s_timed_region": t_wall,
+            "wall_s_timed_region": t_wall, "call_latency": latency,
         }
         if sp_stats:
             line["selfplay"] = {

@@ -194,6 +194,14 @@ int sc_selfplay_run(sc_selfplay *sp, int64_t max_games, int64_t max_moves, doubl
 int64_t sc_selfplay_trace_json(sc_selfplay *sp, int64_t k, char *buf, int64_t cap);
 int sc_selfplay_destroy(sc_selfplay *sp);
 
+/* One self-play game through the one-leaf-at-a-time interface of the reference: the C++ mirror of
+ * `trait Game` / `mcts::mcts` / `mcts::step` (src/game.rs:3-21, src/mcts.rs:132-328; csrc/host/game.hpp)
+ * and the move loop of src/main.rs:153-238, with `predict` = sc_eval of one leaf (predict runs at every
+ * level of every descent, as in the reference).  Uses rollout_num, num_steps, cpuct, epsilon, with_noise,
+ * temperature_switch, temperature, seed, evaluator of `cfg`.  Writes the trace (format above) to `buf`;
+ * returns the bytes needed including the NUL, or -1 (sc_last_error). */
+int64_t sc_game_selfplay(sc_engine *e, const sc_selfplay_config *cfg, char *buf, int64_t cap);
+
 /* ---- arena: two networks play each other (the `play` binary with --black-type nn, src/play.rs:241-343,
  * and scripts/leader-board).  Both players share one configuration, as the reference's CLI does
  * (src/play.rs:43-81): rollout_num = --rollout, cpuct, temperature, temperature_switch; noise is off

@@ -23,7 +23,7 @@ DECLARED_SYMBOLS = [
     "sc_move_index_only", "sc_forward_only", "sc_launch_count", "sc_last_timing", "sc_set_timing", "sc_kernel_timing",
     "sc_eval_submit", "sc_eval_wait", "sc_selfplay_create", "sc_selfplay_run", "sc_selfplay_trace_json",
     "sc_selfplay_destroy", "sc_rules_probe", "sc_arena_create", "sc_encode_steps", "sc_timed_flops_per_leaf",
-    "sc_random_positions", "sc_test_dirichlet",
+    "sc_random_positions", "sc_test_dirichlet", "sc_game_selfplay",
 ]
 
 
@@ -88,6 +88,8 @@ def load_library():
         L.sc_eval_wait.argtypes = [C.c_void_p, C.c_int]
         L.sc_selfplay_create.argtypes = [C.c_void_p, C.POINTER(SelfPlayConfig), C.POINTER(C.c_void_p)]
         L.sc_selfplay_run.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_double, C.POINTER(SelfPlayStats)]
+        L.sc_game_selfplay.restype = C.c_int64
+        L.sc_game_selfplay.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int64]
         L.sc_selfplay_trace_json.restype = C.c_int64
         L.sc_selfplay_trace_json.argtypes = [C.c_void_p, C.c_int64, C.c_char_p, C.c_int64]
         L.sc_selfplay_destroy.argtypes = [C.c_void_p]
@@ -302,6 +304,23 @@ class SelfPlay:
             self.close()
         except Exception:
             pass
+
+
+def game_selfplay(engine, rollout_num=20, num_steps=150, cpuct=2.5, epsilon=0.15, with_noise=False,
+                  temperature_switch=0, temperature=0.0, seed=0, evaluator="engine"):
+    """One game of the `selfplay` binary (src/main.rs:153-238) through the C++ mirror of the reference's
+    `Game` / `mcts` interface (csrc/host/game.hpp), one leaf per `predict`.  Returns the trace dict."""
+    import json
+
+    L = load_library()
+    cfg = SelfPlayConfig(1, rollout_num, num_steps, cpuct, epsilon, int(with_noise), temperature_switch, temperature, seed,
+                         1, 0 if evaluator == "engine" else 1, 1, 1, 1)
+    cap = 1 << 24
+    buf = C.create_string_buffer(cap)
+    n = L.sc_game_selfplay(engine.handle if engine is not None else None, C.byref(cfg), buf, cap)
+    if n < 0:
+        raise SCError("sc_game_selfplay failed: " + L.sc_last_error().decode())
+    return json.loads(buf.value.decode())
 
 
 def rules_probe(history):

@@ -244,3 +244,42 @@ def test_cfg1_game_reproduces_reference_visit_tables(tmp_path):
         assert len(tr["steps"]) == len(gold["steps"])
         # the golden game ends with no legal moves: the driver must have seen the same terminal position
         assert tr["outcome"] is not None or len(gold["steps"]) == cfg["num_steps"]
+
+
+def test_game_interface_mirror_on_engine(co, small_net, tmp_path):
+    """The one-leaf-at-a-time path (`Game::predict` mirror, csrc/host/game.hpp -> sc_eval with n = 1):
+    (1) with the fp32 engine and the seed-0 19-block net it replays the configs[0] golden game;
+    (2) with the bf16 engine it plays exactly the game of the batched driver (same evaluator, batch
+    composition does not change a leaf's result)."""
+    import json
+    import os
+    import time
+
+    import scb200
+
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "search_cfg1.json")))
+    cfg = gold["config"]
+    blob19 = str(tmp_path / "seed0.scw")
+    scb200.write_blob(scb200.random_init_state_dict(cfg["n_res_blocks"], 0), blob19)
+    eng = scb200.Engine(blob19, 0, scb200.SC_MODE_FP32, 1)
+    t0 = time.time()
+    tr = scb200.game_selfplay(eng, rollout_num=cfg["rollout_num"], num_steps=cfg["num_steps"], cpuct=cfg["cpuct"])
+    print("one-leaf path, fp32, 19 blocks: %.1f plies/s" % (len(tr["steps"]) / (time.time() - t0)))
+    eng.close()
+    assert len(tr["steps"]) == len(gold["steps"])
+    for (mv, q, ch), ref in zip(tr["steps"], gold["steps"]):
+        assert mv == ref["move"]
+        assert [(c[0], c[1]) for c in ch] == [(c[0], c[1]) for c in ref["children"]]
+        assert max(abs(c[2] - r[2]) for c, r in zip(ch, ref["children"])) < 1e-3
+    assert tr["outcome"] is not None and tr["outcome"]["termination"] in ("Checkmate", "Stalemate")
+
+    sd, blob = small_net
+    eng = scb200.Engine(blob, 0, scb200.SC_MODE_BF16, 64)
+    sp = scb200.SelfPlay(eng, n_trees=32, rollout_num=30, num_steps=12, cpuct=2.5, with_noise=False, temperature_switch=3,
+                         temperature=0.0, keep_traces=True, pipeline_groups=2, seed=0)
+    sp.run(max_games=32)
+    batched = sp.trace(0)          # tree 0 uses the RNG stream of seed 0, like the mirror
+    sp.close()
+    mirror = scb200.game_selfplay(eng, rollout_num=30, num_steps=12, cpuct=2.5, temperature_switch=3, seed=0)
+    eng.close()
+    assert mirror == batched

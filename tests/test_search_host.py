@@ -271,3 +271,32 @@ def test_virtual_loss_mode_invariants(co):
         # the search differs from K = 1 only through the order in which leaves are evaluated
         same = sum(a["steps"][0][0] == b["steps"][0][0] for a, b in zip(tr1, tr))
         assert same >= 1
+
+
+def test_game_interface_mirror_equals_batched_driver_and_oracle(co):
+    """csrc/host/game.hpp mirrors the reference's `Game::predict` / `mcts::mcts` / `mcts::step` interface
+    (one leaf per predict, predict at every level).  With the same stand-in evaluator it must produce
+    the trace of the batched driver and of the oracle's sequential search, bit for bit — including a
+    game with temperature sampling, where both draw one uniform number per move from the same stream."""
+    import scb200
+
+    plies, rollouts, cpuct = 24, 60, 2.5
+    ref = _oracle_selfplay(co, plies, rollouts, cpuct)
+    tr = scb200.game_selfplay(None, rollout_num=rollouts, num_steps=plies, cpuct=cpuct, evaluator="hash")
+    assert tr["outcome"] is None and len(tr["steps"]) == len(ref)
+    for (mv, q, ch), (rmv, rq, rch) in zip(tr["steps"], ref):
+        assert mv == rmv and np.float32(q) == np.float32(rq)
+        assert [(c[0], c[1]) for c in ch] == [(c[0], c[1]) for c in rch]
+        assert np.array_equal(np.float32([c[2] for c in ch]), np.float32([c[2] for c in rch]))
+        assert np.array_equal(np.float32([c[3] for c in ch]), np.float32([c[3] for c in rch]))
+    for seed, tswitch in ((0, 0), (5, 6)):
+        sp = scb200.SelfPlay(None, n_trees=1, rollout_num=40, num_steps=130, cpuct=1.7, with_noise=False,
+                             temperature_switch=tswitch, temperature=0.0, evaluator="hash", keep_traces=True, seed=seed)
+        sp.run(max_games=1)
+        batched = sp.trace(0)
+        sp.close()
+        mirror = scb200.game_selfplay(None, rollout_num=40, num_steps=130, cpuct=1.7, temperature_switch=tswitch,
+                                      seed=seed, evaluator="hash")
+        assert mirror == batched
+    with pytest.raises(scb200.SCError):
+        scb200.game_selfplay(None, rollout_num=0, evaluator="hash")

@@ -83,8 +83,18 @@ void tc_conv_set_se(TcConv *c, const void *w1p, const float *b1, const void *w2p
 void tc_conv_destroy(TcConv *c);
 // convs: in = bf16 NHWC [rows_alloc boards][64][k_per_tap], n_units = boards.
 // value FC (TC_EPI_RAW): in = bf16 [rows_alloc][16384], n_units = rows, out = fp32 [n_splits][n_units][128].
+// TC_EPI_LN73 with `gather`: the policy map stays on the SM; log-softmax, legal-move gather and renormalisation
+// (policy.cu's policy_gather_kernel) run in the epilogue and only the priors are written.
+struct TcGather {
+    const sc_position *pos;  // [n] (side to move)
+    const sc_move *moves;    // CSR by off, or strided by SC_MAX_MOVES with cnt when off == nullptr
+    const int32_t *off, *cnt;
+    float *priors;           // same layout as moves
+    int n;
+};
 int tc_conv_launch(TcConv *c, const __nv_bfloat16 *in, int rows_alloc, int n_units, void *out,
-                   const __nv_bfloat16 *resid, int relu, int n_splits, int num_sms, cudaStream_t st);
+                   const __nv_bfloat16 *resid, int relu, int n_splits, int num_sms, cudaStream_t st,
+                   const TcGather *gather = nullptr);
 
 // whole-tower kernel: every 256-wide convolution of the residual tower in ONE launch (layers in order)
 struct TcTower;

@@ -140,6 +140,8 @@ struct sc_engine {
     // accounting
     int64_t launches = 0;
     int timing = 0;
+    // SCB200_FUSE_GATHER=0 keeps the stand-alone gather kernel (A/B runs)
+    bool fuse_gather = !(getenv("SCB200_FUSE_GATHER") && getenv("SCB200_FUSE_GATHER")[0] == '0');
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float last_tower_ms = 0.f, last_total_ms = 0.f;
     cudaEvent_t tickets[SC_MAX_INFLIGHT] = {nullptr, nullptr, nullptr, nullptr};
@@ -370,7 +372,9 @@ static int kev_mark(sc_engine *e, cudaStream_t st)
 }
 
 // the network on n boards; planes already in f_planes / h_planes, meta in d_meta.
-static int run_network(sc_engine *e, int n, cudaStream_t st)
+// `gather` (bf16 mode only): the policy head's epilogue turns the logits into legal-move priors itself; the caller
+// then skips launch_policy_gather.  Returns through *fused whether that happened.
+static int run_network(sc_engine *e, int n, cudaStream_t st, const TcGather *gather = nullptr)
 {
     const int rows = n * 64;
     e->kev_used = 0;
@@ -449,7 +453,7 @@ static int run_network(sc_engine *e, int n, cudaStream_t st)
             SCB_CHECK(tc_conv_launch(e->val1.tc, e->h_x, nb, n, e->h_y, nullptr, 1, 1, e->num_sms, st));
             e->launches += 2;
         }
-        SCB_CHECK(tc_conv_launch(e->pol2.tc, e->h_t, nb, n, e->logits, nullptr, 0, 1, e->num_sms, st));
+        SCB_CHECK(tc_conv_launch(e->pol2.tc, e->h_t, nb, n, e->logits, nullptr, 0, 1, e->num_sms, st, gather));
         SCB_CHECK(tc_conv_launch(e->vfc_tc, e->h_y, nb, n, e->vpre, nullptr, 0, e->vsplit, e->num_sms, st));
         e->launches += 2;
     }
@@ -596,13 +600,16 @@ int sc_eval_device(sc_engine *e, int n, const void *d_pos, const void *d_moves, 
     // value goes straight to the caller's buffer
     float *saved = e->d_value;
     e->d_value = static_cast<float *>(d_value_out);
-    int rc = run_network(e, n, st);
+    const TcGather g{pos, static_cast<const sc_move *>(d_moves), static_cast<const int32_t *>(d_move_off), nullptr,
+                     static_cast<float *>(d_priors_out), n};
+    const bool fused = e->mode == SC_MODE_BF16 && e->fuse_gather;
+    int rc = run_network(e, n, st, fused ? &g : nullptr);
     e->d_value = saved;
     SCB_CHECK(rc);
-    SCB_CHECK(launch_policy_gather(e->logits, pos, static_cast<const sc_move *>(d_moves),
-                                   static_cast<const int32_t *>(d_move_off), nullptr, n,
-                                   static_cast<float *>(d_priors_out), st));
-    e->launches += 1;
+    if (!fused) {
+        SCB_CHECK(launch_policy_gather(e->logits, g.pos, g.moves, g.off, nullptr, n, g.priors, st));
+        e->launches += 1;
+    }
     return finish_timing(e, st);
 }
 
@@ -656,11 +663,15 @@ int sc_eval_submit(sc_engine *e, int n, const sc_position *pos, const sc_move *m
         SCB_CHECK(encode_for_mode(e, e->d_pos, n, st));
         const int saved_timing = e->timing;
         e->timing = 0;  // asynchronous path never synchronises
-        int rc = run_network(e, n, st);
+        const TcGather g{e->d_pos, e->d_moves, nullptr, e->d_cnt, e->d_priors, n};
+        const bool fused = e->mode == SC_MODE_BF16 && e->fuse_gather;
+        int rc = run_network(e, n, st, fused ? &g : nullptr);
         e->timing = saved_timing;
         SCB_CHECK(rc);
-        SCB_CHECK(launch_policy_gather(e->logits, e->d_pos, e->d_moves, nullptr, e->d_cnt, n, e->d_priors, st));
-        e->launches += 1;
+        if (!fused) {
+            SCB_CHECK(launch_policy_gather(e->logits, g.pos, g.moves, nullptr, g.cnt, n, g.priors, st));
+            e->launches += 1;
+        }
         SCB_CUDA(cudaMemcpy2DAsync(priors_out_strided, sizeof(float) * SC_MAX_MOVES, e->d_priors, sizeof(float) * SC_MAX_MOVES,
                                    sizeof(float) * (size_t)wmax, (size_t)n, cudaMemcpyDeviceToHost, st));
         SCB_CUDA(cudaMemcpyAsync(value_out, e->d_value, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, st));

@@ -36,6 +36,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "move_index.cuh"
 
 namespace scb {
 
@@ -223,7 +224,9 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N)
 //              over the tile's own rows)                          -> bf16 [rows][256]
 //   EPI_LN73   bias + LayerNorm(73) of the 80-wide policy map     -> fp32 [rows][80]
 //   EPI_RAW    split-K partial sums of the value FC               -> fp32 [split][M][128]
-enum { EPI_LN = 0, EPI_LN_SE = 1, EPI_LN73 = 2, EPI_RAW = 3 };
+//   EPI_LN73_GATHER  EPI_LN73, but the 64 x 73 logits of a leaf stay in shared memory: log-softmax over the
+//              4672 entries, gather at the legal moves' indices, renormalise            -> priors
+enum { EPI_LN = 0, EPI_LN_SE = 1, EPI_LN73 = 2, EPI_RAW = 3, EPI_LN73_GATHER = 4 };
 
 // One convolution layer of the whole-tower kernel (device array, written once at engine creation)
 struct alignas(64) TowerLayer {
@@ -252,6 +255,7 @@ struct TcArgs {
     const TowerLayer *layers;            // TOWER: all conv layers of the residual tower, run back to back
     int n_layers;
     int group;                           // TOWER: tiles per CTA carried through all layers together (0 = all)
+    TcGather gather;                     // EPI_LN73_GATHER: legal moves in, priors out
 };
 
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32])
@@ -280,6 +284,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
 }
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// EPI_LN73_GATHER: one barrier per set of four epilogue warps (set 0 = warps 2..5, set 1 = warps 6..9)
+__device__ __forceinline__ void gather_bar_sync(int set) { asm volatile("bar.sync %0, 128;" ::"r"(2 + set) : "memory"); }
 
 // Sum over the 32 lanes of a warp of 32 per-lane values, result for index `lane` lands in
 // lane `lane` (recursive halving: 16+8+4+2+1 = 31 shuffles instead of 32 x 5).
@@ -365,7 +371,10 @@ template <int BN, bool CTA2 = false, bool YSMEM = false> struct TcCfg {
     // the weight rows, so a stage is 32 KB instead of 48 KB and six of them fit.  The SE variant spends
     // two of those stages on a 64 KB bf16 copy of the tile's LayerNorm output (YSMEM), see the epilogue.
     static constexpr int STAGES = CTA2 ? (YSMEM ? 4 : 6) : TC_STAGES;
-    static constexpr int Y_BYTES = YSMEM ? TC_BM * 256 * 2 : 0;
+    // BN == LD_POLICY: room for the fp32 logits of the tile's two leaves ([128][81], odd row stride = no bank
+    // conflicts), the unnormalised priors of both leaves and the cross-warp reductions (EPI_LN73_GATHER)
+    static constexpr int G_BYTES = BN == LD_POLICY ? 2 * (TC_BM * 81 + 2 * SC_MAX_MOVES + 16) * 4 : 0;  // two warp sets
+    static constexpr int Y_BYTES = YSMEM ? TC_BM * 256 * 2 : G_BYTES;
     static constexpr int B_BYTES = (CTA2 ? BN / 2 : BN) * TC_BK * 2;
     static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
     static constexpr int SMEM_EPI = 3 * 256 * 4 /*bias,gamma,beta*/ + (4 * 256 + 2 * 256 + 2 * 128 + 2 * 256) * 4 /*SE*/ +
@@ -445,7 +454,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int n_layers = TOWER ? args.n_layers : 1;
 
     if (EPI != EPI_RAW && !TOWER) {
-        constexpr int NV = EPI == EPI_LN73 ? C_POLICY : BN;
+        constexpr int NV = (EPI == EPI_LN73 || EPI == EPI_LN73_GATHER) ? C_POLICY : BN;
         for (int i = threadIdx.x; i < 256; i += TC_THREADS) {
             s_bias[i] = i < NV ? args.bias[i] : 0.f;
             s_gamma[i] = i < NV ? args.gamma[i] : 0.f;
@@ -599,7 +608,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 args.prof[blockIdx.x * 16 + 4] = it;
             }
         }
-    } else if ((EPI == EPI_LN || EPI == EPI_LN_SE) || warp < 6) {
+    } else if ((EPI == EPI_LN || EPI == EPI_LN_SE || EPI == EPI_LN73_GATHER) || warp < 6) {
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
         const int te = (warp - 2) * 32 + lane;  // 0..255 (0..127 for the 4-warp epilogues)
@@ -633,6 +642,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int split = EPI == EPI_RAW ? work % args.n_splits : 0;
             const int as = it & 1;
             const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+            if (EPI == EPI_LN73_GATHER && as != (warp >= 6)) continue;  // the other warp set's tile
             long long tp0 = prof ? clock64() : 0;
             mbar_wait(tfull_bar(as), aphase);
             long long tp1 = prof ? clock64() : 0;
@@ -666,6 +676,86 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         staged_store_64B(stg, lane, v, gbase + (ch * 32 + hf * 16) * 4, (size_t)BN * 4, rows_valid);
                     }
                 }
+            } else if constexpr (EPI == EPI_LN73_GATHER) {
+                // ---- policy head: bias + LayerNorm(73), then the leaf's 64 x 73 policy map stays on the SM: rows
+                //      0..63 of the tile are leaf 2*tile (warps of quadrants 0,1), rows 64..127 leaf 2*tile+1; thread =
+                //      one square with its 73 channels in registers.  Even tiles are handled by epilogue warps 2..5, odd
+                //      tiles by warps 6..9 (one accumulator stage and one shared-memory buffer each), so two tiles'
+                //      epilogues run side by side. ----
+                constexpr int LDL = 81;
+                const int es = warp >= 6;
+                float *s_logit = reinterpret_cast<float *>(s_y) + es * (Cfg::G_BYTES / 8);
+                float *s_pri = s_logit + TC_BM * LDL;       // [2 leaves][SC_MAX_MOVES]
+                float *s_red = s_pri + 2 * SC_MAX_MOVES;    // [4 quadrants][max, sum]
+                float v[BN];
+#pragma unroll
+                for (int ch = 0; ch < BN / 16; ch++) {
+                    uint32_t r[16];
+                    tmem_ld16(taddr + ch * 16, r);
+#pragma unroll
+                    for (int j = 0; j < 16; j++) v[ch * 16 + j] = __uint_as_float(r[j]) + s_bias[ch * 16 + j];
+                }
+                tc_fence_before();
+                mbar_arrive(tempty_bar(as));  // the accumulator is free for the MMAs of tile it + 2
+                float sum = 0.f;
+#pragma unroll
+                for (int c = 0; c < C_POLICY; c++) sum += v[c];
+                const float mean = sum * (1.f / C_POLICY);
+                float sq = 0.f;
+#pragma unroll
+                for (int c = 0; c < C_POLICY; c++) {
+                    const float d = v[c] - mean;
+                    sq = fmaf(d, d, sq);
+                }
+                const float rstd = rsqrtf(sq * (1.f / C_POLICY) + LN_EPS);
+                float *mine = s_logit + row * LDL;
+                float mx = -INFINITY;
+#pragma unroll
+                for (int c = 0; c < C_POLICY; c++) {
+                    v[c] = (v[c] - mean) * rstd * s_gamma[c] + s_beta[c];
+                    mine[c] = v[c];
+                    mx = fmaxf(mx, v[c]);
+                }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                if (lane == 0) s_red[quad * 2] = mx;
+                gather_bar_sync(es);
+                const int lf = quad >> 1;
+                const float m = fmaxf(s_red[lf * 4], s_red[lf * 4 + 2]);
+                float se = 0.f;
+#pragma unroll
+                for (int c = 0; c < C_POLICY; c++) se += __expf(v[c] - m);
+#pragma unroll
+                for (int o = 16; o; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+                if (lane == 0) s_red[quad * 2 + 1] = se;
+                gather_bar_sync(es);
+                const float lsum = logf(s_red[lf * 4 + 1] + s_red[lf * 4 + 3]);
+                const TcGather &G = args.gather;
+                const int b = tile * 2 + lf;
+                const int t64 = (quad & 1) * 32 + lane;
+                int beg = 0, cnt = 0;
+                if (b < G.n) {
+                    beg = G.off ? G.off[b] : b * SC_MAX_MOVES;
+                    cnt = G.off ? G.off[b + 1] - beg : G.cnt[b];
+                    cnt = cnt > SC_MAX_MOVES ? SC_MAX_MOVES : cnt;
+                    const int turn = G.pos[b].meta[0];
+                    const float *L = s_logit + lf * 64 * LDL;
+                    for (int k = t64; k < cnt; k += 64) {
+                        const int idx = move_index_dev(G.moves[beg + k], turn, c_queen_dir, c_knight_type);
+                        // flat NCHW index: channel idx / 64, square idx % 64 (py/module.py:75)
+                        s_pri[lf * SC_MAX_MOVES + k] = idx >= 0 ? expf((L[(idx & 63) * LDL + (idx >> 6)] - m) - lsum) : 0.f;
+                    }
+                }
+                gather_bar_sync(es);
+                if (b < G.n) {
+                    // `distr.iter().sum::<f32>() + 1e-5`: left-to-right f32 sum (chess.rs:891), every thread on its own
+                    float tot = 0.f;
+                    for (int k = 0; k < cnt; k++) tot += s_pri[lf * SC_MAX_MOVES + k];
+                    tot += 1e-5f;
+                    for (int k = t64; k < cnt; k += 64) G.priors[beg + k] = __fdiv_rn(s_pri[lf * SC_MAX_MOVES + k], tot);
+                }
+                gather_bar_sync(es);  // this warp set's next tile overwrites s_logit / s_pri
+                continue;
             } else if constexpr (EPI == EPI_LN73) {
                 uint32_t r[16];
                 float sum = 0.f;
@@ -1103,6 +1193,7 @@ int tc_conv_create(TcConv **out, const __nv_bfloat16 *w, int taps, int k_per_tap
         SCB_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<256, EPI_LN_SE, true, true>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256, true, true>::SMEM_BYTES));
         SCB_CHECK((set_smem_attr<LD_POLICY, EPI_LN73, true>()));
+        SCB_CHECK((set_smem_attr<LD_POLICY, EPI_LN73_GATHER, true>()));
         SCB_CHECK((set_smem_attr<N_VALUE_HIDDEN, EPI_RAW, false>()));
         attr_set = true;
     }
@@ -1234,7 +1325,7 @@ int tc_tower_launch(TcTower *t, int n_boards, int num_sms, cudaStream_t st)
 }
 
 int tc_conv_launch(TcConv *c, const __nv_bfloat16 *in, int rows_alloc, int n_units, void *out,
-                   const __nv_bfloat16 *resid, int relu, int n_splits, int num_sms, cudaStream_t st)
+                   const __nv_bfloat16 *resid, int relu, int n_splits, int num_sms, cudaStream_t st, const TcGather *gather)
 {
     if (n_units <= 0) return SC_OK;
     const bool a4d = c->epi != EPI_RAW;
@@ -1327,7 +1418,11 @@ int tc_conv_launch(TcConv *c, const __nv_bfloat16 *in, int rows_alloc, int n_uni
         tc_gemm_kernel<256, EPI_LN_SE, true><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, st>>>(*ma, c->map_w, a);
         break;
     case EPI_LN73:
-        tc_gemm_kernel<LD_POLICY, EPI_LN73, true><<<grid, TC_THREADS, TcCfg<LD_POLICY>::SMEM_BYTES, st>>>(*ma, c->map_w, a);
+        if (gather) {
+            a.gather = *gather;
+            tc_gemm_kernel<LD_POLICY, EPI_LN73_GATHER, true><<<grid, TC_THREADS, TcCfg<LD_POLICY>::SMEM_BYTES, st>>>(*ma, c->map_w, a);
+        } else
+            tc_gemm_kernel<LD_POLICY, EPI_LN73, true><<<grid, TC_THREADS, TcCfg<LD_POLICY>::SMEM_BYTES, st>>>(*ma, c->map_w, a);
         break;
     case EPI_RAW:
         tc_gemm_kernel<N_VALUE_HIDDEN, EPI_RAW, false><<<grid, TC_THREADS, TcCfg<N_VALUE_HIDDEN>::SMEM_BYTES, st>>>(

@@ -357,3 +357,29 @@ def test_large_batch_falls_back_to_per_layer_launches_bit_identically(co, nets):
             assert np.array_equal(pri_big[r * n1:(r + 1) * n1], pri)
     finally:
         e.close()
+
+
+def test_fused_policy_gather_matches_standalone_kernel(co, nets, positions, monkeypatch):
+    """bf16 mode keeps the 64 x 73 policy map of a leaf in shared memory and runs log-softmax, the
+    legal-move gather and the renormalisation in the policy head's epilogue.  It must agree with the
+    stand-alone gather kernel (which reads the same logits from HBM) to fp32 rounding, for CSR
+    (`sc_eval`) and strided (`sc_eval_submit`) move lists, odd batch sizes and leaves with 1 / many moves."""
+    import scb200
+
+    games = positions[1::5][:333]                       # odd count: the last tile holds one leaf
+    pos, moves, off, mv_all = games_to_batch(games)
+    out = {}
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("SCB200_FUSE_GATHER", fuse)
+        e = scb200.Engine(nets["n2"][1], 0, scb200.SC_MODE_BF16, 512)
+        try:
+            l0 = e.launch_count()
+            pri, val = e.eval(pos, moves, off)
+            out[fuse] = (pri.copy(), val.copy(), e.launch_count() - l0)
+        finally:
+            e.close()
+    assert out["1"][2] == out["0"][2] - 1               # one launch fewer
+    assert np.array_equal(out["1"][1], out["0"][1])
+    assert np.abs(out["1"][0] - out["0"][0]).max() < 2e-6
+    sums = np.add.reduceat(out["1"][0], off[:-1])
+    assert (sums > 0).all() and (sums < 1.0).all()

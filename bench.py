@@ -240,6 +240,9 @@ def main():
     ap.add_argument("--leaves-per-tree", type=int, default=1,
                     help="self-play leg: leaves per tree per batch (1 = the reference's sequential search; "
                          ">1 = virtual loss, leaves/K trees)")
+    ap.add_argument("--arena-seconds", type=float, default=0.0,
+                    help="also time the leader-board mode (BASELINE configs[4]: two random-init nets, rollout 100, "
+                         "temperature-switch 8, both colour assignments) for this many seconds per rank (0 = skip)")
     ap.add_argument("--threads", type=int, default=0, help="host worker threads for self-play (0 = cores / ranks)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -372,6 +375,36 @@ def main():
         sp.close()
         eng_sp.close()
 
+    # ---- leader-board mode (BASELINE configs[4]), optional ------------------------------------------
+    arena = None
+    if args.arena_seconds > 0:
+        nthr = args.threads or max(1, (os.cpu_count() or 8) // max(world, 1))
+        sd_b = scb200.random_init_state_dict(N_BLOCKS, 1)      # the second net: same shape, seed 1
+        blob_b = os.path.join(tmp, "seed1.scw")
+        scb200.write_blob(sd_b, blob_b)
+        ea = scb200.Engine(blob, local_rank, mode, B)
+        eb = scb200.Engine(blob_b, local_rank, mode, B)
+        tot = {"leaf_evals": 0, "moves": 0, "seconds": 0.0, "games_finished": 0}
+        for white, black in ((ea, eb), (eb, ea)):               # both colour assignments (scripts/leader-board:49-54)
+            ar = scb200.Arena(white, black, n_trees=B, rollout=100, cpuct=1.5, temperature=0.0, temperature_switch=8,
+                              max_plies=200, seed=shard.rank_seed(200, rank), n_threads=nthr, pipeline_groups=2)
+            barrier()
+            st = ar.run(max_seconds=args.arena_seconds / 2)
+            ar.close()
+            for k in tot:
+                tot[k] += st[k]
+        ea.close()
+        eb.close()
+        t3 = torch.tensor([tot["leaf_evals"], tot["moves"], tot["seconds"]], dtype=torch.float64, device=f"cuda:{local_rank}")
+        if dist is not None:
+            tmax = t3.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t3, op=dist.ReduceOp.SUM)
+            t3[2] = tmax[2]
+        arena = {"leaf_evals_per_s": float(t3[0] / t3[2]), "plies_per_s": float(t3[1] / t3[2]), "seconds": float(t3[2]),
+                 "config": "two random-init 19-block nets (seeds 0 and 1), %d concurrent games per GPU, rollout 100, cpuct 1.5, "
+                           "temperature-switch 8, noise off, both colour assignments, host threads = %d per GPU" % (B, nthr)}
+
     # ---- max over ranks ------------------------------------------------------------------------
     sp_secs = sp_stats["seconds"] if sp_stats else 0.0
     sp_moves = float(sp_stats["moves"]) if sp_stats else 0.0
@@ -441,6 +474,8 @@ def main():
                 "plies": sp_moves, "seconds": sp_secs, "device_wait_frac_rank0": sp_stats["wait_seconds"] / sp_stats["seconds"],
                 "games_finished_rank0": sp_stats["games_finished"],
             }
+        if arena:
+            line["arena"] = arena
         print(json.dumps(line), flush=True)
     eng.close()
     if dist is not None:

@@ -383,3 +383,37 @@ def test_fused_policy_gather_matches_standalone_kernel(co, nets, positions, monk
     assert np.abs(out["1"][0] - out["0"][0]).max() < 2e-6
     sums = np.add.reduceat(out["1"][0], off[:-1])
     assert (sums > 0).all() and (sums < 1.0).all()
+
+
+def test_reference_validation_script_metrics(co, nets, positions):
+    """The checks the reference's own validation scripts make, on the default 19-block net:
+    value abs diff and policy total-variation distance between two inference paths
+    (scripts/validate_inference.py:33-62, scripts/validate_model.py:46-83), agreement of exports at
+    rtol = atol = 1e-2 (scripts/eval_speed.py:40-43), and full-distribution vs gathered priors to two
+    decimals (notebooks/visualize_mcts.ipynb:736)."""
+    import scb200
+
+    sd, blob = nets["n19"]
+    games = positions[3::11][:96]
+    x, meta, lp, v = _oracle_forward(sd, games)
+    pos, moves, off, mv_all = games_to_batch(games)
+    p_ref = np.exp(lp)
+    for mode, tvd_bar, v_bar in ((scb200.SC_MODE_FP32, 1e-5, 1e-5), (scb200.SC_MODE_BF16, 1e-2, 1e-2)):
+        e = scb200.Engine(blob, 0, mode, 128)
+        try:
+            lp_g, v_g = e.forward_only(x, meta)
+            pri, val = e.eval(pos, moves, off)
+        finally:
+            e.close()
+        tvd = 0.5 * np.abs(np.exp(lp_g) - p_ref).sum(axis=1)
+        assert tvd.max() < tvd_bar, (mode, tvd.max())
+        assert np.abs(v_g - v).max() < v_bar
+        assert np.allclose(np.exp(lp_g), p_ref, rtol=1e-2, atol=1e-2) and np.allclose(v_g, v, rtol=1e-2, atol=1e-2)
+        # gathered + renormalised priors against the full distribution restricted to the legal moves
+        for i, g in enumerate(games):
+            idx = g.move_indices(mv_all[i])
+            full = np.exp(lp_g[i])[idx]
+            full = full / (full.sum() + 1e-5)
+            np.testing.assert_almost_equal(pri[off[i]:off[i + 1]], full, decimal=2)
+            assert np.abs(pri[off[i]:off[i + 1]] - full).max() < (1e-6 if mode == scb200.SC_MODE_FP32 else 2e-3)
+        assert np.array_equal(val, v_g) or np.abs(val - v_g).max() < 1e-6

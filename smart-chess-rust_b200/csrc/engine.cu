@@ -147,6 +147,17 @@ struct sc_engine {
     cudaEvent_t tickets[SC_MAX_INFLIGHT] = {nullptr, nullptr, nullptr, nullptr};
     int next_ticket = 0;
     int32_t *d_cnt = nullptr;
+    // asynchronous path (sc_eval_submit): two sets of device io buffers + copy streams, so the H2D of batch k+1
+    // and the D2H of batch k-1 overlap the kernels of batch k
+    struct IoSet {
+        sc_position *pos = nullptr;
+        sc_move *moves = nullptr;
+        int32_t *cnt = nullptr;
+        float *priors = nullptr, *value = nullptr;
+        cudaEvent_t in_done = nullptr, compute_done = nullptr, out_done = nullptr;
+    } io[2];
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    int64_t n_submits = 0;
     std::vector<cudaEvent_t> kev;  // level-2 timing: event pairs around the 3x3 256->256 convs
     int kev_used = 0;
     float last_conv_avg_ms = 0.f;
@@ -569,6 +580,13 @@ int sc_destroy(sc_engine *e)
     for (cudaEvent_t ev : e->kev) cudaEventDestroy(ev);
     for (int i = 0; i < SC_MAX_INFLIGHT; i++)
         if (e->tickets[i]) cudaEventDestroy(e->tickets[i]);
+    for (auto &s : e->io) {
+        if (s.in_done) cudaEventDestroy(s.in_done);
+        if (s.compute_done) cudaEventDestroy(s.compute_done);
+        if (s.out_done) cudaEventDestroy(s.out_done);
+    }
+    if (e->copy_in) cudaStreamDestroy(e->copy_in);
+    if (e->copy_out) cudaStreamDestroy(e->copy_out);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return SC_OK;
@@ -651,32 +669,67 @@ int sc_eval_submit(sc_engine *e, int n, const sc_position *pos, const sc_move *m
     const int t = e->next_ticket;
     e->next_ticket = (t + 1) % SC_MAX_INFLIGHT;
     if (!e->tickets[t]) SCB_CUDA(cudaEventCreateWithFlags(&e->tickets[t], cudaEventDisableTiming));
+    if (!e->copy_in) {
+        SCB_CUDA(cudaStreamCreateWithFlags(&e->copy_in, cudaStreamNonBlocking));
+        SCB_CUDA(cudaStreamCreateWithFlags(&e->copy_out, cudaStreamNonBlocking));
+        for (auto &s : e->io) {
+            SCB_CHECK(dev_alloc(e, &s.pos, (size_t)e->max_batch));
+            SCB_CHECK(dev_alloc(e, &s.moves, (size_t)e->max_batch * SC_MAX_MOVES));
+            SCB_CHECK(dev_alloc(e, &s.cnt, (size_t)e->max_batch));
+            SCB_CHECK(dev_alloc(e, &s.priors, (size_t)e->max_batch * SC_MAX_MOVES));
+            SCB_CHECK(dev_alloc(e, &s.value, (size_t)e->max_batch));
+            SCB_CUDA(cudaEventCreateWithFlags(&s.in_done, cudaEventDisableTiming));
+            SCB_CUDA(cudaEventCreateWithFlags(&s.compute_done, cudaEventDisableTiming));
+            SCB_CUDA(cudaEventCreateWithFlags(&s.out_done, cudaEventDisableTiming));
+        }
+    }
+    sc_engine::IoSet &io = e->io[e->n_submits & 1];
+    const bool reused = e->n_submits >= 2;
+    e->n_submits++;
     if (n > 0) {
-        SCB_CUDA(cudaMemcpyAsync(e->d_pos, pos, sizeof(sc_position) * (size_t)n, cudaMemcpyHostToDevice, st));
-        SCB_CUDA(cudaMemcpyAsync(e->d_cnt, move_cnt, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+        // inputs: wait until the kernels of the batch that used this set two submits ago are done with them
+        if (reused) SCB_CUDA(cudaStreamWaitEvent(e->copy_in, io.compute_done, 0));
+        SCB_CUDA(cudaMemcpyAsync(io.pos, pos, sizeof(sc_position) * (size_t)n, cudaMemcpyHostToDevice, e->copy_in));
+        SCB_CUDA(cudaMemcpyAsync(io.cnt, move_cnt, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, e->copy_in));
         // strided by SC_MAX_MOVES on both sides, but only the first max(move_cnt) moves of every leaf travel
         int wmax = 1;
         for (int i = 0; i < n; i++) wmax = move_cnt[i] > wmax ? move_cnt[i] : wmax;
         if (wmax > SC_MAX_MOVES) wmax = SC_MAX_MOVES;
-        SCB_CUDA(cudaMemcpy2DAsync(e->d_moves, sizeof(sc_move) * SC_MAX_MOVES, moves_strided, sizeof(sc_move) * SC_MAX_MOVES,
-                                   sizeof(sc_move) * (size_t)wmax, (size_t)n, cudaMemcpyHostToDevice, st));
-        SCB_CHECK(encode_for_mode(e, e->d_pos, n, st));
+        SCB_CUDA(cudaMemcpy2DAsync(io.moves, sizeof(sc_move) * SC_MAX_MOVES, moves_strided, sizeof(sc_move) * SC_MAX_MOVES,
+                                   sizeof(sc_move) * (size_t)wmax, (size_t)n, cudaMemcpyHostToDevice, e->copy_in));
+        SCB_CUDA(cudaEventRecord(io.in_done, e->copy_in));
+        // kernels: after the inputs arrived and after the previous results of this set left the device
+        SCB_CUDA(cudaStreamWaitEvent(st, io.in_done, 0));
+        if (reused) SCB_CUDA(cudaStreamWaitEvent(st, io.out_done, 0));
+        SCB_CHECK(encode_for_mode(e, io.pos, n, st));
         const int saved_timing = e->timing;
         e->timing = 0;  // asynchronous path never synchronises
-        const TcGather g{e->d_pos, e->d_moves, nullptr, e->d_cnt, e->d_priors, n};
+        const TcGather g{io.pos, io.moves, nullptr, io.cnt, io.priors, n};
         const bool fused = e->mode == SC_MODE_BF16 && e->fuse_gather;
+        float *saved_value = e->d_value;
+        e->d_value = io.value;
         int rc = run_network(e, n, st, fused ? &g : nullptr);
+        e->d_value = saved_value;
         e->timing = saved_timing;
         SCB_CHECK(rc);
         if (!fused) {
             SCB_CHECK(launch_policy_gather(e->logits, g.pos, g.moves, nullptr, g.cnt, n, g.priors, st));
             e->launches += 1;
         }
-        SCB_CUDA(cudaMemcpy2DAsync(priors_out_strided, sizeof(float) * SC_MAX_MOVES, e->d_priors, sizeof(float) * SC_MAX_MOVES,
-                                   sizeof(float) * (size_t)wmax, (size_t)n, cudaMemcpyDeviceToHost, st));
-        SCB_CUDA(cudaMemcpyAsync(value_out, e->d_value, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, st));
+        SCB_CUDA(cudaEventRecord(io.compute_done, st));
+        // results
+        SCB_CUDA(cudaStreamWaitEvent(e->copy_out, io.compute_done, 0));
+        SCB_CUDA(cudaMemcpy2DAsync(priors_out_strided, sizeof(float) * SC_MAX_MOVES, io.priors, sizeof(float) * SC_MAX_MOVES,
+                                   sizeof(float) * (size_t)wmax, (size_t)n, cudaMemcpyDeviceToHost, e->copy_out));
+        SCB_CUDA(cudaMemcpyAsync(value_out, io.value, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, e->copy_out));
+        SCB_CUDA(cudaEventRecord(io.out_done, e->copy_out));
+        SCB_CUDA(cudaEventRecord(e->tickets[t], e->copy_out));
+    } else {
+        SCB_CUDA(cudaEventRecord(io.in_done, e->copy_in));
+        SCB_CUDA(cudaEventRecord(io.compute_done, st));
+        SCB_CUDA(cudaEventRecord(io.out_done, e->copy_out));
+        SCB_CUDA(cudaEventRecord(e->tickets[t], st));
     }
-    SCB_CUDA(cudaEventRecord(e->tickets[t], st));
     *ticket = t;
     return SC_OK;
 }

@@ -161,6 +161,20 @@ __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar)
         : "memory");
 }
 
+// true in exactly one lane of a converged warp
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t p;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, q;\n\t"
+        "}"
+        : "=r"(p));
+    return p != 0;
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -399,7 +413,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
     constexpr int NSTAGES = Cfg::STAGES;
     static_assert(!CTA2 || (A4D && BN == 256 && (EPI == EPI_LN || EPI == EPI_LN_SE)), "pair mode: tower convs only");
-    const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
+    const uint32_t cta_rank = CTA2 ? __shfl_sync(0xffffffffu, cluster_ctarank(), 0) : 0u;
     const int work0 = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int work_stride = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     // Dynamic shared memory is the only shared allocation of this kernel, so it starts at offset 0 of
@@ -421,7 +435,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_y + Cfg::Y_BYTES);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * NSTAGES + 4 + TC_MAX_SLOTS);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index and CTA rank as warp-uniform values: the producer and MMA warps run their loops with all 32 lanes
+    // and elect one lane only around the TMA / tcgen05 instructions, so descriptors, barrier addresses and
+    // coordinates live in uniform registers instead of being broadcast lane -> uniform before every instruction
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const uint32_t smem_base = smem_u32(smem);
     if (smem_base & 1023u) __trap();
     const uint32_t bar_base = smem_u32(bars);
@@ -504,9 +521,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     auto group_begin = [&](int gi) { return (int)(((long long)gi * n_slots) / n_groups); };
 
     if (warp == 0) {
-        if (lane == 0) {
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+        {
+            if (lane == 0) {
+                asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+                asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+            }
             int stage = 0;
             uint32_t phase = 0;
             long long pc_wait_empty = 0;
@@ -527,7 +546,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         if (args.prof) pc_wait_empty += clock64() - t0;
                         const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
                         const uint32_t b_dst = a_dst + TC_A_BYTES;
-                        if (CTA2) {
+                        if (!elect_one()) {
+                        } else if (CTA2) {
                             // both CTAs load into their own shared memory and complete on the LEADER's barrier,
                             // which the leader alone arms with the bytes of both
                             if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
@@ -551,10 +571,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
             }
             }
-            if (args.prof) args.prof[blockIdx.x * 16 + 0] = pc_wait_empty;
+            if (args.prof && lane == 0) args.prof[blockIdx.x * 16 + 0] = pc_wait_empty;
         }
     } else if (warp == 1) {
-        if (lane == 0 && cta_rank == 0) {
+        if (cta_rank == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(CTA2 ? 2 * TC_BM : TC_BM, BN);
             int stage = 0;
             uint32_t phase = 0;
@@ -580,28 +600,34 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
                     const uint64_t da = umma_desc_sw128(a_addr);
                     const uint64_t db = umma_desc_sw128(a_addr + TC_A_BYTES);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 16; k++) {
-                        // +32 bytes per K=16 slice inside the 128-byte swizzle row
-                        if (CTA2)
-                            tc2_mma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
-                                         (uint32_t)((kb | k) != 0));
-                        else
-                            tc_mma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
-                                        (uint32_t)((kb | k) != 0));
+                        for (int k = 0; k < TC_BK / 16; k++) {
+                            // +32 bytes per K=16 slice inside the 128-byte swizzle row
+                            if (CTA2)
+                                tc2_mma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                                             (uint32_t)((kb | k) != 0));
+                            else
+                                tc_mma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                                            (uint32_t)((kb | k) != 0));
+                        }
+                        if (CTA2) tc2_commit_mc(empty_bar(stage));
+                        else tc_commit(empty_bar(stage));
                     }
-                    if (CTA2) tc2_commit_mc(empty_bar(stage));
-                    else tc_commit(empty_bar(stage));
+                    __syncwarp();
                     if (++stage == NSTAGES) {
                         stage = 0;
                         phase ^= 1u;
                     }
                 }
-                if (CTA2) tc2_commit_mc(tfull_bar(as));
-                else tc_commit(tfull_bar(as));
+                if (elect_one()) {
+                    if (CTA2) tc2_commit_mc(tfull_bar(as));
+                    else tc_commit(tfull_bar(as));
+                }
+                __syncwarp();
             }
             }
-            if (args.prof) {
+            if (args.prof && lane == 0) {
                 args.prof[blockIdx.x * 16 + 1] = pc_wait_tempty;
                 args.prof[blockIdx.x * 16 + 2] = pc_wait_full;
                 args.prof[blockIdx.x * 16 + 3] = clock64() - pc_total;

@@ -45,6 +45,9 @@ constexpr int TC_BN = 256;
 constexpr int TC_BK = 64;
 constexpr int TC_STAGES = 4;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KB
+#ifndef SCB_AREUSE
+#define SCB_AREUSE 1
+#endif
 constexpr int TC_THREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
 
 // ---- PTX wrappers ------------------------------------------------------------------------
@@ -369,6 +372,60 @@ __device__ __forceinline__ void staged_store_64B(uint8_t *stg, int lane, const u
     __syncwarp();
 }
 
+// Same, for accumulator rows ordered (rank, board, file) (pair mode with the shared activation box): the warp of
+// TMEM quadrant `quad` holds ranks 2 quad and 2 quad + 1 of both boards; its 8-row group k is rank 2 quad + k / 2
+// of board k % 2, i.e. tile rows 64 (k % 2) + 8 (2 quad + k / 2) .. + 7 in memory.
+__device__ __forceinline__ void staged_store_64B_hbw(uint8_t *stg, int lane, const uint4 (&v)[4], uint8_t *tile_base,
+                                                     size_t row_stride, int quad)
+{
+#pragma unroll
+    for (int q = 0; q < 4; q++) *reinterpret_cast<uint4 *>(stg + stg_off(lane, q)) = v[q];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int rr = (lane >> 2) + 8 * k;
+        const uint4 t = *reinterpret_cast<const uint4 *>(stg + stg_off(rr, lane & 3));
+        const int grow = (k & 1) * 64 + (quad * 2 + (k >> 1)) * 8 + (lane >> 2);
+        *reinterpret_cast<uint4 *>(tile_base + (size_t)grow * row_stride + (lane & 3) * 16) = t;
+    }
+    __syncwarp();
+}
+
+// Column sums over the 16 lanes of each board for rows ordered (rank, board, file): lane bit 3 is the board, so
+// the recursive halving skips that bit.  Lane l ends with the sums of its board for indices i0, i0 + 1,
+// i0 = 16 b16 + 8 b4 + 4 b2 + 2 b1 (30 shuffles).
+__device__ __forceinline__ float2 warp_transpose_reduce_2boards(float (&v)[32], int lane, int &i0)
+{
+    const bool b16 = lane & 16, b4 = lane & 4, b2 = lane & 2, b1 = lane & 1;
+    float w16[16], w8[8], w4[4], w2[2];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        float send = b16 ? v[i] : v[i + 16];
+        float keep = b16 ? v[i + 16] : v[i];
+        w16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        float send = b4 ? w16[i] : w16[i + 8];
+        float keep = b4 ? w16[i + 8] : w16[i];
+        w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float send = b2 ? w8[i] : w8[i + 4];
+        float keep = b2 ? w8[i + 4] : w8[i];
+        w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        float send = b1 ? w4[i] : w4[i + 2];
+        float keep = b1 ? w4[i + 2] : w4[i];
+        w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+    }
+    i0 = (b16 ? 16 : 0) + (b4 ? 8 : 0) + (b2 ? 4 : 0) + (b1 ? 2 : 0);
+    return make_float2(w2[0], w2[1]);
+}
+
 // 4 registers loaded with the coalesced mapping (row (lane>>2)+8k, chunk lane&3) -> lane's own row
 __device__ __forceinline__ void staged_gather_64B(uint8_t *stg, int lane, const uint4 *coal /*[4]*/, uint4 (&mine)[4])
 {
@@ -385,6 +442,12 @@ template <int BN, bool CTA2 = false, bool YSMEM = false> struct TcCfg {
     // the weight rows, so a stage is 32 KB instead of 48 KB and six of them fit.  The SE variant spends
     // two of those stages on a 64 KB bf16 copy of the tile's LayerNorm output (YSMEM), see the epilogue.
     static constexpr int STAGES = CTA2 ? (YSMEM ? 4 : 6) : TC_STAGES;
+    // Pair mode, A re-use: the three dy taps of a (channel chunk, dx) read ONE activation box of 10 board rows
+    // (rank -1..8, zero-filled outside the board) instead of three boxes of 8: separate rings for the 20 KB
+    // activation boxes (NA) and the 16 KB weight tiles (NB), 29 % fewer bytes from L2 per tile.
+    static constexpr bool AREUSE = CTA2 && (SCB_AREUSE != 0);
+    static constexpr int NA = YSMEM ? 3 : 4, NB = YSMEM ? 4 : 7;
+    static constexpr int A_BOX_BYTES = 160 * TC_BK * 2;  // rows ordered (rank, board, file): 10 x 2 x 8
     // BN == LD_POLICY: room for the fp32 logits of the tile's two leaves ([128][81], odd row stride = no bank
     // conflicts), the unnormalised priors of both leaves and the cross-warp reductions (EPI_LN73_GATHER)
     static constexpr int G_BYTES = BN == LD_POLICY ? 2 * (TC_BM * 81 + 2 * SC_MAX_MOVES + 16) * 4 : 0;  // two warp sets
@@ -393,7 +456,9 @@ template <int BN, bool CTA2 = false, bool YSMEM = false> struct TcCfg {
     static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
     static constexpr int SMEM_EPI = 3 * 256 * 4 /*bias,gamma,beta*/ + (4 * 256 + 2 * 256 + 2 * 128 + 2 * 256) * 4 /*SE*/ +
                                     (2 * 256 + 4 * 128) * 4 /*LN partials, FC1 partials*/ + 8 * 2048 /*store staging*/;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SMEM_EPI + Y_BYTES + 768;
+    static constexpr int RING_BYTES = AREUSE ? NA * A_BOX_BYTES + NB * B_BYTES : STAGES * STAGE_BYTES;
+    static constexpr int N_RING_BARS = AREUSE ? 2 * (NA + NB) : 2 * STAGES;
+    static constexpr int SMEM_BYTES = RING_BYTES + SMEM_EPI + Y_BYTES + 768;
 };
 
 constexpr int TC_MAX_SLOTS = 32;  // TOWER: tiles per CTA whose layer-to-layer hand-over is tracked
@@ -421,7 +486,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // the pointers directly from the __shared__ symbol keeps every access an LDS/STS (a pointer
     // laundered through an integer cast degrades to generic LD/ST).
     extern __shared__ __align__(1024) uint8_t smem[];
-    float *s_bias = reinterpret_cast<float *>(smem + NSTAGES * STAGE_BYTES);
+    constexpr bool AREUSE = Cfg::AREUSE;
+    constexpr int NA = Cfg::NA, NB = Cfg::NB, A_BOX = Cfg::A_BOX_BYTES, B_TILE = Cfg::B_BYTES;
+    constexpr int NRB = Cfg::N_RING_BARS;
+    float *s_bias = reinterpret_cast<float *>(smem + Cfg::RING_BYTES);
     float *s_gamma = s_bias + 256;
     float *s_beta = s_gamma + 256;
     float *s_pool = s_beta + 256;   // [4 quads][256]
@@ -433,7 +501,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint8_t *s_stage = reinterpret_cast<uint8_t *>(s_hidp + 512);  // [8 epilogue warps][32 rows][64 B]
     uint8_t *s_y = s_stage + 8 * 2048;  // YSMEM: [128 rows][32 chunks of 16 B], chunk index XOR (row & 7)
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_y + Cfg::Y_BYTES);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * NSTAGES + 4 + TC_MAX_SLOTS);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + NRB + 4 + TC_MAX_SLOTS);
 
     // warp index and CTA rank as warp-uniform values: the producer and MMA warps run their loops with all 32 lanes
     // and elect one lane only around the TMA / tcgen05 instructions, so descriptors, barrier addresses and
@@ -444,9 +512,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t bar_base = smem_u32(bars);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (NSTAGES + s); };
-    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * NSTAGES + s); };
-    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * NSTAGES + 2 + s); };
-    auto ready_bar = [&](int s) { return bar_base + 8u * (2 * NSTAGES + 4 + s); };  // TOWER: tile s written by layer l
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (NRB + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (NRB + 2 + s); };
+    auto ready_bar = [&](int s) { return bar_base + 8u * (NRB + 4 + s); };  // TOWER: tile s written by layer l
+    // AREUSE rings: activation boxes first, then weight tiles
+    auto afull_bar = [&](int s) { return bar_base + 8u * s; };
+    auto aempty_bar = [&](int s) { return bar_base + 8u * (NA + s); };
+    auto bfull_bar = [&](int s) { return bar_base + 8u * (2 * NA + s); };
+    auto bempty_bar = [&](int s) { return bar_base + 8u * (2 * NA + NB + s); };
+    auto abox_addr = [&](int s) { return smem_base + (uint32_t)(s * A_BOX); };
+    auto btile_addr = [&](int s) { return smem_base + (uint32_t)(NA * A_BOX + s * B_TILE); };
 
     struct LayerView {
         const CUtensorMap *ma, *mw;
@@ -479,10 +554,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     }
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTAGES; s++) {
-            mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), 1);
-        }
+        for (int s = 0; s < NRB; s++) mbar_init(bar_base + 8u * s, 1);  // ring barriers: one producer / one commit each
         if (TOWER)
             for (int s = 0; s < TC_MAX_SLOTS; s++) mbar_init(ready_bar(s), 256);
         for (int s = 0; s < 2; s++) {
@@ -526,8 +598,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
                 asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
             }
-            int stage = 0;
-            uint32_t phase = 0;
+            int stage = 0, astage = 0, bstage = 0;
+            uint32_t phase = 0, aphase = 0, bphase = 0;
             long long pc_wait_empty = 0;
             for (int gi = 0; gi < n_groups; gi++)
             for (int layer = 0; layer < n_layers; layer++) {
@@ -537,6 +609,43 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 if (TOWER && layer > 0) mbar_wait(ready_bar(slot), (uint32_t)(layer - 1) & 1u);  // this tile's input is written
                 const int tile = EPI == EPI_RAW ? work / args.n_splits : (CTA2 ? work * 2 + (int)cta_rank : work);
                 const int split = EPI == EPI_RAW ? work % args.n_splits : 0;
+                if constexpr (AREUSE) {
+                    const int nd = P.taps == 9 ? 3 : 1;
+                    for (int kc = 0; kc < P.kchunks; kc++)
+                        for (int dxi = 0; dxi < nd; dxi++) {
+                            const long long t0 = args.prof ? clock64() : 0;
+                            mbar_wait(aempty_bar(astage), aphase ^ 1u);
+                            if (args.prof) pc_wait_empty += clock64() - t0;
+                            if (elect_one()) {
+                                // both CTAs load into their own shared memory and complete on the LEADER's barrier,
+                                // which the leader alone arms with the bytes of both
+                                if (cta_rank == 0) mbar_expect_tx(afull_bar(astage), 2 * A_BOX);
+                                tma2_load_4d(abox_addr(astage), P.ma, afull_bar(astage), kc * TC_BK, nd == 3 ? dxi - 1 : 0, tile * 2, -1);
+                            }
+                            __syncwarp();
+                            for (int dyi = 0; dyi < nd; dyi++) {
+                                const int tap = nd == 3 ? dyi * 3 + dxi : 0;
+                                const long long t1 = args.prof ? clock64() : 0;
+                                mbar_wait(bempty_bar(bstage), bphase ^ 1u);
+                                if (args.prof) pc_wait_empty += clock64() - t1;
+                                if (elect_one()) {
+                                    if (cta_rank == 0) mbar_expect_tx(bfull_bar(bstage), 2 * B_TILE);
+                                    tma2_load_2d(btile_addr(bstage), P.mw, bfull_bar(bstage), kc * TC_BK,
+                                                 tap * BN + (int)cta_rank * (BN / 2));
+                                }
+                                __syncwarp();
+                                if (++bstage == NB) {
+                                    bstage = 0;
+                                    bphase ^= 1u;
+                                }
+                            }
+                            if (++astage == NA) {
+                                astage = 0;
+                                aphase ^= 1u;
+                            }
+                        }
+                    continue;
+                }
                 for (int tap = 0; tap < P.taps; tap++) {
                     const int dy = P.taps == 9 ? tap / 3 - 1 : 0;
                     const int dx = P.taps == 9 ? tap % 3 - 1 : 0;
@@ -576,8 +685,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     } else if (warp == 1) {
         if (cta_rank == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(CTA2 ? 2 * TC_BM : TC_BM, BN);
-            int stage = 0;
-            uint32_t phase = 0;
+            int stage = 0, ra = 0, rb = 0;
+            uint32_t phase = 0, rap = 0, rbp = 0;
             int it = 0;
             long long pc_wait_tempty = 0, pc_wait_full = 0, pc_total = args.prof ? clock64() : 0;
             for (int gi = 0; gi < n_groups; gi++)
@@ -592,6 +701,45 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 if (args.prof) pc_wait_tempty += clock64() - t0;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
+                if constexpr (AREUSE) {
+                    const int nd = P.taps == 9 ? 3 : 1;
+                    uint32_t acc = 0;
+                    for (int g = 0; g < P.kchunks * nd; g++) {
+                        t0 = args.prof ? clock64() : 0;
+                        mbar_wait(afull_bar(ra), rap);
+                        if (args.prof) pc_wait_full += clock64() - t0;
+                        for (int dyi = 0; dyi < nd; dyi++) {
+                            t0 = args.prof ? clock64() : 0;
+                            mbar_wait(bfull_bar(rb), rbp);
+                            if (args.prof) pc_wait_full += clock64() - t0;
+                            tc_fence_after();
+                            // tap dy reads rows [16 (dy + 1), 16 (dy + 1) + 128) of the box: a 2 KB step, which keeps
+                            // the 1024-byte swizzle atoms aligned
+                            const uint64_t da = umma_desc_sw128(abox_addr(ra) + (uint32_t)((nd == 3 ? dyi : 1) * 2048));
+                            const uint64_t db = umma_desc_sw128(btile_addr(rb));
+                            if (elect_one()) {
+#pragma unroll
+                                for (int k = 0; k < TC_BK / 16; k++)
+                                    tc2_mma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (acc | (uint32_t)k) != 0);
+                                tc2_commit_mc(bempty_bar(rb));
+                                if (dyi == nd - 1) tc2_commit_mc(aempty_bar(ra));
+                            }
+                            __syncwarp();
+                            acc = 1;
+                            if (++rb == NB) {
+                                rb = 0;
+                                rbp ^= 1u;
+                            }
+                        }
+                        if (++ra == NA) {
+                            ra = 0;
+                            rap ^= 1u;
+                        }
+                    }
+                    if (elect_one()) tc2_commit_mc(tfull_bar(as));
+                    __syncwarp();
+                    continue;
+                }
                 for (int kb = 0; kb < nkb; kb++) {
                     t0 = args.prof ? clock64() : 0;
                     mbar_wait(full_bar(stage), phase);
@@ -637,6 +785,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     } else if ((EPI == EPI_LN || EPI == EPI_LN_SE || EPI == EPI_LN73_GATHER) || warp < 6) {
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
+        // pair mode with the shared activation box: accumulator row = (rank, board, file); orow = its row in memory
+        const int orow = AREUSE ? ((row >> 3) & 1) * 64 + (row >> 4) * 8 + (row & 7) : row;
         const int te = (warp - 2) * 32 + lane;  // 0..255 (0..127 for the 4-warp epilogues)
         const int chalf = (warp - 2) >> 2;      // which 128-column half of the tile this warp owns
         int it = 0;
@@ -902,11 +1052,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                     pw[i] = *reinterpret_cast<uint32_t *>(&h);
                                 }
                                 const int chunk = (c0 + ch * 32) / 8 + q;
-                                *reinterpret_cast<uint4 *>(s_y + row * 512 + ((chunk ^ (row & 7)) << 4)) =
+                                *reinterpret_cast<uint4 *>(s_y + orow * 512 + ((chunk ^ (orow & 7)) << 4)) =
                                     make_uint4(pw[0], pw[1], pw[2], pw[3]);
                             }
                         }
-                        s_pool[quad * 256 + c0 + ch * 32 + lane] = warp_transpose_reduce(y, lane);
+                        if constexpr (AREUSE) {
+                            // partial sums per (quadrant, board) live in the (idle) store-staging area
+                            int i0;
+                            const float2 ps = warp_transpose_reduce_2boards(y, lane, i0);
+                            float *s_poolx = reinterpret_cast<float *>(s_stage);
+                            *reinterpret_cast<float2 *>(s_poolx + (quad * 2 + ((lane >> 3) & 1)) * 256 + c0 + ch * 32 + i0) = ps;
+                        } else
+                            s_pool[quad * 256 + c0 + ch * 32 + lane] = warp_transpose_reduce(y, lane);
                         if (ch < 3) tmem_wait_ld();
                     }
                     if constexpr (YSMEM) {
@@ -926,7 +1083,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     for (int i = 0; i < 2; i++) {
                         const int idx = te + 256 * i;  // [board][channel]
                         const int b = idx >> 8, c = idx & 255;
-                        s_mean[idx] = (s_pool[(2 * b) * 256 + c] + s_pool[(2 * b + 1) * 256 + c]) * (1.f / 64.f);
+                        if constexpr (AREUSE) {
+                            const float *s_poolx = reinterpret_cast<const float *>(s_stage);
+                            s_mean[idx] = ((s_poolx[b * 256 + c] + s_poolx[(2 + b) * 256 + c]) +
+                                           (s_poolx[(4 + b) * 256 + c] + s_poolx[(6 + b) * 256 + c])) * (1.f / 64.f);
+                        } else
+                            s_mean[idx] = (s_pool[(2 * b) * 256 + c] + s_pool[(2 * b + 1) * 256 + c]) * (1.f / 64.f);
                     }
                     epi_bar_sync();
                     // ---- excitation FC1 (256 -> 128): thread = (hidden unit j, channel half hc), both boards
@@ -1038,6 +1200,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 // ---- final pass: y (recomputed from TMEM), [gate * y + x], ReLU, bf16 store ------
                 const float *gate = s_gate + (quad >> 1) * 256;
                 uint8_t *gout = reinterpret_cast<uint8_t *>(static_cast<__nv_bfloat16 *>(P.out) + wrow0 * BN + c0);
+                uint8_t *gtile = reinterpret_cast<uint8_t *>(static_cast<__nv_bfloat16 *>(P.out) + (size_t)tile * TC_BM * BN + c0);
+                (void)gtile;
                 uint32_t rm[32];
                 tmem_ld32(tcol, r);
 #pragma unroll
@@ -1068,7 +1232,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         else if ((j & 3) == 2) pk[j >> 2].z = hv;
                         else pk[j >> 2].w = hv;
                     }
-                    staged_store_64B(stg, lane, pk, gout + ch * 64, (size_t)BN * 2, 32);
+                    if constexpr (AREUSE)
+                        staged_store_64B_hbw(stg, lane, pk, gtile + ch * 64, (size_t)BN * 2, quad);
+                    else
+                        staged_store_64B(stg, lane, pk, gout + ch * 64, (size_t)BN * 2, 32);
                     if (ch < 3) tmem_wait_ld();
                 }
                 if (prof) pe_final += clock64() - tp2;
@@ -1123,6 +1290,7 @@ static EncodeTiledFn get_encode()
 struct ActMap {
     const void *ptr;
     int rows, c;
+    bool hbw;
     CUtensorMap map;
 };
 
@@ -1163,6 +1331,16 @@ static int make_act_map_4d(const void *ptr, int boards, int c, CUtensorMap *m)
     cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)c * 16, (cuuint64_t)c * 128};
     cuuint32_t box[4] = {TC_BK, 8, 8, 2};
     return encode_map(m, ptr, 4, dims, strides, box, "activations 4d");
+}
+
+// the same activations as {C, file, board, rank}: a box of 64 channels x 8 files x 2 boards x 10 ranks lands in
+// shared memory with rows ordered (rank, board, file), so the three dy taps are 2 KB apart in ONE box
+static int make_act_map_hbw(const void *ptr, int boards, int c, CUtensorMap *m)
+{
+    cuuint64_t dims[4] = {(cuuint64_t)c, 8, (cuuint64_t)boards, 8};
+    cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)c * 128, (cuuint64_t)c * 16};
+    cuuint32_t box[4] = {TC_BK, 8, 2, 10};
+    return encode_map(m, ptr, 4, dims, strides, box, "activations (rank, board, file)");
 }
 
 // plain row-major [rows][k] matrix, box = 64 k x 128 rows
@@ -1253,7 +1431,10 @@ int tc_tower_create(TcTower **out, const TcTowerLayerDesc *descs, int n, int boa
             return SC_E_INVAL;
         }
         memset(&h[i], 0, sizeof(TowerLayer));
-        SCB_CHECK(make_act_map_4d(descs[i].in, boards_alloc, c->k_per_tap, &h[i].map_a));
+        if (TcCfg<256, true, true>::AREUSE)
+            SCB_CHECK(make_act_map_hbw(descs[i].in, boards_alloc, c->k_per_tap, &h[i].map_a));
+        else
+            SCB_CHECK(make_act_map_4d(descs[i].in, boards_alloc, c->k_per_tap, &h[i].map_a));
         h[i].map_w = c->map_w_half;
         h[i].out = descs[i].out;
         h[i].resid = descs[i].resid;
@@ -1355,15 +1536,23 @@ int tc_conv_launch(TcConv *c, const __nv_bfloat16 *in, int rows_alloc, int n_uni
 {
     if (n_units <= 0) return SC_OK;
     const bool a4d = c->epi != EPI_RAW;
+    // CTA-pair (cta_group::2) path for the 256-wide tower convolutions: clusters of two CTAs, each pair
+    // owns a 256-row tile (4 boards).  SCB200_CTA_PAIR=0 selects the single-CTA kernel.
+    static const bool pair_enabled = !(getenv("SCB200_CTA_PAIR") && getenv("SCB200_CTA_PAIR")[0] == '0');
+    const bool use_pair = pair_enabled && c->pair_ok;  // also for a single tile: the arithmetic must not depend on the batch size
+    const bool hbw = use_pair && TcCfg<256, true>::AREUSE;
     const CUtensorMap *ma = nullptr;
     for (auto &m : c->act_maps)
-        if (m.ptr == in && m.rows == rows_alloc && m.c == c->k_per_tap) ma = &m.map;
+        if (m.ptr == in && m.rows == rows_alloc && m.c == c->k_per_tap && m.hbw == hbw) ma = &m.map;
     if (!ma) {
         ActMap am;
         am.ptr = in;
         am.rows = rows_alloc;
         am.c = c->k_per_tap;
-        if (a4d)
+        am.hbw = hbw;
+        if (hbw)
+            SCB_CHECK(make_act_map_hbw(in, rows_alloc, c->k_per_tap, &am.map));
+        else if (a4d)
             SCB_CHECK(make_act_map_4d(in, rows_alloc, c->k_per_tap, &am.map));
         else
             SCB_CHECK(make_act_map_2d(in, rows_alloc, c->k_per_tap, &am.map));
@@ -1402,10 +1591,7 @@ int tc_conv_launch(TcConv *c, const __nv_bfloat16 *in, int rows_alloc, int n_uni
     }
     const int n_work = a4d ? a.n_tiles : a.n_tiles * a.n_splits;
     const int grid = n_work < num_sms ? n_work : num_sms;
-    // CTA-pair (cta_group::2) path for the 256-wide tower convolutions: clusters of two CTAs, each pair
-    // owns a 256-row tile (4 boards).  SCB200_CTA_PAIR=0 selects the single-CTA kernel.
-    static const bool pair_enabled = !(getenv("SCB200_CTA_PAIR") && getenv("SCB200_CTA_PAIR")[0] == '0');
-    if (pair_enabled && c->pair_ok) {  // also for a single tile: the arithmetic must not depend on the batch size
+    if (use_pair) {
         const int n_pairs = (a.n_tiles + 1) / 2;
         int g2 = 2 * n_pairs;
         if (g2 > (num_sms & ~1)) g2 = num_sms & ~1;

@@ -436,14 +436,14 @@ def main():
             # residual); one of each per residual block -> average per timed launch
             # one launch of each per residual block; the whole-tower launch contains all of them
             # whole-tower launch: 3.615 GB read + 2.677 GB written (profiles/r01e_tower_full_raw.csv)
-            traffic = ((95.4e6 + 161.0e6) / 2 if conv_n > 1 else 1.590e9) if B == 2048 else None
+            traffic = ((95.4e6 + 161.0e6) / 2 if conv_n > 1 else 1.644e9) if B == 2048 else None
             roof = {"bound": "tensor",
                     "kernel": ("tc_gemm_kernel<256, pair, TOWER>: stem + 19 x (conv3x3+LN+ReLU, conv3x3+LN+SE+residual+ReLU) + 2 head 1x1 convs in one launch"
                                if conv_n == 1 else
                                "tc_gemm_kernel<256, EPI_LN | EPI_LN_SE, pair> (3x3 256->256 conv, bias+LN[+SE+residual] fused)"),
                     "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
                     "peak_kind": f"bf16_tflops_sustained ({peaks['src']})", "traffic": traffic,
-                    "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01k_summary.md)",
+                    "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01m_summary.md)",
                     "launches_timed_per_step": conv_n, "avg_launch_ms": conv_avg_ms,
                     "flops_per_launch": B * timed_flops / conv_n,
                     "whole_step_tflops": value / world * FLOP_PER_LEAF / 1e12}

@@ -431,18 +431,18 @@ def main():
         roof = None
         if conv_avg_ms and conv_avg_ms > 0 and args.mode == "bf16":
             ach = B * timed_flops / (conv_tot_ms * 1e-3) / 1e12
-            # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture in
-            # profiles/r01d_conv_full_raw.csv at this workload: 95.4 MB (conv1) and 161.0 MB (conv2 + SE +
-            # residual); one of each per residual block -> average per timed launch
-            # one launch of each per residual block; the whole-tower launch contains all of them
-            # whole-tower launch: 3.615 GB read + 2.677 GB written (profiles/r01e_tower_full_raw.csv)
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch from ncu --set full captures at this workload:
+            # per-layer launches (SCB200_TOWER=0): 95.4 MB (conv1) / 161.0 MB (conv2 + SE + residual), one of each
+            # per residual block (profiles/r01d_conv_full_raw.csv); whole-tower launch: 237 MB read + 1407 MB
+            # written (profiles/r01m_step_full_raw.csv)
             traffic = ((95.4e6 + 161.0e6) / 2 if conv_n > 1 else 1.644e9) if B == 2048 else None
             roof = {"bound": "tensor",
                     "kernel": ("tc_gemm_kernel<256, pair, TOWER>: stem + 19 x (conv3x3+LN+ReLU, conv3x3+LN+SE+residual+ReLU) + 2 head 1x1 convs in one launch"
                                if conv_n == 1 else
                                "tc_gemm_kernel<256, EPI_LN | EPI_LN_SE, pair> (3x3 256->256 conv, bias+LN[+SE+residual] fused)"),
                     "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
-                    "peak_kind": f"bf16_tflops_sustained ({peaks['src']})", "traffic": traffic,
+                    "peak_kind": f"bf16_tflops_sustained ({peaks['src']}): the kernel is timed inside a long step",
+                    "peak_burst": peaks["tflops_burst"], "frac_of_burst": ach / peaks["tflops_burst"], "traffic": traffic,
                     "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01m_summary.md)",
                     "launches_timed_per_step": conv_n, "avg_launch_ms": conv_avg_ms,
                     "flops_per_launch": B * timed_flops / conv_n,

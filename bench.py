@@ -236,7 +236,7 @@ def main():
     ap.add_argument("--leaves", type=int, default=2048, help="leaves per step per GPU")
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline work (rank 0, N=1)")
-    ap.add_argument("--selfplay-moves", type=int, default=4096, help="plies of batched self-play to time (0 = skip)")
+    ap.add_argument("--selfplay-moves", type=int, default=16384, help="plies of batched self-play to time (0 = skip)")
     ap.add_argument("--leaves-per-tree", type=int, default=1,
                     help="self-play leg: leaves per tree per batch (1 = the reference's sequential search; "
                          ">1 = virtual loss, leaves/K trees)")

@@ -179,6 +179,18 @@ class Engine:
         _check(load_library().sc_eval_device(self._h, n, _ptr(d_pos), _ptr(d_moves), _ptr(d_off), n_moves_total,
                                              _ptr(d_priors), _ptr(d_value), stream or None), "sc_eval_device")
 
+    def submit(self, positions, moves_strided, move_cnt, priors_out_strided, value_out, stream: int = 0) -> int:
+        """Asynchronous `predict` (sc_eval_submit): moves / priors strided by 256 per leaf, buffers must stay alive
+        (and should be pinned) until `wait(ticket)` returns.  At most SC_MAX_INFLIGHT = 4 tickets in flight."""
+        t = C.c_int(-1)
+        _check(load_library().sc_eval_submit(self._h, len(positions), _ptr(positions), _ptr(moves_strided), _ptr(move_cnt),
+                                             _ptr(priors_out_strided), _ptr(value_out), stream or None, C.byref(t)),
+               "sc_eval_submit")
+        return t.value
+
+    def wait(self, ticket: int):
+        _check(load_library().sc_eval_wait(self._h, ticket), "sc_eval_wait")
+
     def encode_only(self, positions: np.ndarray):
         n = len(positions)
         positions = np.ascontiguousarray(positions, dtype=POSITION_DTYPE)

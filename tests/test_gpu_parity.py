@@ -417,3 +417,39 @@ def test_reference_validation_script_metrics(co, nets, positions):
             np.testing.assert_almost_equal(pri[off[i]:off[i + 1]], full, decimal=2)
             assert np.abs(pri[off[i]:off[i + 1]] - full).max() < (1e-6 if mode == scb200.SC_MODE_FP32 else 2e-3)
         assert np.array_equal(val, v_g) or np.abs(val - v_g).max() < 1e-6
+
+
+def test_async_submit_four_in_flight_equals_sync_eval(co, nets, positions):
+    """sc_eval_submit / sc_eval_wait (the path the batched driver uses): four batches in flight over the two
+    device io sets and the copy streams; every ticket must deliver exactly what the synchronous call does."""
+    import scb200
+
+    e = scb200.Engine(nets["n2"][1], 0, scb200.SC_MODE_BF16, 256)
+    try:
+        batches = [positions[i::13][:n] for i, n in ((0, 200), (1, 37), (2, 256), (3, 1), (4, 129), (5, 64))]
+        want, bufs = [], []
+        for games in batches:
+            pos, moves, off, _ = games_to_batch(games)
+            pri, val = e.eval(pos, moves, off)
+            want.append((pri.copy(), val.copy(), off))
+            n = len(games)
+            ms = np.zeros((n, 256), dtype=scb200.MOVE_DTYPE)
+            cnt = np.diff(off).astype(np.int32)
+            for i in range(n):
+                ms[i, : cnt[i]] = moves[off[i]:off[i + 1]]
+            bufs.append((np.ascontiguousarray(pos), ms, cnt, np.full((n, 256), -1, np.float32), np.zeros(n, np.float32)))
+        for rounds in range(3):
+            tickets = []
+            for k in range(4):
+                b = bufs[(rounds + k) % len(bufs)]
+                b[3][:] = -1
+                tickets.append(((rounds + k) % len(bufs), e.submit(*b)))
+            for k, t in tickets:
+                e.wait(t)
+                pri, val, off = want[k]
+                got = bufs[k]
+                assert np.array_equal(got[4], val)
+                for i in range(len(val)):
+                    assert np.array_equal(got[3][i, : got[2][i]], pri[off[i]:off[i + 1]])
+    finally:
+        e.close()

@@ -18,6 +18,7 @@ static __constant__ int8_t c_knight_type[25] = {-1, 4,  -1, 3,  -1,   // d_rank 
 
 __device__ __forceinline__ int move_index_dev(sc_move m, int turn, const int8_t *qdir, const int8_t *ktype)
 {
+    if ((m.from | m.to) & 0xC0) return -1;  // not a square: no index, prior 0 (keeps every later lookup in range)
     int fr = m.from >> 3, ff = m.from & 7, tr = m.to >> 3, tf = m.to & 7;
     if (!turn) {  // Move::rotate for Black to move
         fr = 7 - fr;

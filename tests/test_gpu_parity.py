@@ -453,3 +453,31 @@ def test_async_submit_four_in_flight_equals_sync_eval(co, nets, positions):
                     assert np.array_equal(got[3][i, : got[2][i]], pri[off[i]:off[i + 1]])
     finally:
         e.close()
+
+
+def test_garbage_inputs_do_not_fault(nets):
+    """The reference has no error channel here (it panics on inconsistent input); the library must at least stay
+    memory-safe: random bytes as positions and moves give finite, sub-normalised priors (0 for anything that is
+    not a move on the board) in both modes, and the engine keeps working afterwards."""
+    import scb200
+
+    rng = np.random.default_rng(7)
+    n = 300
+    pos = np.frombuffer(rng.bytes(n * scb200.POSITION_DTYPE.itemsize), dtype=scb200.POSITION_DTYPE).copy()
+    pos["n_hist"] = rng.integers(-3, 12, n)            # out-of-range history lengths too
+    pos["meta"][:, 0] = rng.integers(0, 2, n)          # the value is scaled by (2 turn - 1) as in py/module.py:147-149
+    cnt = rng.integers(1, 219, n)
+    off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
+    moves = np.frombuffer(rng.bytes(int(off[-1]) * 4), dtype=scb200.MOVE_DTYPE).copy()
+    for mode in (scb200.SC_MODE_BF16, scb200.SC_MODE_FP32):
+        e = scb200.Engine(nets["n2"][1], 0, mode, 512)
+        try:
+            pri, val = e.eval(pos, moves, off)
+            assert np.isfinite(pri).all() and (pri >= 0).all() and np.isfinite(val).all() and (np.abs(val) <= 1).all()
+            assert (np.add.reduceat(pri, off[:-1]) <= 1.0 + 1e-5).all()
+            bad = ((moves["from"] | moves["to"]) & 0xC0) != 0
+            assert (pri[bad] == 0).all()
+            idx = e.move_index_only(pos, moves, off)
+            assert ((idx >= -1) & (idx < 4672)).all() and (idx[bad] == -1).all()
+        finally:
+            e.close()

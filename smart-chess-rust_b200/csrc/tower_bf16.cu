@@ -7,23 +7,28 @@
 // SqueezeExcitation(256, 128) = sigmoid(fc2(relu(fc1(avgpool)))) * x (torchvision).
 //
 // GEMM view of one 3x3 layer: M = 64 * boards, N = 256 output channels, K = 9 taps x Cin.
-//   A (activations, bf16 NHWC [board][rank][file][C]) is never materialised as im2col: for
-//   tap (dy,dx) and channel chunk kc the TMA loads the 4-D box {64 ch, 8 files, 8 ranks,
-//   2 boards} at coordinates (64*kc, dx, dy, board0); ranks/files outside [0,8) are
-//   zero-filled by the TMA unit, which IS the conv padding.  The box lands in shared memory
-//   as 128 rows x 128 bytes, 128B-swizzled = the canonical K-major UMMA operand layout.
+//   A (activations, bf16 NHWC [board][rank][file][C]) is never materialised as im2col.  Single-CTA
+//   kernels: for tap (dy,dx) and channel chunk kc the TMA loads the 4-D box {64 ch, 8 files, 8 ranks,
+//   2 boards} at coordinates (64*kc, dx, dy, board0).  Pair kernels (the tower): ONE box {64 ch,
+//   8 files, 2 boards, 10 ranks} at (64*kc, dx, board0, -1) serves the three dy taps of (kc, dx); it
+//   lands as 160 rows ordered (rank, board, file) and tap dy is the 128-row tile 2 KB * (dy + 1) into it.
+//   Ranks/files outside [0,8) are zero-filled by the TMA unit, which IS the conv padding; 128B swizzle
+//   makes every tile the canonical K-major UMMA operand.
 //   B (weights, bf16 [tap][cout][cin]) is a plain 2-D box.
 //   D accumulates in TMEM (128 lanes x 256 fp32 columns per tile, two tiles = all 512
 //   columns, so the epilogue of tile i overlaps the MMAs of tile i+1).
 // One kernel template, tc_gemm_kernel<BN, EPI, A4D, CTA2, TOWER>:
 //   * CTA2: clusters of two CTAs issue tcgen05.mma.cta_group::2 (256-row tiles, each CTA
-//     stages its 128 rows of A and half of the weight rows);
+//     stages its own rows of A and half of the weight rows);
 //   * TOWER: the stem, all residual blocks and the two 256-wide head 1x1 convolutions run
 //     in ONE persistent launch; a tile's layers are chained by a per-tile mbarrier inside
 //     the CTA (boards never interact inside the tower), tiles are carried through all
 //     layers in groups of 3-4 so that layer outputs are re-read from L2;
-//   * the narrow head GEMMs (256->73 with LayerNorm(73); value FC 16384->128 as a split-K
+//   * the narrow head GEMMs (256->73 with LayerNorm(73), optionally followed in the same epilogue
+//     by log-softmax + legal-move gather + renormalisation; value FC 16384->128 as a split-K
 //     GEMM whose rows are boards) are single-CTA instantiations of the same kernel.
+// Producer and MMA warps run warp-uniform loops and elect one lane around the TMA / MMA / commit
+// instructions only, which keeps descriptors and barrier addresses in uniform registers.
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
 // warps 2..9 = epilogue (two warps per TMEM lane quadrant, each owning 128 of the 256
 // columns of its 32 rows; one thread = one (board, square) row, so LayerNorm over channels

@@ -283,3 +283,28 @@ def test_game_interface_mirror_on_engine(co, small_net, tmp_path):
     mirror = scb200.game_selfplay(eng, rollout_num=30, num_steps=12, cpuct=2.5, temperature_switch=3, seed=0)
     eng.close()
     assert mirror == batched
+
+
+def test_run_batch_writes_traces_the_reference_pipeline_reads(co, small_net, tmp_path, capsys):
+    """`python -m scb200.run_batch` (scripts/run_batch for this backend): trace{k}.json files in the format of
+    src/trace.rs that py/dataset.py:47-87 consumes: {"steps": [[uci, q, [[uci, n, q, uct], ...]], ...], "outcome"}."""
+    import json
+
+    from scb200 import run_batch
+
+    sd, blob = small_net
+    out = tmp_path / "traces"
+    rc = run_batch.main(["-c", blob, "-N", "5", "--prefix", str(out), "--trees", "4", "--rollout-num", "12", "-n", "9",
+                         "--temperature-switch", "3", "--cpuct", "2.5", "--threads", "2"])
+    assert rc == 0
+    lines = [l for l in capsys.readouterr().out.splitlines() if l and not l.startswith("#")]
+    assert len(lines) == 5 and lines[0].startswith("01, null, num-steps: 9")
+    for k in range(1, 6):
+        tr = json.load(open(out / f"trace{k}.json"))
+        assert set(tr) == {"steps", "outcome"} and len(tr["steps"]) == 9
+        g = co.Game()
+        for mv, q, ch in tr["steps"]:
+            assert isinstance(q, float) and mv in g.legal_uci()
+            assert [c[0] for c in ch] == g.legal_uci() and sum(c[1] for c in ch) == 11
+            assert all(len(c) == 4 for c in ch)
+            g.push(mv)

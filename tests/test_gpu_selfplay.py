@@ -308,3 +308,31 @@ def test_run_batch_writes_traces_the_reference_pipeline_reads(co, small_net, tmp
             assert [c[0] for c in ch] == g.legal_uci() and sum(c[1] for c in ch) == 11
             assert all(len(c) == 4 for c in ch)
             g.push(mv)
+
+
+def test_leader_board_script(co, small_net, tmp_path, capsys):
+    """`python -m scb200.leader_board` (scripts/leader-board + show-result + elo.py): both colour assignments,
+    trace files per game, the `total / white / black` tallies and the Elo line."""
+    import json
+
+    import net
+    import scb200
+    from scb200 import leader_board
+
+    sd_a, blob_a = small_net
+    blob_b = str(tmp_path / "b.scw")
+    scb200.write_blob(net.perturb_norm_params(net.init_state_dict(2, 11), 99), blob_b)
+    out = tmp_path / "replay"
+    rc = leader_board.main(["-W", blob_a, "-B", blob_b, "-N", "6", "--prefix", str(out), "--rollout", "10", "--max-plies", "40",
+                            "--temperature-switch", "4", "--threads", "2", "--trees", "6"])
+    assert rc == 0
+    text = capsys.readouterr().out
+    assert "Swapping the players" in text and text.count(" / ") >= 2
+    for tag in ("w", "b"):
+        for k in range(1, 7):
+            tr = json.load(open(out / f"{tag}_{k}.json"))
+            g = co.Game()
+            for mv, q, ch in tr["steps"]:
+                assert mv in g.legal_uci()
+                g.push(mv)
+            assert len(tr["steps"]) <= 40

@@ -207,9 +207,10 @@ int64_t sc_game_selfplay(sc_engine *e, const sc_selfplay_config *cfg, char *buf,
  * (src/play.rs:43-81): rollout_num = --rollout, cpuct, temperature, temperature_switch; noise is off
  * (play.rs:250), temperature 0 picks uniformly among the most visited children (play.rs:269-278), a game
  * ends when outcome(claim_draw=true) is set after a ply or after num_steps (200) plies.  `white` moves on
- * even plies.  Games are played in rounds of n_trees; within a pipeline group every tree is at the same
- * ply, so each device batch belongs to one network.  Colour-swapped rounds = a second arena with the
- * engines exchanged, as scripts/leader-board:49-54 does. */
+ * even plies.  Within a pipeline group every game is at a ply of the same parity (a slot whose game ended
+ * starts the run's next game at the next even group ply), so each device batch belongs to one network and
+ * the batches stay full.  Colour-swapped games = a second arena with the engines exchanged, as
+ * scripts/leader-board:49-54 does. */
 int sc_arena_create(sc_engine *white, sc_engine *black, const sc_selfplay_config *cfg, sc_selfplay **out);
 
 /* Synthetic workload: seeded uniform random play from the start position with the driver's

@@ -74,8 +74,9 @@ struct Tree {
     // current search / game
     int rollouts_done = 0;
     int move_index = 0;      // `i` of the self-play loop (main.rs:168)
+    int ply_offset = 0;      // arena: the (even) group ply at which this slot's current game started
     bool active = true;
-    bool game_over = false;  // arena: waiting for the round to end
+    bool game_over = false;  // arena: this slot's game ended (the next one starts at the next even group ply)
     TraceRec trace;
     std::vector<float> noisy;  // scratch for root priors mixed with Dirichlet noise
 
@@ -531,15 +532,28 @@ void finish_pending(sc_selfplay *sp, Tree &t, const float *priors, const float *
 }
 
 // arena: a tree only searches the ply its pipeline group is at, then waits for the others
+// A finished game's slot starts the run's next game at the next EVEN group ply: White (the first network) is
+// to move at even group plies in every game of the group, so one batch never mixes the two networks.
 void advance_tree_arena(sc_selfplay *sp, Tree &t, int group_ply, const BatchOut &out, const float *priors,
                         const float *value)
 {
     finish_pending(sp, t, priors, value);
+    auto next_game = [&]() {
+        const int64_t k = sp->games_started.fetch_add(1) + 1;
+        if (sp->max_games > 0 && k > sp->max_games) {
+            t.active = false;
+            return;
+        }
+        t.new_game(0);
+        t.ply_offset = (group_ply + 2) & ~1;  // > group_ply and even
+    };
     for (;;) {
-        if (!t.active || t.game_over || t.move_index > group_ply) return;
+        if (t.active && t.game_over) next_game();
+        if (!t.active || t.move_index + t.ply_offset > group_ply) return;
         const int r = collect_leaves(sp, t, out, [&]() {
             play_move_arena(sp, t);
-            return t.active && !t.game_over && t.move_index <= group_ply;
+            if (t.game_over) next_game();
+            return t.active && t.move_index + t.ply_offset <= group_ply;
         });
         if (r >= 0) return;
     }
@@ -760,35 +774,16 @@ int sc_selfplay_run(sc_selfplay *sp, int64_t max_games, int64_t max_moves, doubl
             parallel_advance(sp, g);
             int n_leaves = G.n_used.load(std::memory_order_relaxed);
             if (sp->arena) {
-                // nobody produced a leaf: the whole group finished this ply -> next ply, or next round
+                // nobody produced a leaf: every game of the group made its move of this ply -> next ply
                 for (int guard = 0; n_leaves == 0 && guard < 1000000; guard++) {
                     bool playing = false;
-                    for (int i = 0; i < G.count; i++) {
-                        const Tree &t = sp->trees[G.first + i];
-                        playing = playing || (t.active && !t.game_over);
-                    }
-                    if (playing)
-                        sp->group_ply[g]++;
-                    else {
-                        bool started = false;
-                        for (int i = 0; i < G.count; i++) {
-                            Tree &t = sp->trees[G.first + i];
-                            if (!t.active) continue;
-                            int64_t k = sp->games_started.fetch_add(1) + 1;
-                            if (sp->max_games > 0 && k > sp->max_games) {
-                                t.active = false;
-                                continue;
-                            }
-                            t.new_game(0);
-                            started = true;
-                        }
-                        if (!started) break;
-                        sp->group_ply[g] = 0;
-                    }
+                    for (int i = 0; i < G.count; i++) playing = playing || sp->trees[G.first + i].active;
+                    if (!playing) break;
+                    sp->group_ply[g]++;
                     parallel_advance(sp, g);
                     n_leaves = G.n_used.load(std::memory_order_relaxed);
                     if (sp->cfg.evaluator == 1) {
-                        // hash evaluator never leaves a leaf pending: keep stepping plies until the round is over
+                        // hash evaluator never leaves a leaf pending: keep stepping plies until every game is played
                         bool left = false;
                         for (int i = 0; i < G.count; i++) left = left || sp->trees[G.first + i].active;
                         if (!left) break;

@@ -481,3 +481,36 @@ def test_garbage_inputs_do_not_fault(nets):
             assert ((idx >= -1) & (idx < 4672)).all() and (idx[bad] == -1).all()
         finally:
             e.close()
+
+
+def test_bf16_mode_deviation_is_operand_rounding(co, nets, positions):
+    """the reference's bf16 path rounds the operands of every conv / linear to bf16 and accumulates
+    in fp32.  oracle.net.forward_bf16_operands emulates that on the CPU.  The three results (engine bf16, emulation,
+    fp32) must be mutually within a few 1e-3: the engine's deviation from fp32 is of the size of the operand rounding
+    the reference's own bf16 path has (measured on B200: 1.4e-3 / 3.9e-3 engine vs fp32 for the 2- / 19-block net,
+    2.1e-3 / 2.0e-3 emulation vs fp32), an order of magnitude inside the 2e-2 gate."""
+    import net
+    import scb200
+
+    for key, n in (("n2", 64), ("n19", 24)):
+        sd, blob = nets[key]
+        games = positions[5::17][:n]
+        planes = np.stack([g.encode()[0] for g in games])
+        meta = np.stack([g.encode()[1] for g in games])
+        x = net.planes_i8_hwc_to_nchw(planes)
+        m = torch.from_numpy(meta).float()
+        lp32, v32 = net.forward(sd, x, m)
+        lpe, ve = net.forward_bf16_operands(sd, x, m)
+        e = scb200.Engine(blob, 0, scb200.SC_MODE_BF16, 64)
+        try:
+            lpg, vg = e.forward_only(x.numpy(), meta.astype(np.float32))
+        finally:
+            e.close()
+        p32, pe, pg = np.exp(lp32.numpy()), np.exp(lpe.numpy()), np.exp(lpg)
+        d_emu = max(np.abs(pg - pe).max(), np.abs(vg - ve.numpy().reshape(-1)).max())
+        d_f32 = max(np.abs(pg - p32).max(), np.abs(vg - v32.numpy().reshape(-1)).max())
+        d_ref = max(np.abs(pe - p32).max(), np.abs(ve.numpy() - v32.numpy()).max())
+        print(f"{key}: |gpu - bf16 emulation| {d_emu:.2e}  |gpu - fp32| {d_f32:.2e}  |emulation - fp32| {d_ref:.2e}")
+        assert d_f32 < BF16_TOL
+        assert d_emu < 1e-2
+        assert d_f32 < 4 * d_ref + 1e-4          # same order as the rounding the reference's bf16 path has

@@ -228,6 +228,10 @@ int sc_test_dirichlet(uint64_t seed, float alpha, int n, float *out);
  * would see there: legal moves in python-chess generation order, the packed leaf `_encode` would be
  * given (node depth = ply), and outcome(claim_draw=True) (termination code of src/chess.rs:87-105 or
  * 0, winner 1/0/-1).  Returns SC_E_INVAL if a history move is not legal. */
+/* perft (number of leaf nodes of the legal-move tree of the given depth <= 7) of the driver's native rules from a
+ * FEN (NULL = start position): pins the move generator to the published perft tables. */
+int sc_rules_perft(const char *fen, int depth, uint64_t *nodes);
+
 int sc_rules_probe(const sc_move *history, int n_history, sc_move *legal_out, int *n_legal, sc_position *packed_out,
                    int *termination, int *winner);
 

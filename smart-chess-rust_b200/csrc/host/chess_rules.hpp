@@ -11,6 +11,7 @@
 // sliding attacks by directional rays and bit scans (classical ray attacks).
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <cstring>
 #include <vector>
 
@@ -154,6 +155,62 @@ struct Position {
         ep = -1;
         halfmove = 0;
         fullmove = 1;
+    }
+    // Forsyth-Edwards notation (test hook: perft from the published test positions); false if malformed
+    bool set_fen(const char *fen)
+    {
+        memset(this, 0, sizeof(*this));
+        ep = -1;
+        halfmove = 0;
+        fullmove = 1;
+        int r = 7, f = 0;
+        const char *p = fen;
+        for (; *p && *p != ' '; p++) {
+            const char ch = *p;
+            if (ch == '/') {
+                r--;
+                f = 0;
+            } else if (ch >= '1' && ch <= '8')
+                f += ch - '0';
+            else {
+                static const char *names = " pnbrqk";
+                const char lo = (char)(ch | 0x20);
+                const char *q = strchr(names + 1, lo);
+                if (!q || r < 0 || f > 7) return false;
+                const int color = ch == lo ? BLACK : WHITE;
+                pt[q - names] |= bit(r * 8 + f);
+                occ[color] |= bit(r * 8 + f);
+                f++;
+            }
+        }
+        all = occ[WHITE] | occ[BLACK];
+        if (*p != ' ') return false;
+        p++;
+        turn = *p == 'w' ? WHITE : BLACK;
+        p++;
+        if (*p != ' ') return false;
+        for (p++; *p && *p != ' '; p++) {
+            if (*p == 'K') castling |= bit(7);
+            if (*p == 'Q') castling |= bit(0);
+            if (*p == 'k') castling |= bit(63);
+            if (*p == 'q') castling |= bit(56);
+        }
+        if (*p != ' ') return false;
+        p++;
+        if (*p != '-') {
+            if (p[0] < 'a' || p[0] > 'h' || p[1] < '1' || p[1] > '8') return false;
+            ep = (p[1] - '1') * 8 + (p[0] - 'a');
+            p++;
+        }
+        p++;
+        if (*p == ' ') {
+            int hm = 0, fm = 1;
+            if (sscanf(p, " %d %d", &hm, &fm) >= 1) {
+                halfmove = hm;
+                fullmove = fm;
+            }
+        }
+        return (pt[KING] & occ[WHITE]) && (pt[KING] & occ[BLACK]);
     }
     int piece_at(int s) const
     {

@@ -887,6 +887,31 @@ int sc_test_dirichlet(uint64_t seed, float alpha, int n, float *out)
     return SC_OK;
 }
 
+static uint64_t perft_nodes(const Position &p, int depth)
+{
+    MoveList l;
+    p.legal_moves(l);
+    if (depth <= 1) return depth == 1 ? (uint64_t)l.n : 1;
+    uint64_t n = 0;
+    for (int i = 0; i < l.n; i++) {
+        Position c = p;
+        c.push(l.m[i]);
+        n += perft_nodes(c, depth - 1);
+    }
+    return n;
+}
+
+int sc_rules_perft(const char *fen, int depth, uint64_t *nodes)
+{
+    Position p;
+    if (!nodes || depth < 0 || depth > 7 || (fen ? !p.set_fen(fen) : (p.set_start(), false))) {
+        set_error("sc_rules_perft: bad argument");
+        return SC_E_INVAL;
+    }
+    *nodes = perft_nodes(p, depth);
+    return SC_OK;
+}
+
 int sc_rules_probe(const sc_move *history, int n_history, sc_move *legal_out, int *n_legal, sc_position *packed_out,
                    int *termination, int *winner)
 {

@@ -10,6 +10,7 @@ from .binding import (  # noqa: F401
     Arena,
     elo,
     rules_probe,
+    rules_perft,
     game_selfplay,
     random_positions,
     SCError,

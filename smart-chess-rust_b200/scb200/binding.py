@@ -23,7 +23,7 @@ DECLARED_SYMBOLS = [
     "sc_move_index_only", "sc_forward_only", "sc_launch_count", "sc_last_timing", "sc_set_timing", "sc_kernel_timing",
     "sc_eval_submit", "sc_eval_wait", "sc_selfplay_create", "sc_selfplay_run", "sc_selfplay_trace_json",
     "sc_selfplay_destroy", "sc_rules_probe", "sc_arena_create", "sc_encode_steps", "sc_timed_flops_per_leaf",
-    "sc_random_positions", "sc_test_dirichlet", "sc_game_selfplay",
+    "sc_random_positions", "sc_test_dirichlet", "sc_game_selfplay", "sc_rules_perft",
 ]
 
 
@@ -96,6 +96,7 @@ def load_library():
         L.sc_arena_create.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(SelfPlayConfig), C.POINTER(C.c_void_p)]
         L.sc_random_positions.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.sc_test_dirichlet.argtypes = [C.c_uint64, C.c_float, C.c_int, C.c_void_p]
+        L.sc_rules_perft.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_uint64)]
         L.sc_rules_probe.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.c_void_p,
                                      C.POINTER(C.c_int), C.POINTER(C.c_int)]
         _LIB = L
@@ -333,6 +334,13 @@ def game_selfplay(engine, rollout_num=20, num_steps=150, cpuct=2.5, epsilon=0.15
     if n < 0:
         raise SCError("sc_game_selfplay failed: " + L.sc_last_error().decode())
     return json.loads(buf.value.decode())
+
+
+def rules_perft(fen, depth: int) -> int:
+    """perft of the driver's native rules (fen None = start position)."""
+    n = C.c_uint64()
+    _check(load_library().sc_rules_perft(fen.encode() if fen else None, depth, C.byref(n)), "sc_rules_perft")
+    return int(n.value)
 
 
 def rules_probe(history):

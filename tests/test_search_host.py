@@ -300,3 +300,27 @@ def test_game_interface_mirror_equals_batched_driver_and_oracle(co):
         assert mirror == batched
     with pytest.raises(scb200.SCError):
         scb200.game_selfplay(None, rollout_num=0, evaluator="hash")
+
+
+def test_native_rules_perft_matches_published_tables():
+    """The product's own move generator (csrc/host/chess_rules.hpp, independent of the oracle's) against the
+    published perft tables: start position to depth 5, Kiwipete and four more standard test positions
+    (castling through check, en-passant pins, promotions with check, discovered checks)."""
+    import scb200
+
+    assert [scb200.rules_perft(None, d) for d in range(1, 6)] == [20, 400, 8902, 197281, 4865609]
+    cases = [
+        ("r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq - 0 1", [48, 2039, 97862, 4085603]),
+        ("8/2p5/3p4/KP5r/1R3p1k/8/4P1P1/8 w - - 0 1", [14, 191, 2812, 43238, 674624]),
+        ("r3k2r/Pppp1ppp/1b3nbN/nP6/BBP1P3/q4N2/Pp1P2PP/R2Q1RK1 w kq - 0 1", [6, 264, 9467, 422333]),
+        ("rnbq1k1r/pp1Pbppp/2p5/8/2B5/8/PPP1NnPP/RNBQK2R w KQ - 1 8", [44, 1486, 62379, 2103487]),
+        ("r4rk1/1pp1qppp/p1np1n2/2b1p1B1/2B1P1b1/P1NP1N2/1PP1QPPP/R4RK1 w - - 0 10", [46, 2079, 89890, 3894594]),
+        ("1k1r4/1r5p/p4n1P/1ppP1P2/PP6/4PP1b/3B4/R1N1K3 b - - 0 39", None),     # src/chess_fast.rs:84-98
+    ]
+    for fen, exp in cases:
+        if exp is None:
+            assert scb200.rules_perft(fen, 1) > 0
+            continue
+        assert [scb200.rules_perft(fen, d + 1) for d in range(len(exp))] == exp, fen
+    with pytest.raises(scb200.SCError):
+        scb200.rules_perft("not a fen", 1)

@@ -169,6 +169,36 @@ def cpu_reference_throughput(sd, games, budget_s: float, batch: int):
     return batched, b1, done, torch.get_num_threads()
 
 
+def cpu_reference_selfplay(sd, budget_s: float):
+    """The reference's self-play loop on the CPU (sequential search of src/mcts.rs restated in the oracle, one
+    leaf per forward): plies/s at 180 rollouts/move, (i) as the reference runs it -- `select` calls `predict` at
+    every level of every descent -- and (ii) with the priors cached on the children."""
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import chess_oracle as co
+    import net
+
+    def ev(game, depth, moves):
+        planes, meta = game.encode(depth)
+        with torch.no_grad():
+            lp, v = net.forward(sd, net.planes_i8_hwc_to_nchw(planes[None]), torch.from_numpy(meta[None]).float())
+        return co.post_process(lp[0].numpy(), game.move_indices(moves)), float(v[0, 0])
+
+    t = co.Tree(ev)
+    t0 = time.perf_counter()
+    rollouts = 0
+    while time.perf_counter() - t0 < budget_s:
+        t.search(10, 2.5)            # 10 more rollouts on the same root
+        rollouts += 10
+    el = time.perf_counter() - t0
+    evals, predicts = t.n_evals, t.n_predicts
+    cached = rollouts / el / 180.0
+    faithful = cached * evals / max(predicts, 1)
+    return {"plies_per_s_priors_cached": cached, "plies_per_s_predict_every_level": faithful,
+            "rollouts_timed": rollouts, "network_evals": evals, "predict_calls_of_the_reference": predicts}
+
+
 def reference_arm(args):
     """`--impl reference`: the reference's CPU implementation of the path.  The Rust binary cannot
     be built here (no cargo; python-chess and tch-rs absent), so this is the oracle port: the
@@ -452,7 +482,8 @@ def main():
             b, b1, n, thr = cpu_reference_throughput(sd, oracle_sample(512, seed=1000), args.cpu_budget, 64)
             cpu = {"value": b, "unit": "leaf evals/s", "cores": thr, "kind": "port",
                    "sample": f"{n} leaves of the same workload in batches of 64 (fp32 libtorch CPU oracle)",
-                   "batch1_value": b1, "host_cpus": os.cpu_count()}
+                   "batch1_value": b1, "host_cpus": os.cpu_count(),
+                   "selfplay_180_rollouts": cpu_reference_selfplay(sd, min(5.0, args.cpu_budget / 2))}
         h2d = int(pos.nbytes + moves.nbytes + off.nbytes)
         d2h = int(n_moves * 4 + B * 4)
         line = {

@@ -13,6 +13,10 @@
 // priors are stored on the children at expansion instead of re-running `predict` at every level of
 // every descent, positions are native bitboards (host/chess_rules.hpp) instead of python-chess
 // objects, and trees are split in two groups that alternate between host work and device work.
+// Batch rows are handed out densely (one atomic counter per group).  Optional, not reference-exact:
+// leaves_per_tree > 1 lets a tree contribute several leaves per batch, in-flight paths carrying a
+// virtual loss.  Arena mode (two networks, src/play.rs) keeps every game of a group at a ply of the
+// same parity, so a batch belongs to one network; finished games are replaced at the next even ply.
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -531,7 +535,7 @@ void finish_pending(sc_selfplay *sp, Tree &t, const float *priors, const float *
     t.n_pend = 0;
 }
 
-// arena: a tree only searches the ply its pipeline group is at, then waits for the others
+// arena: a tree only searches the ply its pipeline group is at, then waits for the others.
 // A finished game's slot starts the run's next game at the next EVEN group ply: White (the first network) is
 // to move at even group plies in every game of the group, so one batch never mixes the two networks.
 void advance_tree_arena(sc_selfplay *sp, Tree &t, int group_ply, const BatchOut &out, const float *priors,

@@ -166,7 +166,9 @@ typedef struct sc_selfplay_config {
     int32_t keep_traces;        /* keep the traces of finished games in memory (sc_selfplay_trace_json) */
     int32_t leaves_per_tree;    /* 0/1: one leaf per tree per batch, the reference's exact sequential search.
                                    K > 1: up to K leaves per tree per batch; in-flight paths carry a virtual loss
-                                   (one visit lost by the mover).  Not visit-count identical to the reference. */
+                                   (one visit lost by the mover).  Not visit-count identical to the reference.
+                                   -1: 1 while the trees fill the batch, then trees-of-the-group / trees-still-playing
+                                   (<= 16) so that the tail of a finite run keeps the device busy. */
 } sc_selfplay_config;
 
 typedef struct sc_selfplay_stats {

@@ -125,6 +125,8 @@ struct sc_selfplay {
         sc_engine *eng = nullptr;  // engine the in-flight batch was submitted to
         std::atomic<int> n_used{0};  // rows of the batch buffers filled by the current step (dense)
         int capacity = 0;            // trees of the group x leaves_per_tree
+        int k_now = 1;               // leaves per tree of the current step (leaves_per_tree = -1: follows the
+                                     // number of trees still playing, so that the batch stays full)
     } groups[2];
     int n_groups = 1;
     // stats
@@ -474,12 +476,13 @@ struct BatchOut {
     sc_move *moves;
     int32_t *cnt;
     std::atomic<int> *n_used;
+    int k;  // leaves per tree of this step
 };
 
 template <typename Ready>
 int collect_leaves(sc_selfplay *sp, Tree &t, const BatchOut &out, Ready finish_move)
 {
-    const int K = sp->cfg.leaves_per_tree > 1 ? sp->cfg.leaves_per_tree : 1;
+    const int K = out.k;
     if ((int)t.pend.size() < K) t.pend.resize(K);
     int collected = 0;
     for (;;) {
@@ -594,7 +597,7 @@ void run_group_slice(sc_selfplay *sp, int g, int worker, int n_workers)
     sc_selfplay::Group &G = sp->groups[g];
     const int per = (G.count + n_workers - 1) / n_workers;
     const int lo = worker * per, hi = std::min(G.count, lo + per);
-    const BatchOut out{G.pos, G.moves, G.cnt, &G.n_used};
+    const BatchOut out{G.pos, G.moves, G.cnt, &G.n_used, G.k_now};
     for (int i = lo; i < hi; i++) {
         Tree &t = sp->trees[G.first + i];
         if (sp->arena)
@@ -627,6 +630,21 @@ void worker_main(sc_selfplay *sp, int worker, int n_workers)
 // n_threads = T: the calling thread takes slice 0, T - 1 pool threads take the others
 void parallel_advance(sc_selfplay *sp, int g)
 {
+    {
+        // leaves per tree of this step
+        sc_selfplay::Group &G = sp->groups[g];
+        const int k = sp->cfg.leaves_per_tree;
+        if (k >= 0)
+            G.k_now = k > 1 ? k : 1;
+        else {
+            // auto: one leaf per tree (the reference's search) while most trees are playing; when games run out
+            // the remaining trees share the batch rows, up to 16 leaves each, with virtual loss
+            int active = 0;
+            for (int i = 0; i < G.count; i++) active += sp->trees[G.first + i].active ? 1 : 0;
+            int kk = active > 0 ? G.count / active : 1;
+            G.k_now = kk < 1 ? 1 : (kk > 16 ? 16 : kk);
+        }
+    }
     const int nw = (int)sp->workers.size();
     if (nw == 0) {
         run_group_slice(sp, g, 0, 1);
@@ -655,8 +673,8 @@ int sc_selfplay_create(sc_engine *e, const sc_selfplay_config *cfg, sc_selfplay 
         set_error("sc_selfplay_create: bad argument");
         return SC_E_INVAL;
     }
-    if (cfg->leaves_per_tree < 0 || cfg->leaves_per_tree > 64) {
-        set_error("sc_selfplay_create: leaves_per_tree must be 0..64");
+    if (cfg->leaves_per_tree < -1 || cfg->leaves_per_tree > 64) {
+        set_error("sc_selfplay_create: leaves_per_tree must be -1 (auto) or 0..64");
         return SC_E_INVAL;
     }
     const int kleaves = cfg->leaves_per_tree > 1 ? cfg->leaves_per_tree : 1;

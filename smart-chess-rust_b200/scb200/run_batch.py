@@ -29,7 +29,9 @@ def main(argv=None):
     ap.add_argument("--temperature-switch", type=int, default=30)
     ap.add_argument("--epsilon", type=float, default=0.15)
     ap.add_argument("--fp32", action="store_true", help="parity mode (FP32 FFMA) instead of bf16 tensor cores")
-    ap.add_argument("--leaves-per-tree", type=int, default=1)
+    ap.add_argument("--leaves-per-tree", type=int, default=1,
+                    help="1 = the reference's sequential search; K > 1 = K leaves per tree per batch (virtual loss); "
+                         "-1 = 1 until games run out, then the remaining games share the batch")
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--seed", type=int, default=0)
     a = ap.parse_args(argv)
@@ -45,7 +47,7 @@ def main(argv=None):
     sp = SelfPlay(eng, n_trees=trees, rollout_num=a.rollout_num, num_steps=a.num_steps, cpuct=a.cpuct, epsilon=a.epsilon,
                   with_noise=True, temperature_switch=a.temperature_switch, temperature=a.temperature,
                   seed=rank_seed(a.seed, rank), n_threads=a.threads or max(1, (os.cpu_count() or 8) // world),
-                  pipeline_groups=2 if trees >= 2 else 1, keep_traces=True, leaves_per_tree=kl)
+                  pipeline_groups=2 if trees >= 2 else 1, keep_traces=True, leaves_per_tree=a.leaves_per_tree)
     st = sp.run(max_games=len(mine))
     os.makedirs(a.prefix, exist_ok=True)
     for k, gid in enumerate(mine):

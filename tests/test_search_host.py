@@ -324,3 +324,30 @@ def test_native_rules_perft_matches_published_tables():
         assert [scb200.rules_perft(fen, d + 1) for d in range(len(exp))] == exp, fen
     with pytest.raises(scb200.SCError):
         scb200.rules_perft("not a fen", 1)
+
+
+def test_auto_leaves_per_tree_fills_the_tail(co):
+    """leaves_per_tree = -1: one leaf per tree while the trees fill the batch; when the run's games run out, the trees
+    still playing share the rows.  12 games on 8 trees: the last 4 run with two leaves each.  Same invariants as the
+    fixed multi-leaf mode, and fewer batches than the one-leaf mode needs for the same games."""
+    import scb200
+
+    def run(k):
+        sp = scb200.SelfPlay(None, n_trees=8, rollout_num=40, num_steps=10, cpuct=2.5, with_noise=False,
+                             temperature_switch=0, temperature=0.0, evaluator="hash", keep_traces=True, leaves_per_tree=k,
+                             pipeline_groups=1)
+        st = sp.run(max_games=12)
+        tr = [sp.trace(i) for i in range(12)]
+        sp.close()
+        return st, tr
+
+    st1, tr1 = run(1)
+    sta, tra = run(-1)
+    for st in (st1, sta):
+        assert st["games_finished"] == 12 and st["moves"] == 120 and st["rollouts"] == 120 * 40
+    assert tra[:8] == tr1[:8]                       # the first 8 games never share rows: identical to the one-leaf mode
+    for t in tra:
+        g = co.Game()
+        for mv, q, ch in t["steps"]:
+            assert [c[0] for c in ch] == g.legal_uci() and sum(c[1] for c in ch) == 39
+            g.push(mv)

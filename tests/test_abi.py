@@ -51,3 +51,36 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "chess_oracle" not in txt and "oracle/" not in txt and "import net" not in txt, f
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/sc_b200.h must be consumable from C (the Rust/cgo/JNI side binds a C ABI): a C99 translation unit that
+    includes it, checks the struct layouts the Rust shim mirrors, and links against libscb200.so."""
+    import subprocess
+
+    import scb200
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "sc_b200.h"
+int main(void) {
+    if (sizeof(sc_position) != 544 || sizeof(sc_move) != 4) return 1;
+    sc_engine *e = NULL;
+    /* no device work: a missing blob must come back as an error code with a message, not a crash */
+    int rc = sc_create("/nonexistent.scw", 0, SC_MODE_BF16, 8, &e);
+    if (rc == SC_OK || e != NULL) return 2;
+    if (sc_last_error() == NULL || sc_last_error()[0] == 0) return 3;
+    unsigned long long nodes = 0;
+    if (sc_rules_perft(NULL, 3, (uint64_t *)&nodes) != SC_OK || nodes != 8902) return 4;
+    printf("ok %d\n", rc);
+    return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    lib = scb200.lib_path()
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), str(src), "-o", str(exe),
+                           lib, "-Wl,-rpath," + os.path.dirname(lib)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)

@@ -640,7 +640,9 @@ int sc_eval(sc_engine *e, int n, const sc_position *pos, const sc_move *moves, c
     }
     if (n == 0) return SC_OK;
     const int total = move_off[n];
-    if (move_off[0] != 0 || total < 0 || total > e->max_moves_total) {
+    bool mono = move_off[0] == 0 && total >= 0 && total <= e->max_moves_total;
+    for (int i = 0; mono && i < n; i++) mono = move_off[i + 1] >= move_off[i];
+    if (!mono) {
         set_error("sc_eval: bad move offsets");
         return SC_E_INVAL;
     }

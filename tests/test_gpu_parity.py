@@ -230,6 +230,8 @@ def test_eval_edge_cases(co, nets, eng_f32_small):
     with pytest.raises(scb200.SCError):
         eng_f32_small.eval(np.zeros(4096, dtype=scb200.POSITION_DTYPE), np.zeros(0, dtype=scb200.MOVE_DTYPE),
                            np.zeros(4097, dtype=np.int32))
+    with pytest.raises(scb200.SCError):                      # offsets must be non-decreasing
+        eng_f32_small.eval(pos, moves, np.array([0, 218, 100, off[3]], dtype=np.int32))
 
 
 @pytest.fixture(scope="module")

@@ -55,16 +55,42 @@ def main(argv=None):
     ap.add_argument("--device", type=int, default=0)
     a = ap.parse_args(argv)
 
+    # under torchrun every rank plays its share of the games on its own GPU (games are independent: no collective
+    # until the final tally)
+    from .shard import games_for_rank, rank_seed
+
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    if world > 1:
+        a.device = int(os.environ.get("LOCAL_RANK", 0))
+        a.seed = rank_seed(a.seed, rank)
+        a.prefix = os.path.join(a.prefix, f"rank{rank}")
+        a.threads = a.threads or max(1, (os.cpu_count() or 8) // world)
+    n_games = games_for_rank(a.games, rank, world)
     os.makedirs(a.prefix, exist_ok=True)
-    mb = max(1, min(a.trees, a.games))
-    ea = Engine(a.white_checkpoint, a.device, SC_MODE_BF16, mb)
-    eb = Engine(a.black_checkpoint, a.device, SC_MODE_BF16, mb)
-    print(f"Results are saved in {a.prefix}")
-    t1, w1, b1 = play_half(ea, eb, a.games, a.prefix, "w", a)
-    print("Swapping the players")
-    t2, w2, b2 = play_half(eb, ea, a.games, a.prefix, "b", a)
-    ea.close()
-    eb.close()
+    tallies = [0] * 6
+    if n_games > 0:
+        mb = max(1, min(a.trees, n_games))
+        ea = Engine(a.white_checkpoint, a.device, SC_MODE_BF16, mb)
+        eb = Engine(a.black_checkpoint, a.device, SC_MODE_BF16, mb)
+        print(f"Results are saved in {a.prefix}")
+        t1, w1, b1 = play_half(ea, eb, n_games, a.prefix, "w", a)
+        print("Swapping the players")
+        t2, w2, b2 = play_half(eb, ea, n_games, a.prefix, "b", a)
+        ea.close()
+        eb.close()
+        tallies = [t1, w1, b1, t2, w2, b2]
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        dist.init_process_group("gloo")
+        t = torch.tensor(tallies, dtype=torch.int64)
+        dist.all_reduce(t)
+        tallies = [int(x) for x in t]
+        dist.destroy_process_group()
+        if rank != 0:
+            return 0
+    t1, w1, b1, t2, w2, b2 = tallies
     total, win, lost = t1 + t2, w1 + b2, b1 + w2            # from the first network's point of view
     print(f"{a.white_checkpoint}: {total}/{win}/{lost}")
     if 0 < win + (total - win - lost) / 2 < total:

@@ -71,6 +71,9 @@ int sc_destroy(sc_engine *e);
 const char *sc_last_error(void);
 /* number of residual blocks found in the blob; max batch; mode */
 int sc_info(const sc_engine *e, int *n_res_blocks, int *max_batch, int *mode);
+/* CUDA device ordinal the engine lives on and its SM count (one engine per worker thread / per GPU,
+ * the in-process form of scripts/run_batch:21's one process per job) */
+int sc_device_info(const sc_engine *e, int *device, int *num_sms);
 
 /* -------- the hot path: replaces chess_tch_predict (src/backends/torch.rs:89-146) and
  *          ChessOnnx::predict (src/backends/onnx.rs:13-56) for n non-terminal leaves ---------
@@ -152,7 +155,7 @@ double sc_timed_flops_per_leaf(const sc_engine *e);
  * any result.  Field names follow the reference's CLI (src/main.rs:25-60). */
 typedef struct sc_selfplay_config {
     int32_t n_trees;            /* games in flight (BASELINE configs[2]: 2048) */
-    int32_t rollout_num;        /* --rollout-num */
+    int32_t rollout_num;        /* --rollout-num; 0 together with rollout_factor 0 = the reference's default of 300 */
     int32_t num_steps;          /* --num-steps: maximum plies per game */
     float cpuct;                /* --cpuct */
     float epsilon;              /* --epsilon: Dirichlet(0.3) mix at the root (src/mcts.rs:171-184) */
@@ -169,6 +172,8 @@ typedef struct sc_selfplay_config {
                                    (one visit lost by the mover).  Not visit-count identical to the reference.
                                    -1: 1 while the trees fill the batch, then trees-of-the-group / trees-still-playing
                                    (<= 16) so that the tail of a finite run keeps the device busy. */
+    float rollout_factor;       /* --rollout-factor (src/main.rs:175-180): > 0 (then rollout_num must be 0): the rollouts
+                                   of a move are min(300, (int)(legal moves at the root * rollout_factor)) */
 } sc_selfplay_config;
 
 typedef struct sc_selfplay_stats {
@@ -181,15 +186,26 @@ typedef struct sc_selfplay_stats {
     int64_t batches;
     double seconds;         /* wall time of sc_selfplay_run */
     double wait_seconds;    /* of which: host waiting for the device */
+    int64_t games_dropped;  /* games abandoned because the network returned a non-finite prior / value for one of
+                               their leaves (the reference only prints a warning, src/backends/torch.rs:129-135);
+                               the slot starts the run's next game, the other games are not affected */
 } sc_selfplay_stats;
 
 typedef struct sc_selfplay sc_selfplay;
 
 int sc_selfplay_create(sc_engine *e, const sc_selfplay_config *cfg, sc_selfplay **out);
 /* plays until `max_games` games have finished (each tree slot starts a new game when one ends), or
- * until `max_moves` plies were played in total (<= 0: no limit), or `max_seconds` elapsed (<= 0: none) */
+ * until `max_moves` plies were played in total (<= 0: no limit), or `max_seconds` elapsed (<= 0: none).
+ * ONE run per driver object: a second call returns SC_E_STATE (create a new driver instead). */
 int sc_selfplay_run(sc_selfplay *sp, int64_t max_games, int64_t max_moves, double max_seconds,
                     sc_selfplay_stats *stats);
+/* In-process multi-GPU: runs n drivers (each created on its own engine, normally one engine per GPU) on n host
+ * threads of THIS process and returns when all have finished -- the in-process form of scripts/run_batch:21
+ * (the reference scales by independent processes; a Rust host has no torchrun).  Every driver gets the same
+ * limits; stats[i] belongs to sps[i].  Games are sharded by the caller (seeds / max_games per driver); there
+ * is no exchange between the drivers.  Returns the first non-zero status. */
+int sc_selfplay_run_many(sc_selfplay **sps, int n, int64_t max_games, int64_t max_moves, double max_seconds,
+                         sc_selfplay_stats *stats);
 /* trace of the k-th finished game in the format of src/trace.rs:23-32
  * ({"steps": [[uci, q, [[uci, n, q, uct], ...]], ...], "outcome": {...} | null}); returns the number
  * of bytes needed (including the NUL); copies at most `cap`. */
@@ -225,15 +241,15 @@ int sc_random_positions(int n, uint64_t seed, int max_ply, sc_position *pos_out,
  * uses rand_distr::Dirichlet(0.3)); lets the tests check its moments. */
 int sc_test_dirichlet(uint64_t seed, float alpha, int n, float *out);
 
+/* perft (number of leaf nodes of the legal-move tree of the given depth <= 7) of the driver's native rules from a
+ * FEN (NULL = start position): pins the move generator to the published perft tables. */
+int sc_rules_perft(const char *fen, int depth, uint64_t *nodes);
+
 /* Host rules probe: replays `n_history` moves from the start position with the driver's native rules
  * (the replacement of the python-chess calls at src/chess.rs:665-788) and reports what the reference
  * would see there: legal moves in python-chess generation order, the packed leaf `_encode` would be
  * given (node depth = ply), and outcome(claim_draw=True) (termination code of src/chess.rs:87-105 or
  * 0, winner 1/0/-1).  Returns SC_E_INVAL if a history move is not legal. */
-/* perft (number of leaf nodes of the legal-move tree of the given depth <= 7) of the driver's native rules from a
- * FEN (NULL = start position): pins the move generator to the published perft tables. */
-int sc_rules_perft(const char *fen, int depth, uint64_t *nodes);
-
 int sc_rules_probe(const sc_move *history, int n_history, sc_move *legal_out, int *n_legal, sc_position *packed_out,
                    int *termination, int *winner);
 

@@ -106,7 +106,8 @@ struct TcTowerLayerDesc {
     int relu;
 };
 int tc_tower_create(TcTower **out, const TcTowerLayerDesc *descs, int n, int boards_alloc);
-int tc_tower_launch(TcTower *t, int n_boards, int num_sms, cudaStream_t st);
+// group = tiles per CTA carried through all layers together (0 = all of the CTA's tiles)
+int tc_tower_launch(TcTower *t, int n_boards, int num_sms, int group, cudaStream_t st);
 void tc_tower_destroy(TcTower *t);
 
 }  // namespace scb

@@ -142,6 +142,10 @@ struct sc_engine {
     int timing = 0;
     // SCB200_FUSE_GATHER=0 keeps the stand-alone gather kernel (A/B runs)
     bool fuse_gather = !(getenv("SCB200_FUSE_GATHER") && getenv("SCB200_FUSE_GATHER")[0] == '0');
+    // A/B switches, read when the engine is created: SCB200_TOWER=0 one launch per layer instead of the whole-tower
+    // kernel; SCB200_TOWER_GROUP=n tiles per CTA carried through all layers together (0 = all)
+    bool tower_enabled = !(getenv("SCB200_TOWER") && getenv("SCB200_TOWER")[0] == '0');
+    int tower_group = getenv("SCB200_TOWER_GROUP") ? atoi(getenv("SCB200_TOWER_GROUP")) : 3;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float last_tower_ms = 0.f, last_total_ms = 0.f;
     cudaEvent_t tickets[SC_MAX_INFLIGHT] = {nullptr, nullptr, nullptr, nullptr};
@@ -428,11 +432,10 @@ static int run_network(sc_engine *e, int n, cudaStream_t st, const TcGather *gat
         e->launches += 3;
     } else {
         const int nb = e->alloc_boards;
-        static const bool tower_enabled = !(getenv("SCB200_TOWER") && getenv("SCB200_TOWER")[0] == '0');
         int trc = SC_E_STATE;
-        if (tower_enabled && e->tower) {
+        if (e->tower_enabled && e->tower) {
             SCB_CHECK(kev_mark(e, st));
-            trc = tc_tower_launch(e->tower, n, e->num_sms, st);
+            trc = tc_tower_launch(e->tower, n, e->num_sms, e->tower_group, st);
             if (trc == SC_OK) {
                 SCB_CHECK(kev_mark(e, st));
                 e->launches += 1;
@@ -598,6 +601,14 @@ int sc_info(const sc_engine *e, int *n_res_blocks, int *max_batch, int *mode)
     if (n_res_blocks) *n_res_blocks = e->n_blocks;
     if (max_batch) *max_batch = e->max_batch;
     if (mode) *mode = e->mode;
+    return SC_OK;
+}
+
+int sc_device_info(const sc_engine *e, int *device, int *num_sms)
+{
+    if (!e) return SC_E_INVAL;
+    if (device) *device = e->device;
+    if (num_sms) *num_sms = e->num_sms;
     return SC_OK;
 }
 
@@ -803,6 +814,15 @@ int sc_encode_steps(sc_engine *e, int n, const sc_move *played, const sc_move *c
         return SC_E_INVAL;
     }
     if (n == 0) return SC_OK;
+    if (child_off[0] != 0) {
+        set_error("sc_encode_steps: child_off[0] must be 0");
+        return SC_E_INVAL;
+    }
+    for (int i = 0; i < n; i++)
+        if (child_off[i + 1] < child_off[i]) {
+            set_error("sc_encode_steps: child_off must be non-decreasing");
+            return SC_E_INVAL;
+        }
     // ---- host: replay with the native rules (the reference replays through python-chess) -------------
     chess::Game g;
     std::vector<sc_position> pos((size_t)n);
@@ -811,14 +831,19 @@ int sc_encode_steps(sc_engine *e, int n, const sc_move *played, const sc_move *c
     for (int i = 0; i < n; i++) {
         chess::MoveList l;
         g.cur.legal_moves(l);
+        // the reference compares the SET of children with the SET of legal moves (src/lib.rs:84-96): every legal
+        // move must be hit exactly once, so a duplicated child cannot stand in for a missing one
         const int cb = child_off[i], ce = child_off[i + 1];
         bool ok = (ce - cb) == l.n;
+        bool seen[256] = {false};
         for (int k = cb; ok && k < ce; k++) {
-            bool found = false;
-            for (int j = 0; j < l.n; j++)
-                found = found || (l.m[j].from == child_moves[k].from && l.m[j].to == child_moves[k].to &&
-                                  l.m[j].promo == child_moves[k].promo);
-            ok = found;
+            int hit = -1;
+            for (int j = 0; j < l.n && hit < 0; j++)
+                if (l.m[j].from == child_moves[k].from && l.m[j].to == child_moves[k].to &&
+                    l.m[j].promo == child_moves[k].promo)
+                    hit = j;
+            ok = hit >= 0 && !seen[hit];
+            if (ok) seen[hit] = true;
         }
         if (!ok) {
             set_error("sc_encode_steps: inconsistent moves at ply " + std::to_string(i));

@@ -50,7 +50,8 @@ double uniform01(void *ctx) { return static_cast<scb::host::Rng *>(ctx)->uniform
 
 extern "C" int64_t sc_game_selfplay(sc_engine *e, const sc_selfplay_config *cfg, char *buf, int64_t cap)
 {
-    if (!cfg || cfg->rollout_num <= 0 || cfg->num_steps <= 0 || (cfg->evaluator == 0 && !e) ||
+    if (!cfg || cfg->rollout_num < 0 || cfg->rollout_factor < 0.f || (cfg->rollout_num > 0 && cfg->rollout_factor > 0.f) ||
+        cfg->num_steps <= 0 || (cfg->evaluator == 0 && !e) ||
         (cfg->evaluator != 0 && cfg->evaluator != 1)) {
         scb::set_error("sc_game_selfplay: bad argument");
         return -1;
@@ -71,7 +72,11 @@ extern "C" int64_t sc_game_selfplay(sc_engine *e, const sc_selfplay_config *cfg,
         std::optional<Outcome> outcome;
         for (int i = 0; i < cfg->num_steps; i++) {
             const float temperature = i < cfg->temperature_switch ? 1.0f : cfg->temperature;
-            mcts::mcts<Game<BoardState>, BoardState>(*chess, cursor.arc(), state, cfg->rollout_num, cfg->cpuct, cfg->epsilon,
+            // src/main.rs:175-180
+            const int rollout = cfg->rollout_factor > 0.f
+                                    ? std::min(300, (int)((float)state.legal_moves().size() * cfg->rollout_factor))
+                                    : (cfg->rollout_num > 0 ? cfg->rollout_num : 300);
+            mcts::mcts<Game<BoardState>, BoardState>(*chess, cursor.arc(), state, rollout, cfg->cpuct, cfg->epsilon,
                                                      cfg->with_noise != 0, dirichlet_noise, &rng);
             scb::host::TraceStep st;
             st.q = cursor.current().q_value;

@@ -77,6 +77,8 @@ struct Tree {
     int n_pend = 0;
     // current search / game
     int rollouts_done = 0;
+    int rollout_target = 0;  // rollouts of the current move (--rollout-num, or --rollout-factor x legal moves at the root)
+    bool failed = false;     // the network returned a non-finite prior / value for one of this game's leaves
     int move_index = 0;      // `i` of the self-play loop (main.rs:168)
     int ply_offset = 0;      // arena: the (even) group ply at which this slot's current game started
     bool active = true;
@@ -99,6 +101,8 @@ struct Tree {
         move_index = 0;
         n_pend = 0;
         game_over = false;
+        failed = false;
+        rollout_target = -1;  // set before the first descent of every move (move_rollouts)
         trace = TraceRec();
         (void)seed;
     }
@@ -131,7 +135,8 @@ struct sc_selfplay {
     int n_groups = 1;
     // stats
     std::atomic<int64_t> leaf_evals{0}, terminal_evals{0}, rollouts{0}, moves{0}, games_finished{0}, white{0}, black{0},
-        draws{0}, unfinished{0}, games_started{0};
+        draws{0}, unfinished{0}, games_started{0}, games_dropped{0};
+    bool ran = false;  // sc_selfplay_run is single-shot
     int64_t batches = 0;
     int64_t max_games = 0, max_moves = 0;
     std::mutex trace_mu;
@@ -169,6 +174,17 @@ inline void apply_vloss(Tree &t, const std::vector<int> &path, float sign)
         c.n += (int)sign;
         c.q += sign * (c.step_color == WHITE ? 1.f : -1.f);  // mover was Black iff White is to move after it
     }
+}
+
+// rollouts of the move the tree is about to search (src/main.rs:175-180)
+inline int move_rollouts(const sc_selfplay_config &cfg, Tree &t)
+{
+    if (cfg.rollout_factor > 0.f) {
+        MoveList l;
+        t.game.cur.legal_moves(l);
+        return std::min(300, (int)((float)l.n * cfg.rollout_factor));
+    }
+    return cfg.rollout_num > 0 ? cfg.rollout_num : 300;
 }
 
 // expansion (src/mcts.rs:269-283) + backward (src/mcts.rs:90-98) for one pending leaf
@@ -369,6 +385,7 @@ bool play_move(sc_selfplay *sp, Tree &t)
         if (!over && t.move_index >= cfg.num_steps) over = true;  // loop bound: trace saved without outcome
     }
     t.rollouts_done = 0;
+    t.rollout_target = -1;
     if (over) {
         if (t.trace.has_outcome) {
             if (t.trace.winner == WHITE) sp->white++;
@@ -447,6 +464,7 @@ void play_move_arena(sc_selfplay *sp, Tree &t)
     t.nodes.push_back(nr);
     t.root = 0;
     t.rollouts_done = 0;
+    t.rollout_target = -1;
     t.move_index++;
     sp->moves.fetch_add(1, std::memory_order_relaxed);
     int w;
@@ -486,7 +504,8 @@ int collect_leaves(sc_selfplay *sp, Tree &t, const BatchOut &out, Ready finish_m
     if ((int)t.pend.size() < K) t.pend.resize(K);
     int collected = 0;
     for (;;) {
-        if (t.rollouts_done + collected >= sp->cfg.rollout_num) {
+        if (t.rollout_target < 0) t.rollout_target = move_rollouts(sp->cfg, t);
+        if (t.rollouts_done + collected >= t.rollout_target) {
             if (collected > 0) break;           // the move's last evaluations are in flight
             if (!finish_move()) break;          // move played / game over / tree waits
             continue;
@@ -529,13 +548,33 @@ int collect_leaves(sc_selfplay *sp, Tree &t, const BatchOut &out, Ready finish_m
     return collected;
 }
 
+// Per-game failure isolation: a leaf whose priors / value came back non-finite poisons only its own game.  The
+// reference prints a warning and plays on with NaNs in the tree (src/backends/torch.rs:129-135); here the game is
+// dropped and counted, the slot starts the run's next game, every other game of the batch is untouched.
 void finish_pending(sc_selfplay *sp, Tree &t, const float *priors, const float *value)
 {
     for (int i = 0; i < t.n_pend; i++) {
         Tree::Pending &P = t.pend[i];
-        finish_rollout(sp, t, P, priors + (size_t)P.slot * SC_MAX_MOVES, value[P.slot]);
+        const float *pr = priors + (size_t)P.slot * SC_MAX_MOVES;
+        bool ok = std::isfinite(value[P.slot]);
+        for (int k = 0; ok && k < P.moves.n; k++) ok = std::isfinite(pr[k]);
+        if (!ok) t.failed = true;
+        if (!t.failed) finish_rollout(sp, t, P, pr, value[P.slot]);
     }
     t.n_pend = 0;
+    if (t.failed) {
+        sp->games_dropped++;
+        const int64_t started = sp->games_started.fetch_add(1) + 1;
+        if (sp->max_games > 0 && started > sp->max_games) {
+            t.new_game(0);
+            t.active = false;
+        } else {
+            const int off = t.ply_offset, mi = t.move_index;
+            t.new_game(0);
+            // arena: the replacement game starts at the next even group ply after the one the slot was searching
+            if (sp->arena) t.ply_offset = (off + mi + 2) & ~1;
+        }
+    }
 }
 
 // arena: a tree only searches the ply its pipeline group is at, then waits for the others.
@@ -668,7 +707,11 @@ extern "C" {
 
 int sc_selfplay_create(sc_engine *e, const sc_selfplay_config *cfg, sc_selfplay **out)
 {
-    if (!cfg || !out || cfg->n_trees <= 0 || cfg->rollout_num <= 0 || cfg->num_steps <= 0 ||
+    if (cfg && cfg->rollout_factor > 0.f && cfg->rollout_num > 0) {
+        set_error("sc_selfplay_create: both rollout_factor and rollout_num are specified");  // main.rs:179 panics
+        return SC_E_INVAL;
+    }
+    if (!cfg || !out || cfg->n_trees <= 0 || cfg->rollout_num < 0 || cfg->rollout_factor < 0.f || cfg->num_steps <= 0 ||
         (cfg->evaluator == 0 && !e) || (cfg->evaluator != 0 && cfg->evaluator != 1)) {
         set_error("sc_selfplay_create: bad argument");
         return SC_E_INVAL;
@@ -688,8 +731,8 @@ int sc_selfplay_create(sc_engine *e, const sc_selfplay_config *cfg, sc_selfplay 
     // of a single 2048 batch.
     int size0 = sp->n_groups == 1 ? cfg->n_trees : (cfg->n_trees + 1) / 2;
     if (sp->n_groups == 2 && e) {
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+        int sms = 148, dev = 0;
+        sc_device_info(e, &dev, &sms);  // the engine's device, not device 0
         const int wave = 2 * sms;
         if (size0 * kleaves >= wave) size0 = std::max(1, size0 * kleaves / wave * wave / kleaves);
     }
@@ -768,6 +811,11 @@ int sc_arena_create(sc_engine *white, sc_engine *black, const sc_selfplay_config
 int sc_selfplay_run(sc_selfplay *sp, int64_t max_games, int64_t max_moves, double max_seconds, sc_selfplay_stats *stats)
 {
     if (!sp) return SC_E_INVAL;
+    if (sp->ran) {
+        set_error("sc_selfplay_run: a driver object plays one run; create a new one");
+        return SC_E_STATE;
+    }
+    sp->ran = true;
     using clk = std::chrono::steady_clock;
     const auto t0 = clk::now();
     sp->max_games = max_games;
@@ -822,12 +870,17 @@ int sc_selfplay_run(sc_selfplay *sp, int64_t max_games, int64_t max_moves, doubl
             }
         }
         if (max_seconds > 0 && std::chrono::duration<double>(clk::now() - t0).count() > max_seconds) {
+            // time is up: take the results of the batches in flight into the trees (no virtual visit, no pending
+            // flag is left behind), then stop
+            for (int g = 0; g < sp->n_groups; g++) {
+                sc_selfplay::Group &G = sp->groups[g];
+                if (!G.inflight) continue;
+                rc = sc_eval_wait(G.eng ? G.eng : sp->eng, G.ticket);
+                G.inflight = false;
+                if (rc != SC_OK) break;
+                for (int i = 0; i < G.count; i++) finish_pending(sp, sp->trees[G.first + i], G.priors, G.value);
+            }
             for (auto &t : sp->trees) t.active = false;
-            for (int g = 0; g < sp->n_groups; g++)
-                if (sp->groups[g].inflight) {
-                    sc_eval_wait(sp->groups[g].eng ? sp->groups[g].eng : sp->eng, sp->groups[g].ticket);
-                    sp->groups[g].inflight = false;
-                }
             break;
         }
     }
@@ -844,8 +897,33 @@ int sc_selfplay_run(sc_selfplay *sp, int64_t max_games, int64_t max_moves, doubl
         stats->batches = sp->batches;
         stats->seconds = std::chrono::duration<double>(clk::now() - t0).count();
         stats->wait_seconds = wait_s;
+        stats->games_dropped = sp->games_dropped;
     }
     return rc;
+}
+
+int sc_selfplay_run_many(sc_selfplay **sps, int n, int64_t max_games, int64_t max_moves, double max_seconds,
+                         sc_selfplay_stats *stats)
+{
+    if (!sps || n <= 0 || !stats) {
+        set_error("sc_selfplay_run_many: bad argument");
+        return SC_E_INVAL;
+    }
+    std::vector<int> rcs((size_t)n, SC_OK);
+    std::vector<std::string> errs((size_t)n);
+    std::vector<std::thread> th;
+    for (int i = 0; i < n; i++)
+        th.emplace_back([&, i] {
+            rcs[i] = sc_selfplay_run(sps[i], max_games, max_moves, max_seconds, stats + i);
+            if (rcs[i] != SC_OK) errs[i] = sc_last_error();  // the message is thread-local
+        });
+    for (auto &t : th) t.join();
+    for (int i = 0; i < n; i++)
+        if (rcs[i] != SC_OK) {
+            set_error("driver " + std::to_string(i) + ": " + errs[i]);
+            return rcs[i];
+        }
+    return SC_OK;
 }
 
 int64_t sc_selfplay_trace_json(sc_selfplay *sp, int64_t k, char *buf, int64_t cap)

@@ -38,6 +38,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -1393,7 +1395,13 @@ int tc_conv_create(TcConv **out, const __nv_bfloat16 *w, int taps, int k_per_tap
         }
         c->pair_ok = true;
     }
-    static bool attr_set = false;
+    // function attributes belong to the device (context): set them once per device, not once per process
+    static std::mutex attr_mu;
+    static std::map<int, bool> attr_done;
+    int dev = 0;
+    SCB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(attr_mu);
+    bool &attr_set = attr_done[dev];
     if (!attr_set) {
         SCB_CHECK((set_smem_attr<256, EPI_LN, true>()));
         SCB_CHECK((set_smem_attr<256, EPI_LN_SE, true>()));
@@ -1419,6 +1427,27 @@ void tc_conv_set_se(TcConv *c, const void *w1p, const float *b1, const void *w2p
 }
 
 void tc_conv_destroy(TcConv *c) { delete c; }
+
+
+// SCB200_PHASE_PROFILE=1: [grid][16] phase cycle counters, one buffer per device, sized from the device's SM count
+static int prof_buffer(int num_sms, cudaStream_t st, long long **out)
+{
+    static std::mutex mu;
+    static std::map<int, std::pair<long long *, int>> bufs;
+    int dev = 0;
+    SCB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    auto &b = bufs[dev];
+    if (b.second < num_sms) {
+        if (b.first) cudaFree(b.first);
+        b.first = nullptr;
+        SCB_CUDA(cudaMalloc(&b.first, (size_t)num_sms * 16 * sizeof(long long)));
+        b.second = num_sms;
+    }
+    SCB_CUDA(cudaMemsetAsync(b.first, 0, (size_t)num_sms * 16 * sizeof(long long), st));
+    *out = b.first;
+    return SC_OK;
+}
 
 // ---- whole-tower kernel --------------------------------------------------------------------------------
 struct TcTower {
@@ -1482,7 +1511,7 @@ void tc_tower_destroy(TcTower *t)
 
 // returns SC_E_STATE (without an error message) when the batch needs more tile slots per CTA than the
 // kernel tracks; the caller then runs the layers one launch at a time
-int tc_tower_launch(TcTower *t, int n_boards, int num_sms, cudaStream_t st)
+int tc_tower_launch(TcTower *t, int n_boards, int num_sms, int group, cudaStream_t st)
 {
     if (n_boards <= 0) return SC_OK;
     const int n_tiles = (n_boards + 1) / 2;
@@ -1497,7 +1526,6 @@ int tc_tower_launch(TcTower *t, int n_boards, int num_sms, cudaStream_t st)
     a.n_splits = 1;
     a.layers = t->d_layers;
     a.n_layers = t->n_layers;
-    static const int group = getenv("SCB200_TOWER_GROUP") ? atoi(getenv("SCB200_TOWER_GROUP")) : 3;
     a.group = group;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(g2);
@@ -1512,19 +1540,18 @@ int tc_tower_launch(TcTower *t, int n_boards, int num_sms, cudaStream_t st)
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     static CUtensorMap dummy;  // the layer array carries the tensor maps
-    static long long *d_prof = nullptr;
+    long long *d_prof = nullptr;
     static const bool want_prof = getenv("SCB200_PHASE_PROFILE") != nullptr;
     if (want_prof) {
-        if (!d_prof) SCB_CUDA(cudaMalloc(&d_prof, 148 * 16 * sizeof(long long)));
-        SCB_CUDA(cudaMemsetAsync(d_prof, 0, 148 * 16 * sizeof(long long), st));
+        SCB_CHECK(prof_buffer(num_sms, st, &d_prof));
         a.prof = d_prof;
     }
     SCB_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<256, EPI_LN_SE, true, true, true>, dummy, dummy, a));
     SCB_CUDA(cudaGetLastError());
     if (want_prof) {
-        static long long h[148 * 16];
+        std::vector<long long> h((size_t)num_sms * 16);
         SCB_CUDA(cudaStreamSynchronize(st));
-        SCB_CUDA(cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost));
+        SCB_CUDA(cudaMemcpy(h.data(), d_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         double acc[16] = {0};
         for (int b = 0; b < g2; b += 2)  // leader CTAs carry the MMA counters
             for (int k = 0; k < 16; k++) acc[k] += (double)h[b * 16 + k] / (g2 / 2);
@@ -1566,11 +1593,10 @@ int tc_conv_launch(TcConv *c, const __nv_bfloat16 *in, int rows_alloc, int n_uni
     }
     TcArgs a;
     memset(&a, 0, sizeof(a));
-    static long long *d_prof = nullptr;
+    long long *d_prof = nullptr;
     static const bool want_prof = getenv("SCB200_PHASE_PROFILE") != nullptr;
     if (want_prof) {
-        if (!d_prof) SCB_CUDA(cudaMalloc(&d_prof, 148 * 16 * sizeof(long long)));
-        SCB_CUDA(cudaMemsetAsync(d_prof, 0, 148 * 16 * sizeof(long long), st));
+        SCB_CHECK(prof_buffer(num_sms, st, &d_prof));
         a.prof = d_prof;
     }
     a.out = out;
@@ -1653,9 +1679,9 @@ launched:
     SCB_CUDA(cudaGetLastError());
     if (want_prof) {
         // debugging aid: per-phase SM-cycle counters of this launch, averaged over CTAs (synchronous!)
-        static long long h[148 * 16];
+        std::vector<long long> h((size_t)num_sms * 16);
         SCB_CUDA(cudaStreamSynchronize(st));
-        SCB_CUDA(cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost));
+        SCB_CUDA(cudaMemcpy(h.data(), d_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         double acc[16] = {0};
         for (int b = 0; b < grid; b++)
             for (int k = 0; k < 16; k++) acc[k] += (double)h[b * 16 + k] / grid;

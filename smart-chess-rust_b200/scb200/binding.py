@@ -23,7 +23,8 @@ DECLARED_SYMBOLS = [
     "sc_move_index_only", "sc_forward_only", "sc_launch_count", "sc_last_timing", "sc_set_timing", "sc_kernel_timing",
     "sc_eval_submit", "sc_eval_wait", "sc_selfplay_create", "sc_selfplay_run", "sc_selfplay_trace_json",
     "sc_selfplay_destroy", "sc_rules_probe", "sc_arena_create", "sc_encode_steps", "sc_timed_flops_per_leaf",
-    "sc_random_positions", "sc_test_dirichlet", "sc_game_selfplay", "sc_rules_perft",
+    "sc_random_positions", "sc_test_dirichlet", "sc_game_selfplay", "sc_rules_perft", "sc_device_info",
+    "sc_selfplay_run_many",
 ]
 
 
@@ -33,14 +34,14 @@ class SelfPlayConfig(C.Structure):
                 ("epsilon", C.c_float), ("with_noise", C.c_int32), ("temperature_switch", C.c_int32),
                 ("temperature", C.c_float), ("seed", C.c_uint64), ("n_threads", C.c_int32), ("evaluator", C.c_int32),
                 ("pipeline_groups", C.c_int32), ("keep_traces", C.c_int32),
-                ("leaves_per_tree", C.c_int32)]
+                ("leaves_per_tree", C.c_int32), ("rollout_factor", C.c_float)]
 
 
 class SelfPlayStats(C.Structure):
     _fields_ = [("leaf_evals", C.c_int64), ("terminal_evals", C.c_int64), ("rollouts", C.c_int64), ("moves", C.c_int64),
                 ("games_finished", C.c_int64), ("white_wins", C.c_int64), ("black_wins", C.c_int64),
                 ("draws", C.c_int64), ("unfinished", C.c_int64), ("batches", C.c_int64), ("seconds", C.c_double),
-                ("wait_seconds", C.c_double)]
+                ("wait_seconds", C.c_double), ("games_dropped", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -70,6 +71,9 @@ def load_library():
         L.sc_create.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         L.sc_destroy.argtypes = [C.c_void_p]
         L.sc_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.sc_device_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.sc_selfplay_run_many.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int64, C.c_int64, C.c_double,
+                                           C.POINTER(SelfPlayStats)]
         L.sc_eval.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 6
         L.sc_eval_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                      C.c_void_p, C.c_void_p]
@@ -158,15 +162,22 @@ class Engine:
         return self._h
 
     def info(self):
-        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        a, b, c, d, s = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
         _check(load_library().sc_info(self._h, C.byref(a), C.byref(b), C.byref(c)), "sc_info")
-        return {"n_res_blocks": a.value, "max_batch": b.value, "mode": c.value}
+        _check(load_library().sc_device_info(self._h, C.byref(d), C.byref(s)), "sc_device_info")
+        return {"n_res_blocks": a.value, "max_batch": b.value, "mode": c.value, "device": d.value, "num_sms": s.value}
 
     def eval(self, positions: np.ndarray, moves: np.ndarray, move_off: np.ndarray, priors_out=None, value_out=None,
              stream: int = 0):
         """`predict` for n leaves: returns (priors CSR float32, values float32[n])."""
         n = len(positions)
         positions = np.ascontiguousarray(positions, dtype=POSITION_DTYPE) if not hasattr(positions, "data_ptr") else positions
+        # numpy inputs are coerced to the ABI's element types (an int64 move_off or a strided view would otherwise be
+        # reinterpreted); torch tensors (pinned host buffers of bench.py) are taken as they are
+        if not hasattr(moves, "data_ptr"):
+            moves = np.ascontiguousarray(moves, dtype=MOVE_DTYPE)
+        if not hasattr(move_off, "data_ptr"):
+            move_off = np.ascontiguousarray(move_off, dtype=np.int32)
         total = int(move_off[n]) if n else 0
         if priors_out is None:
             priors_out = np.zeros(max(total, 1), dtype=np.float32)
@@ -274,14 +285,15 @@ class SelfPlay:
 
     def __init__(self, engine, n_trees=2048, rollout_num=180, num_steps=150, cpuct=2.5, epsilon=0.15,
                  with_noise=True, temperature_switch=4, temperature=0.0, seed=0, n_threads=0, evaluator="engine",
-                 pipeline_groups=2, keep_traces=False, black_engine=None, arena=False, leaves_per_tree=1):
+                 pipeline_groups=2, keep_traces=False, black_engine=None, arena=False, leaves_per_tree=1,
+                 rollout_factor=0.0):
         import json as _json
 
         self._json = _json
         L = load_library()
         cfg = SelfPlayConfig(n_trees, rollout_num, num_steps, cpuct, epsilon, int(with_noise), temperature_switch,
                              temperature, seed, n_threads, 0 if evaluator == "engine" else 1, pipeline_groups,
-                             int(keep_traces), int(leaves_per_tree))
+                             int(keep_traces), int(leaves_per_tree), float(rollout_factor))
         h = C.c_void_p()
         self._engine = (engine, black_engine)  # keep alive
         if arena:
@@ -297,6 +309,15 @@ class SelfPlay:
         st = SelfPlayStats()
         _check(load_library().sc_selfplay_run(self._h, max_games, max_moves, max_seconds, C.byref(st)), "sc_selfplay_run")
         return st.as_dict()
+
+    @staticmethod
+    def run_many(drivers, max_games=0, max_moves=0, max_seconds=0.0):
+        """sc_selfplay_run_many: every driver on its own host thread of this process (one engine per GPU)."""
+        n = len(drivers)
+        hs = (C.c_void_p * n)(*[d._h for d in drivers])
+        st = (SelfPlayStats * n)()
+        _check(load_library().sc_selfplay_run_many(hs, n, max_games, max_moves, max_seconds, st), "sc_selfplay_run_many")
+        return [s.as_dict() for s in st]
 
     def trace(self, k: int):
         L = load_library()
@@ -327,7 +348,7 @@ def game_selfplay(engine, rollout_num=20, num_steps=150, cpuct=2.5, epsilon=0.15
 
     L = load_library()
     cfg = SelfPlayConfig(1, rollout_num, num_steps, cpuct, epsilon, int(with_noise), temperature_switch, temperature, seed,
-                         1, 0 if evaluator == "engine" else 1, 1, 1, 1)
+                         1, 0 if evaluator == "engine" else 1, 1, 1, 1, 0.0)
     cap = 1 << 24
     buf = C.create_string_buffer(cap)
     n = L.sc_game_selfplay(engine.handle if engine is not None else None, C.byref(cfg), buf, cap)

@@ -18,7 +18,8 @@ def play_half(white, black, n_games, prefix, tag, a):
     from . import Arena
 
     ar = Arena(white, black, n_trees=max(1, min(a.trees, n_games)), rollout=a.rollout, cpuct=a.cpuct,
-               temperature=a.temperature, temperature_switch=a.temperature_switch, max_plies=a.max_plies, seed=a.seed,
+               temperature=a.temperature, temperature_switch=a.temperature_switch, max_plies=a.max_plies,
+               seed=a.seed * 2 + (1 if tag == "b" else 0),   # the colour-swapped half draws from its own RNG streams
                n_threads=a.threads or (os.cpu_count() or 8), keep_traces=True,
                pipeline_groups=2 if min(a.trees, n_games) >= 2 else 1)
     st = ar.run(max_games=n_games)

@@ -59,7 +59,9 @@ def test_gpu_selfplay_visit_counts_match_cpu_reference_search(co, small_net):
             break
         assert np.allclose([c[2] for c in ch], rq, atol=5e-3)
     print("first divergence ply:", first_div)
-    assert first_div is None or first_div >= 3
+    # measured on B200 (rounds 1-2): no divergence over the tested plies; the kernels are deterministic, so anything
+    # else is a regression (a legitimate near-tie flip would show up here with its ply)
+    assert first_div is None, f"visit counts diverge from the CPU reference search at ply {first_div}"
     sp.close()
     eng.close()
 
@@ -238,8 +240,8 @@ def test_cfg1_game_reproduces_reference_visit_tables(tmp_path):
         max_dq = max(max_dq, max(abs(c[2] - r[2]) for c, r in zip(ch, ref["children"])), abs(q - ref["root_q"]))
     print("plies compared:", min(len(tr["steps"]), len(gold["steps"])), "first divergence:", first_div, "max |dQ|:", max_dq)
     assert max_dq < 1e-3
-    # uct near-ties may flip on the 1e-4 forward tolerance; the game must agree well into the middle game
-    assert first_div is None or first_div >= 20
+    # measured on B200 (rounds 1-2): all 82 plies identical, max |dQ| 5.2e-6; deterministic kernels -> pinned to that
+    assert first_div is None, f"golden configs[0] game diverges at ply {first_div} (max |dQ| so far {max_dq:.2e})"
     if first_div is None:
         assert len(tr["steps"]) == len(gold["steps"])
         # the golden game ends with no legal moves: the driver must have seen the same terminal position
@@ -336,3 +338,69 @@ def test_leader_board_script(co, small_net, tmp_path, capsys):
                 assert mv in g.legal_uci()
                 g.push(mv)
             assert len(tr["steps"]) <= 40
+
+
+def test_two_engines_two_drivers_one_process(co, small_net):
+    """In-process multi-GPU (north_star: one worker per GPU, each with its own tree pool and CUDA streams; reference
+    analogue scripts/run_batch:21): N engines on N devices, N drivers on N host threads of ONE process
+    (sc_selfplay_run_many), results identical to the runs of the same seeds one after another on one GPU.
+    With a single visible GPU both engines live on device 0 (still two engines, two streams, two host threads)."""
+    import scb200
+
+    sd, blob = small_net
+    ndev = torch.cuda.device_count()
+    devs = [0, 1 % ndev]
+    kw = dict(n_trees=16, rollout_num=24, num_steps=8, cpuct=2.5, with_noise=True, temperature_switch=3, temperature=0.0,
+              keep_traces=True, pipeline_groups=2, n_threads=2)
+
+    def traces(sp, n):
+        return sorted(str(sp.trace(k)) for k in range(n))
+
+    solo = []
+    for i, seed in enumerate((11, 12)):
+        eng = scb200.Engine(blob, 0, scb200.SC_MODE_BF16, 16)
+        sp = scb200.SelfPlay(eng, seed=seed, **kw)
+        st = sp.run(max_games=16)
+        assert st["games_finished"] == 16
+        solo.append(traces(sp, 16))
+        sp.close()
+        eng.close()
+    engs = [scb200.Engine(blob, d, scb200.SC_MODE_BF16, 16) for d in devs]
+    assert [e.info()["device"] for e in engs] == devs
+    sps = [scb200.SelfPlay(e, seed=seed, **kw) for e, seed in zip(engs, (11, 12))]
+    stats = scb200.SelfPlay.run_many(sps, max_games=16)
+    assert [s["games_finished"] for s in stats] == [16, 16]
+    for sp, want in zip(sps, solo):
+        assert traces(sp, 16) == want
+    print("in-process drivers on devices", devs, "leaf evals", [s["leaf_evals"] for s in stats])
+    for sp in sps:
+        sp.close()
+    for e in engs:
+        e.close()
+
+
+def test_non_finite_leaf_drops_only_its_own_game(co, tmp_path):
+    """Per-game failure isolation: a network that returns NaN for SOME positions (value-FC meta column of the
+    side-to-move's king-side castling right set to +inf: inf * 0 = NaN once that right is gone, finite -- tanh(+-inf) --
+    while it is there) must cost exactly the games that run into such a leaf; the others finish."""
+    import net
+    import scb200
+
+    sd = net.perturb_norm_params(net.init_state_dict(2, 7), 1234)
+    w = sd["value_head.ffn.0.weight"].clone()
+    w[0, 64 * 256 + 2] = float("inf")      # ONE hidden unit: inf * 1 -> value +-1 (finite); inf * 0 -> NaN
+    sd["value_head.ffn.0.weight"] = w
+    blob = str(tmp_path / "nan.scw")
+    scb200.write_blob(sd, blob)
+    eng = scb200.Engine(blob, 0, scb200.SC_MODE_BF16, 64)
+    sp = scb200.SelfPlay(eng, n_trees=64, rollout_num=16, num_steps=14, cpuct=2.5, with_noise=True, temperature_switch=14,
+                         temperature=1.0, keep_traces=True, pipeline_groups=2, n_threads=2, seed=5)
+    st = sp.run(max_games=64)
+    print("dropped", st["games_dropped"], "finished", st["games_finished"])
+    assert st["games_dropped"] > 0 and st["games_finished"] > 0
+    assert st["games_dropped"] + st["games_finished"] == 64
+    for k in range(st["games_finished"]):
+        tr = sp.trace(k)
+        assert all(np.isfinite(s[1]) and all(np.isfinite(c[2]) for c in s[2]) for s in tr["steps"])
+    sp.close()
+    eng.close()

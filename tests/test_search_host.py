@@ -299,7 +299,41 @@ def test_game_interface_mirror_equals_batched_driver_and_oracle(co):
                                       seed=seed, evaluator="hash")
         assert mirror == batched
     with pytest.raises(scb200.SCError):
-        scb200.game_selfplay(None, rollout_num=0, evaluator="hash")
+        scb200.game_selfplay(None, rollout_num=-1, evaluator="hash")
+
+
+def test_rollout_factor_follows_the_reference_cli():
+    """`--rollout-factor v` (src/main.rs:175-180): the rollouts of a move are min(300, (legal moves at the root * v) as
+    i32); both given is an error (the reference panics); neither = 300.  Batched driver and one-leaf mirror agree."""
+    import scb200
+
+    for v in (1.5, 20.0):
+        sp = scb200.SelfPlay(None, n_trees=1, rollout_num=0, rollout_factor=v, num_steps=12, cpuct=2.0, with_noise=False,
+                             temperature_switch=0, temperature=0.0, evaluator="hash", keep_traces=True, seed=3)
+        st = sp.run(max_games=1)
+        tr = sp.trace(0)
+        sp.close()
+        assert st["moves"] == 12
+        for mv, q, ch in tr["steps"]:
+            want = min(300, int(np.float32(len(ch)) * np.float32(v)))
+            assert sum(c[1] for c in ch) == want - 1          # the first rollout expands the (reset) root
+        cfgd = dict(rollout_num=0, num_steps=12, cpuct=2.0, temperature_switch=0, seed=3, evaluator="hash")
+        L = scb200.binding.load_library()
+        import ctypes as C
+        cfg = scb200.binding.SelfPlayConfig(1, 0, 12, 2.0, 0.15, 0, 0, 0.0, 3, 1, 1, 1, 1, 1, v)
+        buf = C.create_string_buffer(1 << 22)
+        assert L.sc_game_selfplay(None, C.byref(cfg), buf, 1 << 22) > 0
+        import json
+        assert json.loads(buf.value.decode()) == tr
+    with pytest.raises(scb200.SCError):
+        scb200.SelfPlay(None, n_trees=1, rollout_num=10, rollout_factor=2.0, evaluator="hash")
+    sp = scb200.SelfPlay(None, n_trees=1, rollout_num=0, num_steps=1, with_noise=False, temperature_switch=0,
+                         evaluator="hash", keep_traces=True)
+    sp.run(max_games=1)
+    assert sum(c[1] for c in sp.trace(0)["steps"][0][2]) == 299
+    with pytest.raises(scb200.SCError):
+        sp.run(max_games=1)                                   # one run per driver object
+    sp.close()
 
 
 def test_native_rules_perft_matches_published_tables():

@@ -213,14 +213,14 @@ def reference_arm(args):
 
     torch.set_num_threads(os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1; use every host core
     sd = net.init_state_dict(N_BLOCKS, 0)
-    games = oracle_sample(256, seed=1000)
-    batch = 64
-    steps, warm = args.steps, args.warmup
     import numpy as np
     import chess_oracle as co
 
-    def step():
-        sub = games[:batch]
+    chunk = 64                                    # leaves per forward (batched far beyond the reference's batch 1)
+    games = oracle_sample(min(args.leaves, 512), seed=1000)
+    steps, warm = args.steps, args.warmup
+
+    def forward_chunk(sub):
         planes = np.stack([g.encode()[0] for g in sub])
         meta = np.stack([g.encode()[1] for g in sub])
         lp, v = net.forward(sd, net.planes_i8_hwc_to_nchw(planes), torch.from_numpy(meta).float())
@@ -228,21 +228,42 @@ def reference_arm(args):
         for i, g in enumerate(sub):
             co.post_process(lp[i], g.move_indices())
 
-    for _ in range(warm):
-        step()
+    for _ in range(max(warm, 1)):                 # warm-up: one chunk each
+        forward_chunk(games[:chunk])
+    t0 = time.perf_counter()
+    forward_chunk(games[:chunk])
+    rate = chunk / (time.perf_counter() - t0)
+    # a step = the arm's leaves_per_step when K steps of it fit ~150 s of CPU work, else the largest bounded sample that does
+    budget = 150.0
+    per_step = args.leaves
+    if steps * per_step / rate > budget:
+        per_step = max(chunk, int(budget * rate / steps) // chunk * chunk)
+
+    def step():
+        for lo in range(0, per_step, chunk):
+            forward_chunk([games[(lo + i) % len(games)] for i in range(min(chunk, per_step - lo))])
+
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     el = time.perf_counter() - t0
-    v = steps * batch / el
+    v = steps * per_step / el
+    # the reference's real operating point: one position per forward (src/backends/torch.rs:119 unsqueeze(0))
+    n1, t1 = 0, time.perf_counter()
+    while time.perf_counter() - t1 < 3.0:
+        forward_chunk([games[n1 % len(games)]])
+        n1 += 1
+    b1 = n1 / (time.perf_counter() - t1)
     line = {
         "impl": "reference", "metric": "leaf_evals_per_s", "value": v, "unit": "leaf evals/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": el / steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.leaves),
         "cpu_baseline": {"value": v, "unit": "leaf evals/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{batch} leaves per step (bounded sample of the {args.leaves}-leaf step), "
-                                   f"fp32 libtorch CPU, batched forward"},
+                         "leaves_per_step_run": per_step, "batch1_value": b1,
+                         "sample": f"{per_step} leaves per step (of the {args.leaves}-leaf step of config), evaluated as "
+                                   f"forwards of {chunk} leaves, fp32 libtorch CPU on all host threads; batch1_value = "
+                                   f"one leaf per forward, the reference's own operating point"},
         "e2e": {"value": v, "unit": "leaf evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -252,7 +273,7 @@ def workload_config(leaves):
     return {"workload": f"batched leaf eval, {leaves} leaves/step = one leaf per concurrent search tree "
                         f"(BASELINE configs[2]: 2048 concurrent trees, 19-block LayerNorm+SE net, "
                         f"seeded random-play positions with 8-ply history)",
-            "leaves_per_step": leaves, "n_res_blocks": N_BLOCKS, "l2": "flushed between timed steps (256 MiB memset)",
+            "leaves_per_step": leaves, "n_res_blocks": N_BLOCKS, "l2": "flushed between timed steps (256 MiB memset); the separate sustained leg runs back to back",
             "parallelism": "leaves sharded by game, one process per GPU, no collective on the data path"}
 
 
@@ -274,6 +295,8 @@ def main():
                     help="also time the leader-board mode (BASELINE configs[4]: two random-init nets, rollout 100, "
                          "temperature-switch 8, both colour assignments) for this many seconds per rank (0 = skip)")
     ap.add_argument("--threads", type=int, default=0, help="host worker threads for self-play (0 = cores / ranks)")
+    ap.add_argument("--sustain", type=float, default=5.0,
+                    help="seconds of back-to-back steps for the sustained roofline leg and the clock samples (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -361,6 +384,26 @@ def main():
         t_wall = time.perf_counter() - t_wall0
         launches = eng.launch_count() - launches0
         eng_timed_flops = eng.timed_flops_per_leaf()
+        # ---- sustained leg: the same step back to back for >= args.sustain seconds, no flush, no idle gap beyond the
+        #      engine's own event read-back: what the kernel does under continuous load (power cap); its roofline
+        #      fraction is taken against the SUSTAINED peak, the event-bracketed steps above against the BURST peak.
+        #      The step's activations (~200 MB of bf16 maps at 2048 leaves) exceed nothing the flush would add: inputs
+        #      and weights are L2-resident in steady state, as they are in self-play.
+        sus = None
+        if args.sustain > 0:
+            sus_conv_ms, sus_steps = 0.0, 0
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev0.record(stream)
+            t_s0 = time.perf_counter()
+            while time.perf_counter() - t_s0 < args.sustain:
+                dev_step()
+                a, n = eng.kernel_timing()
+                sus_conv_ms += a * n
+                sus_steps += 1
+            ev1.record(stream)
+            ev1.synchronize()
+            sus = {"seconds": ev0.elapsed_time(ev1) * 1e-3, "steps": sus_steps, "conv_ms_total": sus_conv_ms}
         clocks = sampler.stop()
         eng.set_timing(0)
     total_ms = float(sum(step_ms))
@@ -459,24 +502,42 @@ def main():
         conv_avg_ms = conv_tot_ms / conv_n if conv_tot_ms and conv_n else None
         timed_flops = eng_timed_flops
         roof = None
-        if conv_avg_ms and conv_avg_ms > 0 and args.mode == "bf16":
+        if conv_avg_ms and conv_avg_ms > 0:
             ach = B * timed_flops / (conv_tot_ms * 1e-3) / 1e12
-            # dram__bytes_read.sum + dram__bytes_write.sum per launch from ncu --set full captures at this workload:
-            # per-layer launches (SCB200_TOWER=0): 95.4 MB (conv1) / 161.0 MB (conv2 + SE + residual), one of each
-            # per residual block (profiles/r01d_conv_full_raw.csv); whole-tower launch: 237 MB read + 1407 MB
-            # written (profiles/r01m_step_full_raw.csv)
-            traffic = ((95.4e6 + 161.0e6) / 2 if conv_n > 1 else 1.644e9) if B == 2048 else None
+            tower = conv_n == 1
             roof = {"bound": "tensor",
                     "kernel": ("tc_gemm_kernel<256, pair, TOWER>: stem + 19 x (conv3x3+LN+ReLU, conv3x3+LN+SE+residual+ReLU) + 2 head 1x1 convs in one launch"
-                               if conv_n == 1 else
+                               if tower else
                                "tc_gemm_kernel<256, EPI_LN | EPI_LN_SE, pair> (3x3 256->256 conv, bias+LN[+SE+residual] fused)"),
-                    "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
-                    "peak_kind": f"bf16_tflops_sustained ({peaks['src']}): the kernel is timed inside a long step",
-                    "peak_burst": peaks["tflops_burst"], "frac_of_burst": ach / peaks["tflops_burst"], "traffic": traffic,
-                    "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01m_summary.md)",
+                    "achieved": ach, "peak": peaks["tflops_burst"], "unit": "TFLOP/s", "frac": ach / peaks["tflops_burst"],
+                    "peak_kind": f"bf16_tflops burst ({peaks['src']}): each timed step is bracketed by CUDA events and preceded by "
+                                 f"an L2 flush + sync, i.e. the kernel is timed alone",
+                    # not measured by this run: dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed
+                    # ncu --set full capture of this workload
+                    "traffic": (1.644e9 if tower else (95.4e6 + 161.0e6) / 2) if B == 2048 and args.mode == "bf16" else None,
+                    "traffic_source": "constant: ncu --set full capture profiles/r01m_step_full_raw.csv (237 MB read + 1407 MB "
+                                      "written per whole-tower launch); not re-measured by this run",
                     "launches_timed_per_step": conv_n, "avg_launch_ms": conv_avg_ms,
                     "flops_per_launch": B * timed_flops / conv_n,
                     "whole_step_tflops": value / world * FLOP_PER_LEAF / 1e12}
+            if sus and sus["conv_ms_total"] > 0:
+                ach_s = sus["steps"] * B * timed_flops / (sus["conv_ms_total"] * 1e-3) / 1e12
+                roof["sustained"] = {
+                    "achieved": ach_s, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach_s / peaks["tflops"],
+                    "peak_kind": f"bf16_tflops_sustained ({peaks['src']}): {sus['steps']} steps back to back over "
+                                 f"{sus['seconds']:.1f} s, no flush, kernel time from the same event pairs",
+                    "leaf_evals_per_s": sus["steps"] * B / sus["seconds"], "seconds": sus["seconds"], "steps": sus["steps"],
+                    "avg_launch_ms": sus["conv_ms_total"] / sus["steps"] / conv_n}
+            if args.mode == "fp32":
+                # FP32 parity mode: the same kernel runs the bf16x3 operand split (6 tensor-core products per fp32
+                # product), so its ceiling is the bf16 peak / 6; achieved counts fp32 FLOPs
+                roof["peak"] = peaks["tflops_burst"] / 6
+                roof["frac"] = ach / roof["peak"]
+                roof["peak_kind"] = (f"bf16_tflops burst ({peaks['src']}) / 6: fp32 products as 6 bf16 tensor-core products "
+                                     f"(3-way operand split, terms below 2^-16 dropped)")
+                if "sustained" in roof:
+                    roof["sustained"]["peak"] = peaks["tflops"] / 6
+                    roof["sustained"]["frac"] = roof["sustained"]["achieved"] / roof["sustained"]["peak"]
         cpu = None
         if world == 1 and args.cpu_budget > 0:
             b, b1, n, thr = cpu_reference_throughput(sd, oracle_sample(512, seed=1000), args.cpu_budget, 64)
@@ -503,6 +564,10 @@ def main():
                              "" if args.leaves_per_tree <= 1 else " (virtual loss; not the reference's visit counts)",
                              sp_stats["threads"]),
                 "plies": sp_moves, "seconds": sp_secs, "device_wait_frac_rank0": sp_stats["wait_seconds"] / sp_stats["seconds"],
+                "roofline": {"bound": "tensor", "achieved": sp_evals / sp_secs / world * FLOP_PER_LEAF / 1e12,
+                             "peak": peaks["tflops"], "unit": "TFLOP/s",
+                             "frac": sp_evals / sp_secs / world * FLOP_PER_LEAF / 1e12 / peaks["tflops"],
+                             "peak_kind": "bf16_tflops_sustained: whole path (search on the host + every kernel), per GPU"},
                 "games_finished_rank0": sp_stats["games_finished"],
             }
         if arena:

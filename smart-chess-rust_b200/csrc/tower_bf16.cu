@@ -45,200 +45,17 @@
 #include "common.cuh"
 #include "move_index.cuh"
 
+#include "tc_ptx.cuh"
+
 namespace scb {
 
-constexpr int TC_BM = 128;
 constexpr int TC_BN = 256;
-constexpr int TC_BK = 64;
 constexpr int TC_STAGES = 4;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KB
 #ifndef SCB_AREUSE
 #define SCB_AREUSE 1
 #endif
 constexpr int TC_THREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
-
-// ---- PTX wrappers ------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    while (!mbar_try_wait(bar, parity)) {
-    }
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1,
-                                            int c2, int c3)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
-            "r"(dst),
-        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-            dst),
-        "l"(map), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-}
-// ---- cta_group::2 (CTA pair) variants -------------------------------------------------------------
-__device__ __forceinline__ uint32_t cluster_ctarank()
-{
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all()
-{
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// shared::cluster addresses carry the CTA rank in bit 24; clearing it addresses the even (leader) CTA
-constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
-__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1,
-                                             int c2, int c3)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
-            "r"(dst),
-        "l"(map), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-            dst),
-        "l"(map), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tc2_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                             uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// arrives on the barrier at the same shared-memory offset in BOTH CTAs of the pair
-__device__ __forceinline__ void tc2_commit_mc(uint32_t bar)
-{
-    asm volatile(
-        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-        "h"((uint16_t)3)
-        : "memory");
-}
-// arrive on a barrier of the leader CTA (rank 0) of the pair
-__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .b32 ra;\n\t"
-        "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
-        "}" ::"r"(bar)
-        : "memory");
-}
-
-// true in exactly one lane of a converged warp
-__device__ __forceinline__ bool elect_one()
-{
-    uint32_t p;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred q;\n\t"
-        "elect.sync _|q, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, q;\n\t"
-        "}"
-        : "=r"(p));
-    return p != 0;
-}
-
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                            uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tc_commit(uint32_t bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major, 128-byte-swizzled shared-memory operand descriptor (sm_100 UMMA):
-//   bits 0-13 start address >> 4, 16-29 leading byte offset >> 4 (unused for swizzled
-//   K-major, 1), 32-45 stride byte offset >> 4 (8 rows x 128 B = 1024 B between 8-row core
-//   groups), 46-47 descriptor version 1, 61-63 layout type 2 = SWIZZLE_128B.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr)
-{
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-
-// instruction descriptor: fp32 accumulate (bit 4), A/B bf16 (bits 7, 10), both K-major,
-// N >> 3 at bits 17-22, M >> 4 at bits 24-28.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N)
-{
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
 
 // ---- the kernel ---------------------------------------------------------------------------
 // Epilogue variants of the one warp-specialised GEMM kernel:
@@ -262,6 +79,7 @@ struct alignas(64) TowerLayer {
     const uint4 *se_w1p, *se_w2p;
     const float *se_b1, *se_b2;
     int taps, kchunks, relu, se;
+    int ln;                              // 0: no LayerNorm (BatchNorm folded at export): y = acc + bias
 };
 
 struct TcArgs {
@@ -273,6 +91,7 @@ struct TcArgs {
     int n_tiles;                         // M tiles of 128 rows
     int taps, kchunks;                   // k-blocks per work item = taps * kchunks
     int relu;
+    int ln;                              // 0: the layer has no LayerNorm (y = acc + bias)
     int n_splits;                        // EPI_RAW: work items = n_tiles * n_splits
     int m_rows;                          // EPI_RAW: valid rows
     long long *prof;                     // optional [grid][16] phase cycle counters (SCB200_PHASE_PROFILE=1)
@@ -282,79 +101,9 @@ struct TcArgs {
     TcGather gather;                     // EPI_LN73_GATHER: legal moves in, priors out
 };
 
-__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 // EPI_LN73_GATHER: one barrier per set of four epilogue warps (set 0 = warps 2..5, set 1 = warps 6..9)
 __device__ __forceinline__ void gather_bar_sync(int set) { asm volatile("bar.sync %0, 128;" ::"r"(2 + set) : "memory"); }
-
-// Sum over the 32 lanes of a warp of 32 per-lane values, result for index `lane` lands in
-// lane `lane` (recursive halving: 16+8+4+2+1 = 31 shuffles instead of 32 x 5).
-__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane)
-{
-    const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2, b1 = lane & 1;
-    float w16[16], w8[8], w4[4], w2[2];
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-        float send = b16 ? v[i] : v[i + 16];
-        float keep = b16 ? v[i + 16] : v[i];
-        w16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        float send = b8 ? w16[i] : w16[i + 8];
-        float keep = b8 ? w16[i + 8] : w16[i];
-        w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        float send = b4 ? w8[i] : w8[i + 4];
-        float keep = b4 ? w8[i + 4] : w8[i];
-        w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; i++) {
-        float send = b2 ? w4[i] : w4[i + 2];
-        float keep = b2 ? w4[i + 2] : w4[i];
-        w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-    float send = b1 ? w2[0] : w2[1];
-    float keep = b1 ? w2[1] : w2[0];
-    return keep + __shfl_xor_sync(0xffffffffu, send, 1);
-}
-
-__device__ __forceinline__ void bf16x8_to_float(const uint4 &u, float (&f)[8])
-{
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        f[2 * i] = __uint_as_float(w[i] << 16);
-        f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
-    }
-}
 
 // Per-warp staging tile of 32 rows x 64 bytes used to turn the epilogue's thread-per-row data
 // into coalesced global accesses (a row-per-lane access has a 512-byte lane stride and costs 32
@@ -396,41 +145,6 @@ __device__ __forceinline__ void staged_store_64B_hbw(uint8_t *stg, int lane, con
         *reinterpret_cast<uint4 *>(tile_base + (size_t)grow * row_stride + (lane & 3) * 16) = t;
     }
     __syncwarp();
-}
-
-// Column sums over the 16 lanes of each board for rows ordered (rank, board, file): lane bit 3 is the board, so
-// the recursive halving skips that bit.  Lane l ends with the sums of its board for indices i0, i0 + 1,
-// i0 = 16 b16 + 8 b4 + 4 b2 + 2 b1 (30 shuffles).
-__device__ __forceinline__ float2 warp_transpose_reduce_2boards(float (&v)[32], int lane, int &i0)
-{
-    const bool b16 = lane & 16, b4 = lane & 4, b2 = lane & 2, b1 = lane & 1;
-    float w16[16], w8[8], w4[4], w2[2];
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-        float send = b16 ? v[i] : v[i + 16];
-        float keep = b16 ? v[i + 16] : v[i];
-        w16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        float send = b4 ? w16[i] : w16[i + 8];
-        float keep = b4 ? w16[i + 8] : w16[i];
-        w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        float send = b2 ? w8[i] : w8[i + 4];
-        float keep = b2 ? w8[i + 4] : w8[i];
-        w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; i++) {
-        float send = b1 ? w4[i] : w4[i + 2];
-        float keep = b1 ? w4[i + 2] : w4[i];
-        w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-    }
-    i0 = (b16 ? 16 : 0) + (b4 ? 8 : 0) + (b2 ? 4 : 0) + (b1 ? 2 : 0);
-    return make_float2(w2[0], w2[1]);
 }
 
 // 4 registers loaded with the coalesced mapping (row (lane>>2)+8k, chunk lane&3) -> lane's own row
@@ -538,16 +252,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint4 *w1p, *w2p;
         const float *b1, *b2;
         int taps, kchunks, relu;
-        bool se;
+        bool se, ln;
+        bool se_fc;  // se: squeeze-excitation gate (false with se: residual + ReLU only, `use_se=False`)
     };
     auto layer_view = [&](int l) -> LayerView {
         if constexpr (TOWER) {
             const TowerLayer &T = args.layers[l];
             return LayerView{&T.map_a, &T.map_w, T.out, T.resid, T.bias, T.gamma, T.beta, T.se_w1p, T.se_w2p, T.se_b1, T.se_b2,
-                             T.taps, T.kchunks, T.relu, T.se != 0};
+                             T.taps, T.kchunks, T.relu, T.se != 0, T.ln != 0, T.se == 1};
         } else {
             return LayerView{&map_a, &map_w, args.out, args.resid, args.bias, args.gamma, args.beta, args.se_w1p, args.se_w2p,
-                             args.se_b1, args.se_b2, args.taps, args.kchunks, args.relu, EPI == EPI_LN_SE};
+                             args.se_b1, args.se_b2, args.taps, args.kchunks, args.relu, EPI == EPI_LN_SE, args.ln != 0,
+                             EPI == EPI_LN_SE && args.se_w1p != nullptr};
         }
     };
     const int n_layers = TOWER ? args.n_layers : 1;
@@ -556,8 +272,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         constexpr int NV = (EPI == EPI_LN73 || EPI == EPI_LN73_GATHER) ? C_POLICY : BN;
         for (int i = threadIdx.x; i < 256; i += TC_THREADS) {
             s_bias[i] = i < NV ? args.bias[i] : 0.f;
-            s_gamma[i] = i < NV ? args.gamma[i] : 0.f;
-            s_beta[i] = i < NV ? args.beta[i] : 0.f;
+            s_gamma[i] = i < NV ? (args.ln ? args.gamma[i] : 1.f) : 0.f;
+            s_beta[i] = i < NV && args.ln ? args.beta[i] : 0.f;
         }
     }
     if (threadIdx.x == 0) {
@@ -802,13 +518,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int gi = 0; gi < n_groups; gi++)
         for (int layer = 0; layer < n_layers; layer++) {
         const LayerView P = layer_view(layer);
-        const bool is_se = P.se;
+        const bool is_se = P.se, se_fc = P.se_fc;
         if constexpr (TOWER) {
             // this layer's bias / LayerNorm parameters replace the previous layer's in shared memory
             epi_bar_sync();
             s_bias[te] = P.bias[te];
-            s_gamma[te] = P.gamma[te];
-            s_beta[te] = P.beta[te];
+            s_gamma[te] = P.ln ? P.gamma[te] : 1.f;
+            s_beta[te] = P.ln ? P.beta[te] : 0.f;
             epi_bar_sync();
         }
         // end of a tile in the tower kernel: the tile's output (generic-proxy stores) is handed to the TMA
@@ -988,33 +704,35 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const uint32_t tcol = taddr + (uint32_t)c0;
                 uint32_t r[32];
                 float mean, rstd;
-                {
-                    // one pass: sum and sum of squares of (acc + bias); fp32 is ample for LN inputs
+                if (P.ln) {
+                    // one TMEM pass: per 32-channel chunk the sums of (acc + bias) and its square, combined in the
+                    // fixed tree of tc_ptx.cuh (the latency kernel computes the same chunks in other CTAs)
                     uint32_t r2[32];
-                    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+                    float2 p[4];
 #pragma unroll 1
                     for (int ch = 0; ch < 4; ch += 2) {
                         tmem_ld32_nowait(tcol + ch * 32, r);
                         tmem_ld32_nowait(tcol + ch * 32 + 32, r2);
                         tmem_wait_ld();
+                        float a0[32], a1[32];
 #pragma unroll
                         for (int j = 0; j < 32; j++) {
-                            const float a = __uint_as_float(r[j]) + s_bias[c0 + ch * 32 + j];
-                            const float b = __uint_as_float(r2[j]) + s_bias[c0 + ch * 32 + 32 + j];
-                            s0 += a;
-                            q0 = fmaf(a, a, q0);
-                            s1 += b;
-                            q1 = fmaf(b, b, q1);
+                            a0[j] = __fadd_rn(__uint_as_float(r[j]), s_bias[c0 + ch * 32 + j]);
+                            a1[j] = __fadd_rn(__uint_as_float(r2[j]), s_bias[c0 + ch * 32 + 32 + j]);
                         }
+                        ln_chunk_stats(a0, p[ch].x, p[ch].y);
+                        ln_chunk_stats(a1, p[ch + 1].x, p[ch + 1].y);
                     }
-                    s0 += s1;
-                    q0 += q1;
-                    *reinterpret_cast<float2 *>(s_stat + (chalf * 128 + row) * 2) = make_float2(s0, q0);
+                    const float2 mine = ln_half(p[0], p[1], p[2], p[3]);
+                    *reinterpret_cast<float2 *>(s_stat + (chalf * 128 + row) * 2) = mine;
                     epi_bar_sync();
                     const float2 o = *reinterpret_cast<const float2 *>(s_stat + ((chalf ^ 1) * 128 + row) * 2);
-                    mean = (s0 + o.x) * (1.f / BN);
-                    const float var = fmaxf((q0 + o.y) * (1.f / BN) - mean * mean, 0.f);
-                    rstd = rsqrtf(var + LN_EPS);
+                    ln_finish(chalf ? o : mine, chalf ? mine : o, LN_EPS, mean, rstd);
+                } else {
+                    // no normalisation (BatchNorm folded into weights and bias at export): y = acc + bias exactly
+                    mean = 0.f;
+                    rstd = 1.f;
+                    epi_bar_sync();
                 }
                 long long tp2 = prof ? clock64() : 0;
                 pe_stats += tp2 - tp1;
@@ -1027,7 +745,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 // FC1 weights do not depend on anything computed here: request them before the pooling pass
                 // so their L2 latency is hidden (thread = (hidden unit j, channel half hc))
                 uint4 w1v[16];
-                if (is_se) {
+                if (se_fc) {
                     const int j = te & 127, hc = te >> 7;
 #pragma unroll
                     for (int u = 0; u < 8; u++) w1v[u] = __ldg(P.w1p + (hc * 16 + u) * 128 + j);
@@ -1045,7 +763,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                         for (int j = 0; j < 32; j++) {
                             const int c = c0 + ch * 32 + j;
-                            y[j] = (__uint_as_float(cur[j]) + s_bias[c] - mean) * rstd * s_gamma[c] + s_beta[c];
+                            y[j] = ln_apply(__fadd_rn(__uint_as_float(cur[j]), s_bias[c]), mean, rstd, s_gamma[c], s_beta[c]);
                         }
                         if constexpr (YSMEM) {
                             // keep LN(acc) as bf16 in shared memory: the final pass then needs neither TMEM nor
@@ -1063,7 +781,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                     make_uint4(pw[0], pw[1], pw[2], pw[3]);
                             }
                         }
-                        if constexpr (AREUSE) {
+                        if (!se_fc) {
+                            // residual-only block (use_se=False): no pooling
+                        } else if constexpr (AREUSE) {
                             // partial sums per (quadrant, board) live in the (idle) store-staging area
                             int i0;
                             const float2 ps = warp_transpose_reduce_2boards(y, lane, i0);
@@ -1077,7 +797,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         tc_fence_before();
                         mbar_arrive_leader(tempty_bar(as));  // the accumulator is no longer needed
                     }
-                    {
+                    if (se_fc) {
                         // second half of the FC1 weights (the register file holds 10 warps at <= 168 registers,
                         // so only half of them could be requested before the pooling pass)
                         const int j = te & 127, hc = te >> 7;
@@ -1086,6 +806,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                     epi_bar_sync();
                     if (prof) { const long long t = clock64(); pe_pool += t - tp2; tp2 = t; }
+                    if (se_fc) {
 #pragma unroll
                     for (int i = 0; i < 2; i++) {
                         const int idx = te + 256 * i;  // [board][channel]
@@ -1157,6 +878,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         s_gate[256 + te] = 1.f / (1.f + __expf(-g1));
                     }
                     epi_bar_sync();
+                    } else {
+                        // residual-only block: gate = 1, so the final pass computes relu(y + x) exactly
+                    if constexpr (!YSMEM) {
+                        const uint4 *xw = reinterpret_cast<const uint4 *>(P.resid + (wrow0 + (lane >> 2)) * BN + c0) + (lane & 3);
+#pragma unroll
+                        for (int ch = 0; ch < 4; ch++)
+#pragma unroll
+                            for (int k = 0; k < 4; k++) xa[ch * 4 + k] = xw[(size_t)k * 8 * (BN / 8) + ch * 4];
+                    }
+                        s_gate[te] = 1.f;
+                        s_gate[256 + te] = 1.f;
+                        epi_bar_sync();
+                    }
                     if (prof) { const long long t = clock64(); pe_fc += t - tp2; tp2 = t; }
                 }
 
@@ -1221,8 +955,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                     for (int j = 0; j < 16; j++) {
                         const int c = c0 + ch * 32 + 2 * j;
-                        float y0 = (__uint_as_float(cur[2 * j]) + s_bias[c] - mean) * rstd * s_gamma[c] + s_beta[c];
-                        float y1 = (__uint_as_float(cur[2 * j + 1]) + s_bias[c + 1] - mean) * rstd * s_gamma[c + 1] + s_beta[c + 1];
+                        float y0 = ln_apply(__fadd_rn(__uint_as_float(cur[2 * j]), s_bias[c]), mean, rstd, s_gamma[c], s_beta[c]);
+                        float y1 = ln_apply(__fadd_rn(__uint_as_float(cur[2 * j + 1]), s_bias[c + 1]), mean, rstd, s_gamma[c + 1],
+                                            s_beta[c + 1]);
                         if (!YSMEM && is_se) {
                             const uint4 xq = xr[j >> 2];
                             const uint32_t xw = (j & 3) == 0 ? xq.x : ((j & 3) == 1 ? xq.y : ((j & 3) == 2 ? xq.z : xq.w));

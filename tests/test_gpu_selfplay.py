@@ -380,20 +380,24 @@ def test_two_engines_two_drivers_one_process(co, small_net):
 
 
 def test_non_finite_leaf_drops_only_its_own_game(co, tmp_path):
-    """Per-game failure isolation: a network that returns NaN for SOME positions (value-FC meta column of the
-    side-to-move's king-side castling right set to +inf: inf * 0 = NaN once that right is gone, finite -- tanh(+-inf) --
-    while it is there) must cost exactly the games that run into such a leaf; the others finish."""
+    """Per-game failure isolation: a network that returns NaN for SOME positions must cost exactly the games that
+    run into such a leaf; the others finish.  The NaN is built from finite weights: hidden unit 0 of the value FC
+    gets the weight 4.5e37 on the half-move clock and the weight 0 in the last layer, so its pre-activation overflows
+    to +inf once the clock reaches 8 (8 quiet plies in a row) and 0 * inf = NaN; below that 0 * finite = 0."""
     import net
     import scb200
 
     sd = net.perturb_norm_params(net.init_state_dict(2, 7), 1234)
     w = sd["value_head.ffn.0.weight"].clone()
-    w[0, 64 * 256 + 2] = float("inf")      # ONE hidden unit: inf * 1 -> value +-1 (finite); inf * 0 -> NaN
+    w[0, 64 * 256 + 6] = 4.5e37
     sd["value_head.ffn.0.weight"] = w
+    w2 = sd["value_head.ffn.2.weight"].clone()
+    w2[0, 0] = 0.0
+    sd["value_head.ffn.2.weight"] = w2
     blob = str(tmp_path / "nan.scw")
     scb200.write_blob(sd, blob)
     eng = scb200.Engine(blob, 0, scb200.SC_MODE_BF16, 64)
-    sp = scb200.SelfPlay(eng, n_trees=64, rollout_num=16, num_steps=14, cpuct=2.5, with_noise=True, temperature_switch=14,
+    sp = scb200.SelfPlay(eng, n_trees=64, rollout_num=16, num_steps=24, cpuct=2.5, with_noise=True, temperature_switch=24,
                          temperature=1.0, keep_traces=True, pipeline_groups=2, n_threads=2, seed=5)
     st = sp.run(max_games=64)
     print("dropped", st["games_dropped"], "finished", st["games_finished"])

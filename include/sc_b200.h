@@ -237,6 +237,14 @@ int sc_arena_create(sc_engine *white, sc_engine *black, const sc_selfplay_config
 int sc_random_positions(int n, uint64_t seed, int max_ply, sc_position *pos_out, sc_move *moves_out,
                         int32_t *move_off /* n+1 */, int max_moves_total);
 
+/* Test hook (bf16 engines): encodes n leaves and runs only the first n_layers (0 = all 41: stem, 19 x (conv1, conv2),
+ * the two 256-wide head 1x1 convolutions) of the convolution tower with the throughput kernel (which = 0) or the
+ * small-batch latency kernel (which = 1); copies the three activation buffers (bf16 bit patterns, [n][64][256]:
+ * x = block input / output, t = conv1 output / policy head input, y = value head input) to the host.  Lets the tests
+ * compare the two kernels layer by layer. */
+int sc_debug_tower(sc_engine *e, int n, const sc_position *pos, int n_layers, int which, uint16_t *x_out,
+                   uint16_t *t_out, uint16_t *y_out);
+
 /* Test hook: one Dirichlet(alpha) sample of size n from the driver's root-noise sampler (src/mcts.rs:123-130
  * uses rand_distr::Dirichlet(0.3)); lets the tests check its moments. */
 int sc_test_dirichlet(uint64_t seed, float alpha, int n, float *out);

@@ -107,7 +107,30 @@ struct TcTowerLayerDesc {
 };
 int tc_tower_create(TcTower **out, const TcTowerLayerDesc *descs, int n, int boards_alloc);
 // group = tiles per CTA carried through all layers together (0 = all of the CTA's tiles)
-int tc_tower_launch(TcTower *t, int n_boards, int num_sms, int group, cudaStream_t st);
+// max_layers > 0: only the first max_layers layers (debug hook)
+int tc_tower_launch(TcTower *t, int n_boards, int num_sms, int group, cudaStream_t st, int max_layers = 0);
 void tc_tower_destroy(TcTower *t);
+
+// ---- tower_lat.cu: latency path for small batches (one 2-board tile per cluster of 8 / 4 CTAs) ------------------
+struct LatTower;
+struct LatLayerDesc {
+    const __nv_bfloat16 *w;      // [taps][256][cin_pad] (the throughput kernel's B operand)
+    int taps, cin_pad;
+    const __nv_bfloat16 *in;     // bf16 NHWC [boards_alloc][64][cin_pad]
+    void *out;                   // bf16 NHWC [boards_alloc][64][256]
+    const __nv_bfloat16 *resid;  // residual layers: block input (may alias out)
+    const float *bias, *gamma, *beta;
+    int relu, ln;
+    int se;                      // 0: LN (+ReLU); 1: LN + squeeze-excitation + residual + ReLU; 2: LN + residual + ReLU
+    // SE weights sliced per cluster rank: fc1 [CL][32][128 / CL] x 8 bf16, fc2 [CL][16][256 / CL] x 8 bf16
+    const void *se_w1s8, *se_w2s8, *se_w1s4, *se_w2s4;
+    const float *se_b1, *se_b2;
+};
+int lat_tower_create(LatTower **out, const LatLayerDesc *descs, int n, int boards_alloc);
+// largest batch the latency kernel takes (one wave of clusters); 0 if it cannot run on this device
+int lat_tower_max_boards(const LatTower *t);
+// SC_E_STATE (no message) when the batch does not fit: run the throughput kernel instead
+int lat_tower_launch(LatTower *t, int n_boards, cudaStream_t st, int max_layers = 0);
+void lat_tower_destroy(LatTower *t);
 
 }  // namespace scb

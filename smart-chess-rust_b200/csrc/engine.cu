@@ -102,6 +102,7 @@ struct ConvW {
 struct SeW {
     float *w1t = nullptr, *b1 = nullptr, *w2t = nullptr, *b2 = nullptr;  // fp32 mode
     uint16_t *w1p = nullptr, *w2p = nullptr;                            // bf16 mode, packed for the fused epilogue
+    uint16_t *w1s[2] = {nullptr, nullptr}, *w2s[2] = {nullptr, nullptr};  // latency kernel: sliced per cluster rank (CL = 8, 4)
 };
 
 }  // namespace scb
@@ -120,6 +121,10 @@ struct sc_engine {
     float *vfc_w_f32 = nullptr;           // fp32 mode: [16384][128]
     TcConv *vfc_tc = nullptr;             // bf16 mode: value FC as a split-K tcgen05 GEMM
     TcTower *tower = nullptr;             // bf16 mode: stem + all residual blocks in one launch
+    LatTower *lat = nullptr;              // bf16 mode, small batches: the same layers, one 2-board tile per cluster
+    int lat_max_boards = 0;
+    // SCB200_LATENCY=0 keeps small batches on the throughput kernel (A/B runs and the bit-identity test)
+    bool lat_enabled = !(getenv("SCB200_LATENCY") && getenv("SCB200_LATENCY")[0] == '0');
     double timed_flops_per_leaf = 0.0;    // FLOPs per leaf covered by the level-2 timed launches
     float *v_wmeta = nullptr, *v_b1 = nullptr, *v_w2 = nullptr, *v_b2 = nullptr;
     // io
@@ -292,6 +297,26 @@ static int load_weights(sc_engine *e, const Blob &b)
                         w2p[((size_t)q * C_TOWER + c) * 8 + k] = f2bf(f2->data[(size_t)c * C_SE + 8 * q + k]);
             SCB_CHECK(upload(e, &e->se[i].w1p, w1p));
             SCB_CHECK(upload(e, &e->se[i].w2p, w2p));
+            // latency kernel: the same numbers sliced per cluster rank r -- fc1 rows (hidden units) [r * HJ, +HJ) as
+            // [r][q][j][8], fc2 rows (channels) [r * NC, +NC) as [r][q][c][8]
+            for (int v = 0; v < 2; v++) {
+                const int CL = v == 0 ? 8 : 4, HJ = C_SE / CL, NC = C_TOWER / CL;
+                std::vector<uint16_t> a((size_t)C_TOWER * C_SE), b((size_t)C_SE * C_TOWER);
+                for (int r = 0; r < CL; r++) {
+                    for (int q = 0; q < C_TOWER / 8; q++)
+                        for (int j = 0; j < HJ; j++)
+                            for (int k = 0; k < 8; k++)
+                                a[(((size_t)r * (C_TOWER / 8) + q) * HJ + j) * 8 + k] =
+                                    f2bf(f1->data[(size_t)(r * HJ + j) * C_TOWER + 8 * q + k]);
+                    for (int q = 0; q < C_SE / 8; q++)
+                        for (int c = 0; c < NC; c++)
+                            for (int k = 0; k < 8; k++)
+                                b[(((size_t)r * (C_SE / 8) + q) * NC + c) * 8 + k] =
+                                    f2bf(f2->data[(size_t)(r * NC + c) * C_SE + 8 * q + k]);
+                }
+                SCB_CHECK(upload(e, &e->se[i].w1s[v], a));
+                SCB_CHECK(upload(e, &e->se[i].w2s[v], b));
+            }
             tc_conv_set_se(e->conv2[i].tc, e->se[i].w1p, e->se[i].b1, e->se[i].w2p, e->se[i].b2);
         }
     }
@@ -433,7 +458,21 @@ static int run_network(sc_engine *e, int n, cudaStream_t st, const TcGather *gat
     } else {
         const int nb = e->alloc_boards;
         int trc = SC_E_STATE;
-        if (e->tower_enabled && e->tower) {
+        if (e->lat_enabled && e->lat && n <= e->lat_max_boards) {
+            // small batch: one 2-board tile per cluster of 8 / 4 CTAs (same bits as the throughput kernel)
+            SCB_CHECK(kev_mark(e, st));
+            trc = lat_tower_launch(e->lat, n, st);
+            if (trc == SC_OK) {
+                SCB_CHECK(kev_mark(e, st));
+                e->launches += 1;
+                e->timed_flops_per_leaf =
+                    2.0 * 64 * 256 * (9.0 * C_IN + e->n_blocks * (2 * 9.0 * 256 + 2.0 * C_SE / 64) + 2 * 256.0);
+            } else if (trc != SC_E_STATE)
+                return trc;
+            else
+                e->kev_used = 0;
+        }
+        if (trc != SC_OK && e->tower_enabled && e->tower) {
             SCB_CHECK(kev_mark(e, st));
             trc = tc_tower_launch(e->tower, n, e->num_sms, e->tower_group, st);
             if (trc == SC_OK) {
@@ -555,6 +594,42 @@ int sc_create(const char *weights_blob_path, int device, int mode, int max_batch
             d.push_back(TcTowerLayerDesc{e->pol1.tc, e->h_x, e->h_t, nullptr, 0});
             d.push_back(TcTowerLayerDesc{e->val1.tc, e->h_x, e->h_y, nullptr, 1});
             if ((rc = tc_tower_create(&e->tower, d.data(), (int)d.size(), e->alloc_boards)) != SC_OK) break;
+            // the same layers for the latency kernel
+            std::vector<LatLayerDesc> ld;
+            auto lat_layer = [&](const ConvW &c, const __nv_bfloat16 *in, void *out, const __nv_bfloat16 *resid, int relu,
+                                 int se, const SeW *sw) {
+                LatLayerDesc L{};
+                L.w = c.w_bf16;
+                L.taps = c.taps;
+                L.cin_pad = c.cin_pad;
+                L.in = in;
+                L.out = out;
+                L.resid = resid;
+                L.bias = c.bias;
+                L.gamma = c.gamma;
+                L.beta = c.beta;
+                L.relu = relu;
+                L.ln = 1;
+                L.se = se;
+                if (sw) {
+                    L.se_w1s8 = sw->w1s[0];
+                    L.se_w2s8 = sw->w2s[0];
+                    L.se_w1s4 = sw->w1s[1];
+                    L.se_w2s4 = sw->w2s[1];
+                    L.se_b1 = sw->b1;
+                    L.se_b2 = sw->b2;
+                }
+                ld.push_back(L);
+            };
+            lat_layer(e->stem, e->h_planes, e->h_x, nullptr, 1, 0, nullptr);
+            for (int i = 0; i < e->n_blocks; i++) {
+                lat_layer(e->conv1[i], e->h_x, e->h_t, nullptr, 1, 0, nullptr);
+                lat_layer(e->conv2[i], e->h_t, e->h_x, e->h_x, 0, 1, &e->se[i]);
+            }
+            lat_layer(e->pol1, e->h_x, e->h_t, nullptr, 0, 0, nullptr);
+            lat_layer(e->val1, e->h_x, e->h_y, nullptr, 1, 0, nullptr);
+            if ((rc = lat_tower_create(&e->lat, ld.data(), (int)ld.size(), e->alloc_boards)) != SC_OK) break;
+            e->lat_max_boards = lat_tower_max_boards(e->lat);
         }
         if (cudaDeviceSynchronize() != cudaSuccess) { rc = SC_E_CUDA; set_error("sync after weight upload failed"); break; }
     } while (0);
@@ -575,6 +650,7 @@ int sc_destroy(sc_engine *e)
     kill(e->stem); kill(e->pol1); kill(e->pol2); kill(e->val1);
     if (e->vfc_tc) tc_conv_destroy(e->vfc_tc);
     if (e->tower) tc_tower_destroy(e->tower);
+    if (e->lat) lat_tower_destroy(e->lat);
     for (auto &c : e->conv1) kill(c);
     for (auto &c : e->conv2) kill(c);
     for (void *p : e->allocs) cudaFree(p);
@@ -952,6 +1028,39 @@ int sc_forward_only(sc_engine *e, int n, const float *planes, const float *meta,
     SCB_CHECK(finish_timing(e, st));
     SCB_CUDA(cudaMemcpyAsync(logp_out, d_logp, (size_t)n * SC_N_POLICY * 4, cudaMemcpyDeviceToHost, st));
     SCB_CUDA(cudaMemcpyAsync(value_out, e->d_value, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    SCB_CUDA(cudaStreamSynchronize(st));
+    return SC_OK;
+}
+
+int sc_debug_tower(sc_engine *e, int n, const sc_position *pos, int n_layers, int which, uint16_t *x_out, uint16_t *t_out,
+                   uint16_t *y_out)
+{
+    if (!e || e->mode != SC_MODE_BF16 || n <= 0 || n > e->max_batch || !pos || !e->tower) {
+        set_error("sc_debug_tower: bad argument (bf16 engines only)");
+        return SC_E_INVAL;
+    }
+    cudaStream_t st = e->stream;
+    SCB_CUDA(cudaSetDevice(e->device));
+    const size_t act = (size_t)e->alloc_boards * 64 * C_TOWER * 2;
+    SCB_CUDA(cudaMemsetAsync(e->h_x, 0, act, st));
+    SCB_CUDA(cudaMemsetAsync(e->h_t, 0, act, st));
+    SCB_CUDA(cudaMemsetAsync(e->h_y, 0, act, st));
+    SCB_CUDA(cudaMemcpyAsync(e->d_pos, pos, sizeof(sc_position) * (size_t)n, cudaMemcpyHostToDevice, st));
+    SCB_CHECK(encode_for_mode(e, e->d_pos, n, st));
+    if (which == 1) {
+        if (!e->lat) {
+            set_error("sc_debug_tower: no latency kernel");
+            return SC_E_STATE;
+        }
+        int rc = lat_tower_launch(e->lat, n, st, n_layers);
+        if (rc == SC_E_STATE) set_error("sc_debug_tower: batch too large for the latency kernel");
+        SCB_CHECK(rc);
+    } else
+        SCB_CHECK(tc_tower_launch(e->tower, n, e->num_sms, e->tower_group, st, n_layers));
+    const size_t bytes = (size_t)n * 64 * C_TOWER * 2;
+    if (x_out) SCB_CUDA(cudaMemcpyAsync(x_out, e->h_x, bytes, cudaMemcpyDeviceToHost, st));
+    if (t_out) SCB_CUDA(cudaMemcpyAsync(t_out, e->h_t, bytes, cudaMemcpyDeviceToHost, st));
+    if (y_out) SCB_CUDA(cudaMemcpyAsync(y_out, e->h_y, bytes, cudaMemcpyDeviceToHost, st));
     SCB_CUDA(cudaStreamSynchronize(st));
     return SC_OK;
 }

@@ -333,4 +333,11 @@ __device__ __forceinline__ float ln_apply(float a, float mean, float rstd, float
     return __fmaf_rn(__fmul_rn(__fsub_rn(a, mean), rstd), gamma, beta);
 }
 
+// squeeze-excitation scalar pieces, shared for the same reason
+__device__ __forceinline__ float se_hidden(float b1, float half0, float half1)
+{
+    return fmaxf(__fadd_rn(__fadd_rn(b1, half0), half1), 0.f);
+}
+__device__ __forceinline__ float se_sigmoid(float g) { return __fdiv_rn(1.f, __fadd_rn(1.f, __expf(-g))); }
+
 }  // namespace scb

@@ -46,6 +46,7 @@
 #include "move_index.cuh"
 
 #include "tc_ptx.cuh"
+#include "tc_host.cuh"
 
 namespace scb {
 
@@ -708,9 +709,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     // one TMEM pass: per 32-channel chunk the sums of (acc + bias) and its square, combined in the
                     // fixed tree of tc_ptx.cuh (the latency kernel computes the same chunks in other CTAs)
                     uint32_t r2[32];
-                    float2 p[4];
-#pragma unroll 1
-                    for (int ch = 0; ch < 4; ch += 2) {
+                    float2 p0, p1, p2, p3;
+                    auto chunk_pair = [&](int ch, float2 &pa, float2 &pb) {
                         tmem_ld32_nowait(tcol + ch * 32, r);
                         tmem_ld32_nowait(tcol + ch * 32 + 32, r2);
                         tmem_wait_ld();
@@ -720,10 +720,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             a0[j] = __fadd_rn(__uint_as_float(r[j]), s_bias[c0 + ch * 32 + j]);
                             a1[j] = __fadd_rn(__uint_as_float(r2[j]), s_bias[c0 + ch * 32 + 32 + j]);
                         }
-                        ln_chunk_stats(a0, p[ch].x, p[ch].y);
-                        ln_chunk_stats(a1, p[ch + 1].x, p[ch + 1].y);
-                    }
-                    const float2 mine = ln_half(p[0], p[1], p[2], p[3]);
+                        ln_chunk_stats(a0, pa.x, pa.y);
+                        ln_chunk_stats(a1, pb.x, pb.y);
+                    };
+                    chunk_pair(0, p0, p1);
+                    chunk_pair(2, p2, p3);
+                    const float2 mine = ln_half(p0, p1, p2, p3);
                     *reinterpret_cast<float2 *>(s_stat + (chalf * 128 + row) * 2) = mine;
                     epi_bar_sync();
                     const float2 o = *reinterpret_cast<const float2 *>(s_stat + ((chalf ^ 1) * 128 + row) * 2);
@@ -855,7 +857,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     epi_bar_sync();
                     {
                         const int b = te >> 7, j = te & 127;  // [board][hidden unit]
-                        s_hid[te] = fmaxf(P.b1[j] + s_hidp[b * 128 + j] + s_hidp[(2 + b) * 128 + j], 0.f);
+                        s_hid[te] = se_hidden(P.b1[j], s_hidp[b * 128 + j], s_hidp[(2 + b) * 128 + j]);
                     }
                     epi_bar_sync();
                     // ---- FC2 (128 -> 256) + sigmoid: thread te owns channel te for both boards
@@ -874,8 +876,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             g1 = fmaf(wf[0], h1a.x, g1); g1 = fmaf(wf[1], h1a.y, g1); g1 = fmaf(wf[2], h1a.z, g1); g1 = fmaf(wf[3], h1a.w, g1);
                             g1 = fmaf(wf[4], h1b.x, g1); g1 = fmaf(wf[5], h1b.y, g1); g1 = fmaf(wf[6], h1b.z, g1); g1 = fmaf(wf[7], h1b.w, g1);
                         }
-                        s_gate[te] = 1.f / (1.f + __expf(-g0));
-                        s_gate[256 + te] = 1.f / (1.f + __expf(-g1));
+                        s_gate[te] = se_sigmoid(g0);
+                        s_gate[256 + te] = se_sigmoid(g1);
                     }
                     epi_bar_sync();
                     } else {
@@ -1047,7 +1049,7 @@ struct TcConv {
     std::vector<ActMap> act_maps;
 };
 
-static int encode_map(CUtensorMap *m, const void *ptr, int rank, const cuuint64_t *dims, const cuuint64_t *strides,
+int tc_encode_map(CUtensorMap *m, const void *ptr, int rank, const cuuint64_t *dims, const cuuint64_t *strides,
                       const cuuint32_t *box, const char *what)
 {
     EncodeTiledFn enc = get_encode();
@@ -1072,17 +1074,17 @@ static int make_act_map_4d(const void *ptr, int boards, int c, CUtensorMap *m)
     cuuint64_t dims[4] = {(cuuint64_t)c, 8, 8, (cuuint64_t)boards};
     cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)c * 16, (cuuint64_t)c * 128};
     cuuint32_t box[4] = {TC_BK, 8, 8, 2};
-    return encode_map(m, ptr, 4, dims, strides, box, "activations 4d");
+    return tc_encode_map(m, ptr, 4, dims, strides, box, "activations 4d");
 }
 
 // the same activations as {C, file, board, rank}: a box of 64 channels x 8 files x 2 boards x 10 ranks lands in
 // shared memory with rows ordered (rank, board, file), so the three dy taps are 2 KB apart in ONE box
-static int make_act_map_hbw(const void *ptr, int boards, int c, CUtensorMap *m)
+int tc_make_act_map_hbw(const void *ptr, int boards, int c, CUtensorMap *m)
 {
     cuuint64_t dims[4] = {(cuuint64_t)c, 8, (cuuint64_t)boards, 8};
     cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)c * 128, (cuuint64_t)c * 16};
     cuuint32_t box[4] = {TC_BK, 8, 2, 10};
-    return encode_map(m, ptr, 4, dims, strides, box, "activations (rank, board, file)");
+    return tc_encode_map(m, ptr, 4, dims, strides, box, "activations (rank, board, file)");
 }
 
 // plain row-major [rows][k] matrix, box = 64 k x 128 rows
@@ -1091,7 +1093,7 @@ static int make_act_map_2d(const void *ptr, int rows, int k, CUtensorMap *m)
     cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)k * 2};
     cuuint32_t box[2] = {TC_BK, TC_BM};
-    return encode_map(m, ptr, 2, dims, strides, box, "activations 2d");
+    return tc_encode_map(m, ptr, 2, dims, strides, box, "activations 2d");
 }
 
 template <int BN, int EPI, bool A4D> static int set_smem_attr()
@@ -1116,14 +1118,14 @@ int tc_conv_create(TcConv **out, const __nv_bfloat16 *w, int taps, int k_per_tap
     cuuint64_t dims[2] = {(cuuint64_t)k_per_tap, (cuuint64_t)taps * bn};
     cuuint64_t strides[1] = {(cuuint64_t)k_per_tap * 2};
     cuuint32_t box[2] = {TC_BK, (cuuint32_t)bn};
-    int rc = encode_map(&c->map_w, w, 2, dims, strides, box, "weights");
+    int rc = tc_encode_map(&c->map_w, w, 2, dims, strides, box, "weights");
     if (rc != SC_OK) {
         delete c;
         return rc;
     }
     if (bn == 256 && (epi == EPI_LN || epi == EPI_LN_SE)) {
         cuuint32_t box2[2] = {TC_BK, 128};
-        rc = encode_map(&c->map_w_half, w, 2, dims, strides, box2, "weights (pair half)");
+        rc = tc_encode_map(&c->map_w_half, w, 2, dims, strides, box2, "weights (pair half)");
         if (rc != SC_OK) {
             delete c;
             return rc;
@@ -1201,7 +1203,7 @@ int tc_tower_create(TcTower **out, const TcTowerLayerDesc *descs, int n, int boa
         }
         memset(&h[i], 0, sizeof(TowerLayer));
         if (TcCfg<256, true, true>::AREUSE)
-            SCB_CHECK(make_act_map_hbw(descs[i].in, boards_alloc, c->k_per_tap, &h[i].map_a));
+            SCB_CHECK(tc_make_act_map_hbw(descs[i].in, boards_alloc, c->k_per_tap, &h[i].map_a));
         else
             SCB_CHECK(make_act_map_4d(descs[i].in, boards_alloc, c->k_per_tap, &h[i].map_a));
         h[i].map_w = c->map_w_half;
@@ -1217,9 +1219,11 @@ int tc_tower_create(TcTower **out, const TcTowerLayerDesc *descs, int n, int boa
         h[i].taps = c->taps;
         h[i].kchunks = c->k_per_tap / TC_BK;
         h[i].relu = descs[i].relu;
-        h[i].se = c->epi == EPI_LN_SE;
-        if (h[i].se && (!c->se_w1p || !descs[i].resid)) {
-            set_error("tc_tower_create: SE layer without SE weights / residual");
+        // se: 1 = squeeze-excitation gate, 2 = residual + ReLU only (`use_se=False`, no SE weights)
+        h[i].se = c->epi == EPI_LN_SE ? (c->se_w1p ? 1 : 2) : 0;
+        h[i].ln = c->gamma != nullptr;  // no LayerNorm parameters: BatchNorm folded into weights + bias at export
+        if (h[i].se && !descs[i].resid) {
+            set_error("tc_tower_create: residual layer without block input");
             return SC_E_INVAL;
         }
     }
@@ -1246,7 +1250,7 @@ void tc_tower_destroy(TcTower *t)
 
 // returns SC_E_STATE (without an error message) when the batch needs more tile slots per CTA than the
 // kernel tracks; the caller then runs the layers one launch at a time
-int tc_tower_launch(TcTower *t, int n_boards, int num_sms, int group, cudaStream_t st)
+int tc_tower_launch(TcTower *t, int n_boards, int num_sms, int group, cudaStream_t st, int max_layers)
 {
     if (n_boards <= 0) return SC_OK;
     const int n_tiles = (n_boards + 1) / 2;
@@ -1260,7 +1264,7 @@ int tc_tower_launch(TcTower *t, int n_boards, int num_sms, int group, cudaStream
     a.n_tiles = n_tiles;
     a.n_splits = 1;
     a.layers = t->d_layers;
-    a.n_layers = t->n_layers;
+    a.n_layers = max_layers > 0 && max_layers < t->n_layers ? max_layers : t->n_layers;
     a.group = group;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(g2);
@@ -1318,7 +1322,7 @@ int tc_conv_launch(TcConv *c, const __nv_bfloat16 *in, int rows_alloc, int n_uni
         am.c = c->k_per_tap;
         am.hbw = hbw;
         if (hbw)
-            SCB_CHECK(make_act_map_hbw(in, rows_alloc, c->k_per_tap, &am.map));
+            SCB_CHECK(tc_make_act_map_hbw(in, rows_alloc, c->k_per_tap, &am.map));
         else if (a4d)
             SCB_CHECK(make_act_map_4d(in, rows_alloc, c->k_per_tap, &am.map));
         else
@@ -1344,6 +1348,7 @@ int tc_conv_launch(TcConv *c, const __nv_bfloat16 *in, int rows_alloc, int n_uni
     a.se_b1 = c->se_b1;
     a.se_b2 = c->se_b2;
     a.relu = relu;
+    a.ln = c->gamma != nullptr;
     a.n_splits = n_splits > 0 ? n_splits : 1;
     a.m_rows = n_units;
     if (a4d) {
@@ -1376,8 +1381,8 @@ int tc_conv_launch(TcConv *c, const __nv_bfloat16 *in, int rows_alloc, int n_uni
         if (c->epi == EPI_LN)
             SCB_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<256, EPI_LN, true, true>, *ma, c->map_w_half, a));
         else {
-            if (!c->se_w1p || !resid) {
-                set_error("tc_conv_launch: SE epilogue without SE weights / residual");
+            if (!resid) {
+                set_error("tc_conv_launch: residual epilogue without block input");
                 return SC_E_INVAL;
             }
             SCB_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<256, EPI_LN_SE, true, true>, *ma, c->map_w_half, a));
@@ -1389,8 +1394,8 @@ int tc_conv_launch(TcConv *c, const __nv_bfloat16 *in, int rows_alloc, int n_uni
         tc_gemm_kernel<256, EPI_LN, true><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, st>>>(*ma, c->map_w, a);
         break;
     case EPI_LN_SE:
-        if (!c->se_w1p || !resid) {
-            set_error("tc_conv_launch: SE epilogue without SE weights / residual");
+        if (!resid) {
+            set_error("tc_conv_launch: residual epilogue without block input");
             return SC_E_INVAL;
         }
         tc_gemm_kernel<256, EPI_LN_SE, true><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, st>>>(*ma, c->map_w, a);

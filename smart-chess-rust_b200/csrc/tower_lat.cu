@@ -1,0 +1,613 @@
+// Latency path of the bf16 network for small batches (the `Game::predict` drop-in, src/backends/torch.rs:115-125, is a
+// batch of ONE): the same arithmetic as tower_bf16.cu, bit for bit, laid out for latency instead of throughput.
+//
+// tower_bf16.cu gives a 4-board tile to one CTA pair and walks the 41 convolutions with it: for a batch of <= 4 boards
+// two SMs work and 146 idle (~18 us per layer, 0.75 ms per call).  Here a tile is TWO boards (128 rows) and its 256
+// output channels are split over a thread-block cluster of CL = 8 (32 channels per CTA) or 4 (64 per CTA) CTAs, all
+// layers in one launch:
+//   * every CTA loads the tile's full activations (A, TMA box {64 ch, 8 files, 2 boards, 10 ranks} per (channel chunk,
+//     dx), three dy taps per box as in tower_bf16.cu) and ITS slice of the weights (B, box {64, NC, 1, 3}: the three dy
+//     taps of (chunk, dx) in one load) and issues tcgen05.mma M128 x N(NC) x K16 in the throughput kernel's k order;
+//   * LayerNorm needs statistics over all 256 channels of a row: every CTA pushes its per-32-channel partial sums into
+//     the shared memory of all CTAs of the cluster (st.shared::cluster) and signals their mbarriers; the partials are
+//     combined in the fixed tree of tc_ptx.cuh, which is what makes the result identical to the throughput kernel;
+//   * squeeze-excitation: channel means are pushed the same way, FC1 is split by hidden unit over the CTAs (each
+//     pushes its 128/CL hidden activations), FC2 and the gate are per channel, i.e. local;
+//   * layer l+1 reads layer l's output through L2: after its stores a CTA signals the `ready` mbarrier of every CTA of
+//     the cluster, whose TMA warp then starts the next layer's activation loads.  Weight loads never wait for
+//     activations: their producer warp runs ahead through the layers as far as its ring allows.
+// Warp roles (256 threads): 0 = activation TMA, 1 = weight TMA, 2 = TMEM allocator + MMA issuer, 3 = SE weight
+// staging, 4..7 = epilogue (one thread per row of the tile).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "tc_host.cuh"
+#include "tc_ptx.cuh"
+
+namespace scb {
+
+constexpr int LAT_THREADS = 256;
+constexpr int LAT_A_BOX = 160 * TC_BK * 2;  // 10 ranks x 2 boards x 8 files rows of 128 B
+
+struct alignas(64) LatLayer {
+    CUtensorMap map_a;  // input activations {C, file, board, rank}
+    CUtensorMap map_w;  // weights {cin, cout, dx, dy}, box {64, NC, 1, 3 | 1}
+    void *out;
+    const __nv_bfloat16 *resid;
+    const float *bias, *gamma, *beta;
+    const uint4 *se_w1s, *se_w2s;  // per cluster rank: fc1 slice [32][HJ] x 8 bf16, fc2 slice [16][NC] x 8 bf16
+    const float *se_b1, *se_b2;
+    int taps, kchunks, relu, se, ln;
+};
+
+struct LatArgs {
+    const LatLayer *layers;
+    int n_layers;
+    int n_tiles;
+};
+
+template <int CL> struct LatCfg {
+    static constexpr int NC = 256 / CL;  // output channels per CTA
+    static constexpr int HJ = 128 / CL;  // SE hidden units per CTA
+    static constexpr int NA = 3;         // activation boxes in flight
+    static constexpr int B_TILE = 3 * NC * TC_BK * 2;
+    static constexpr int NBS = CL == 8 ? 8 : 4;
+    static constexpr int W1S_BYTES = 32 * HJ * 16, W2S_BYTES = 16 * NC * 16;
+    static constexpr int OFF_B = NA * LAT_A_BOX;
+    static constexpr int OFF_W1S = OFF_B + NBS * B_TILE;
+    static constexpr int OFF_W2S = OFF_W1S + W1S_BYTES;
+    static constexpr int OFF_STAT = OFF_W2S + W2S_BYTES;  // float2 [8 chunks][128 rows]
+    static constexpr int OFF_PAR = OFF_STAT + 8 * 128 * 8;  // bias, gamma, beta [NC]
+    static constexpr int OFF_POOL = OFF_PAR + 2 * 3 * NC * 4;  // (parameters double-buffered by layer parity) [4 quads][2 boards][NC]
+    static constexpr int OFF_MEAN = OFF_POOL + 8 * NC * 4;  // [2][256]
+    static constexpr int OFF_HIDP = OFF_MEAN + 2 * 256 * 4;  // [2 halves][2 boards][HJ]
+    static constexpr int OFF_HID = OFF_HIDP + 4 * HJ * 4;    // [2][128]
+    static constexpr int OFF_GATE = OFF_HID + 2 * 128 * 4;   // [2][NC]
+    static constexpr int OFF_BARS = (OFF_GATE + 2 * NC * 4 + 7) & ~7;
+    static constexpr int N_BARS = 2 * NA + 2 * NBS + 7;
+    static constexpr int SMEM_BYTES = OFF_BARS + N_BARS * 8 + 16;
+};
+
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t cta)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_f32x2(uint32_t addr, float a, float b)
+{
+    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float a)
+{
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void lat_epi_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// after the stores of a warp: lane c (< CL) signals barrier `bar` (same offset in every CTA) of CTA c
+template <int CL> __device__ __forceinline__ void signal_all(uint32_t bar, int lane)
+{
+    asm volatile("fence.acq_rel.cluster;" ::: "memory");  // this thread's (remote) stores are ordered before the signal
+    __syncwarp();
+    if (lane < CL) mbar_arrive_cluster(map_to_cta(bar, (uint32_t)lane));
+}
+
+template <int CL>
+__global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs args)
+{
+    using Cfg = LatCfg<CL>;
+    constexpr int NC = Cfg::NC, HJ = Cfg::HJ, NA = Cfg::NA, NBS = Cfg::NBS, B_TILE = Cfg::B_TILE;
+    constexpr int NCH = NC / 32;  // 32-channel chunks per CTA
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t smem_base = smem_u32(smem);
+    if (smem_base & 1023u) __trap();
+    float2 *s_stat = reinterpret_cast<float2 *>(smem + Cfg::OFF_STAT);
+    float *s_par = reinterpret_cast<float *>(smem + Cfg::OFF_PAR);
+    float *s_pool = reinterpret_cast<float *>(smem + Cfg::OFF_POOL);
+    float *s_mean = reinterpret_cast<float *>(smem + Cfg::OFF_MEAN);
+    float *s_hidp = reinterpret_cast<float *>(smem + Cfg::OFF_HIDP);
+    float *s_hid = reinterpret_cast<float *>(smem + Cfg::OFF_HID);
+    float *s_gate = reinterpret_cast<float *>(smem + Cfg::OFF_GATE);
+    const uint4 *s_w1s = reinterpret_cast<const uint4 *>(smem + Cfg::OFF_W1S);
+    const uint4 *s_w2s = reinterpret_cast<const uint4 *>(smem + Cfg::OFF_W2S);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::OFF_BARS);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + Cfg::N_BARS);
+    const uint32_t bar_base = smem_u32(bars);
+    auto afull = [&](int s) { return bar_base + 8u * s; };
+    auto aempty = [&](int s) { return bar_base + 8u * (NA + s); };
+    auto bfull = [&](int s) { return bar_base + 8u * (2 * NA + s); };
+    auto bempty = [&](int s) { return bar_base + 8u * (2 * NA + NBS + s); };
+    const uint32_t bar_tfull = bar_base + 8u * (2 * NA + 2 * NBS), bar_ready = bar_tfull + 8, bar_stat = bar_tfull + 16,
+                   bar_mean = bar_tfull + 24, bar_hid = bar_tfull + 32, bar_sewf = bar_tfull + 40, bar_sewe = bar_tfull + 48;
+    auto abox = [&](int s) { return smem_base + (uint32_t)(s * LAT_A_BOX); };
+    auto btile = [&](int s) { return smem_base + (uint32_t)(Cfg::OFF_B + s * B_TILE); };
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const uint32_t rank = __shfl_sync(0xffffffffu, cluster_ctarank(), 0);
+    const int tile = (int)blockIdx.x / CL;
+    const int n_layers = args.n_layers;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2 * NA + 2 * NBS; s++) mbar_init(bar_base + 8u * s, 1);
+        mbar_init(bar_tfull, 1);
+        mbar_init(bar_ready, CL * 4);
+        mbar_init(bar_stat, CL * 4);
+        mbar_init(bar_mean, CL * 4);
+        mbar_init(bar_hid, CL * 4);
+        mbar_init(bar_sewf, 1);
+        mbar_init(bar_sewe, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)(NC < 32 ? 32 : NC))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // every CTA's barriers exist before any remote arrive
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ---- activation boxes: wait until the whole cluster has written the previous layer ----
+        int st = 0;
+        uint32_t ph = 0;
+        for (int l = 0; l < n_layers; l++) {
+            const LatLayer &L = args.layers[l];
+            const int nd = L.taps == 9 ? 3 : 1;
+            if (l > 0) {
+                mbar_wait_cluster(bar_ready, (uint32_t)(l - 1) & 1u);
+                asm volatile("fence.proxy.async;" ::: "memory");
+            }
+            for (int kc = 0; kc < L.kchunks; kc++)
+                for (int dxi = 0; dxi < nd; dxi++) {
+                    mbar_wait(aempty(st), ph ^ 1u);
+                    if (elect_one()) {
+                        mbar_expect_tx(afull(st), LAT_A_BOX);
+                        tma_load_4d(abox(st), &L.map_a, afull(st), kc * TC_BK, nd == 3 ? dxi - 1 : 0, tile * 2, -1);
+                    }
+                    __syncwarp();
+                    if (++st == NA) {
+                        st = 0;
+                        ph ^= 1u;
+                    }
+                }
+        }
+    } else if (warp == 1) {
+        // ---- this CTA's slice of the weights; independent of the activations, runs ahead ----
+        int st = 0;
+        uint32_t ph = 0;
+        for (int l = 0; l < n_layers; l++) {
+            const LatLayer &L = args.layers[l];
+            const int nd = L.taps == 9 ? 3 : 1;
+            for (int kc = 0; kc < L.kchunks; kc++)
+                for (int dxi = 0; dxi < nd; dxi++) {
+                    mbar_wait(bempty(st), ph ^ 1u);
+                    if (elect_one()) {
+                        mbar_expect_tx(bfull(st), (uint32_t)(nd * NC * TC_BK * 2));
+                        tma_load_4d(btile(st), &L.map_w, bfull(st), kc * TC_BK, (int)rank * NC, dxi, 0);
+                    }
+                    __syncwarp();
+                    if (++st == NBS) {
+                        st = 0;
+                        ph ^= 1u;
+                    }
+                }
+        }
+    } else if (warp == 2) {
+        // ---- MMA issuer: k order (channel chunk, dx, dy, 16-element step) as in tower_bf16.cu ----
+        constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, NC);
+        int ra = 0, rb = 0;
+        uint32_t rap = 0, rbp = 0;
+        for (int l = 0; l < n_layers; l++) {
+            const LatLayer &L = args.layers[l];
+            const int nd = L.taps == 9 ? 3 : 1;
+            uint32_t acc = 0;
+            for (int g = 0; g < L.kchunks * nd; g++) {
+                mbar_wait(afull(ra), rap);
+                mbar_wait(bfull(rb), rbp);
+                tc_fence_after();
+                const uint32_t a0 = abox(ra), b0 = btile(rb);
+                if (elect_one()) {
+                    for (int dyi = 0; dyi < nd; dyi++) {
+                        const uint64_t da = umma_desc_sw128(a0 + (uint32_t)((nd == 3 ? dyi : 1) * 2048));
+                        const uint64_t db = umma_desc_sw128(b0 + (uint32_t)(dyi * NC * TC_BK * 2));
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 16; k++)
+                            tc_mma_bf16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                                        (acc | (uint32_t)dyi | (uint32_t)k) != 0);
+                    }
+                    tc_commit(aempty(ra));
+                    tc_commit(bempty(rb));
+                }
+                __syncwarp();
+                acc = 1;
+                if (++ra == NA) {
+                    ra = 0;
+                    rap ^= 1u;
+                }
+                if (++rb == NBS) {
+                    rb = 0;
+                    rbp ^= 1u;
+                }
+            }
+            if (elect_one()) tc_commit(bar_tfull);
+            __syncwarp();
+        }
+    } else if (warp == 3) {
+        // ---- SE weights of this CTA's hidden units (fc1) and channels (fc2) -> shared memory, one SE layer ahead ----
+        int k = 0;
+        for (int l = 0; l < n_layers; l++) {
+            const LatLayer &L = args.layers[l];
+            if (L.se != 1) continue;
+            if (k > 0) mbar_wait(bar_sewe, (uint32_t)(k - 1) & 1u);  // the previous SE layer's FC2 has read them
+            if (elect_one()) {
+                mbar_expect_tx(bar_sewf, Cfg::W1S_BYTES + Cfg::W2S_BYTES);
+                bulk_g2s(smem_base + Cfg::OFF_W1S, L.se_w1s + (size_t)rank * (Cfg::W1S_BYTES / 16), Cfg::W1S_BYTES, bar_sewf);
+                bulk_g2s(smem_base + Cfg::OFF_W2S, L.se_w2s + (size_t)rank * (Cfg::W2S_BYTES / 16), Cfg::W2S_BYTES, bar_sewf);
+            }
+            __syncwarp();
+            k++;
+        }
+    } else {
+        // ---- epilogue: thread = accumulator row (rank, board, file) of the tile ----
+        const int quad = warp & 3;
+        const int te = quad * 32 + lane;               // 0..127 = accumulator row
+        const int board = (te >> 3) & 1;
+        const int orow = board * 64 + (te >> 4) * 8 + (te & 7);  // the row's place in memory
+        const int c0 = (int)rank * NC;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+        const size_t grow = (size_t)tile * TC_BM + orow;
+        int n_stat = 0, n_se = 0;
+        for (int l = 0; l < n_layers; l++) {
+            const LatLayer &L = args.layers[l];
+            // this layer's parameters; double-buffered, a slow warp may still be reading the previous layer's
+            float *s_bias = s_par + (l & 1) * 3 * NC, *s_gamma = s_bias + NC, *s_beta = s_gamma + NC;
+            if (te < NC) {
+                s_bias[te] = L.bias[c0 + te];
+                s_gamma[te] = L.ln ? L.gamma[c0 + te] : 1.f;
+                s_beta[te] = L.ln ? L.beta[c0 + te] : 0.f;
+            }
+            // the residual does not depend on this layer: request it before anything else
+            uint4 xres[NC / 8];
+            if (L.se) {
+                const uint4 *xg = reinterpret_cast<const uint4 *>(L.resid + grow * 256 + c0);
+#pragma unroll
+                for (int i = 0; i < NC / 8; i++) xres[i] = xg[i];
+            }
+            lat_epi_sync();  // parameters visible
+            mbar_wait(bar_tfull, (uint32_t)l & 1u);
+            tc_fence_after();
+            float a[NC];
+#pragma unroll
+            for (int ch = 0; ch < NCH; ch++) {
+                uint32_t r[32];
+                tmem_ld32(taddr + ch * 32, r);
+#pragma unroll
+                for (int j = 0; j < 32; j++) a[ch * 32 + j] = __fadd_rn(__uint_as_float(r[j]), s_bias[ch * 32 + j]);
+            }
+            tc_fence_before();
+            float mean = 0.f, rstd = 1.f;
+            if (L.ln) {
+                // per-chunk partial sums -> every CTA of the cluster
+#pragma unroll
+                for (int ch = 0; ch < NCH; ch++) {
+                    float av[32], s, q;
+#pragma unroll
+                    for (int j = 0; j < 32; j++) av[j] = a[ch * 32 + j];
+                    ln_chunk_stats(av, s, q);
+                    const uint32_t mine = smem_u32(s_stat + ((int)rank * NCH + ch) * 128 + te);
+#pragma unroll
+                    for (int c = 0; c < CL; c++) st_cluster_f32x2(map_to_cta(mine, (uint32_t)c), s, q);
+                }
+                signal_all<CL>(bar_stat, lane);
+                mbar_wait_cluster(bar_stat, (uint32_t)n_stat & 1u);
+                n_stat++;
+                const float2 h0 = ln_half(s_stat[0 * 128 + te], s_stat[1 * 128 + te], s_stat[2 * 128 + te], s_stat[3 * 128 + te]);
+                const float2 h1 = ln_half(s_stat[4 * 128 + te], s_stat[5 * 128 + te], s_stat[6 * 128 + te], s_stat[7 * 128 + te]);
+                ln_finish(h0, h1, LN_EPS, mean, rstd);
+            }
+#pragma unroll
+            for (int j = 0; j < NC; j++) a[j] = ln_apply(a[j], mean, rstd, s_gamma[j], s_beta[j]);
+            __nv_bfloat16 *og = static_cast<__nv_bfloat16 *>(L.out) + grow * 256 + c0;
+            if (!L.se) {
+                // ---- bias + LayerNorm (+ReLU) -> bf16 ----
+#pragma unroll
+                for (int i = 0; i < NC / 8; i++) {
+                    uint32_t pw[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        float y0 = a[8 * i + 2 * k], y1 = a[8 * i + 2 * k + 1];
+                        if (L.relu) {
+                            y0 = fmaxf(y0, 0.f);
+                            y1 = fmaxf(y1, 0.f);
+                        }
+                        __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);
+                        pw[k] = *reinterpret_cast<uint32_t *>(&h);
+                    }
+                    reinterpret_cast<uint4 *>(og)[i] = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+                }
+            } else {
+                if (L.se == 1) {
+                    // ---- squeeze: channel sums of this warp's 16 rows per board, then over the four warps ----
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ch++) {
+                        float y[32];
+#pragma unroll
+                        for (int j = 0; j < 32; j++) y[j] = a[ch * 32 + j];
+                        int i0;
+                        const float2 ps = warp_transpose_reduce_2boards(y, lane, i0);
+                        *reinterpret_cast<float2 *>(s_pool + (quad * 2 + board) * NC + ch * 32 + i0) = ps;
+                    }
+                    lat_epi_sync();
+                    if (te < 2 * NC) {
+                        const int b = te / NC, c = te % NC;
+                        const float m = __fmul_rn(__fadd_rn(__fadd_rn(s_pool[b * NC + c], s_pool[(2 + b) * NC + c]),
+                                                            __fadd_rn(s_pool[(4 + b) * NC + c], s_pool[(6 + b) * NC + c])),
+                                                  1.f / 64.f);
+                        const uint32_t dst = smem_u32(s_mean + b * 256 + c0 + c);
+#pragma unroll
+                        for (int cc = 0; cc < CL; cc++) st_cluster_f32(map_to_cta(dst, (uint32_t)cc), m);
+                    }
+                    signal_all<CL>(bar_mean, lane);
+                    mbar_wait(bar_sewf, (uint32_t)n_se & 1u);  // this layer's SE weights are in shared memory
+                    mbar_wait_cluster(bar_mean, (uint32_t)n_se & 1u);
+                    // ---- excitation FC1, hidden units [rank * HJ, +HJ): thread = (unit, channel half), both boards,
+                    //      one sequential fma chain per (unit, half, board) as in tower_bf16.cu ----
+                    if (te < 2 * HJ) {
+                        const int j = te % HJ, hc = te / HJ;
+                        float h0 = 0.f, h1 = 0.f;
+#pragma unroll 4
+                        for (int u = 0; u < 16; u++) {
+                            const int q = hc * 16 + u;
+                            float wf[8];
+                            bf16x8_to_float(s_w1s[q * HJ + j], wf);
+                            const float4 m0a = *reinterpret_cast<const float4 *>(s_mean + q * 8);
+                            const float4 m0b = *reinterpret_cast<const float4 *>(s_mean + q * 8 + 4);
+                            const float4 m1a = *reinterpret_cast<const float4 *>(s_mean + 256 + q * 8);
+                            const float4 m1b = *reinterpret_cast<const float4 *>(s_mean + 256 + q * 8 + 4);
+                            h0 = fmaf(wf[0], m0a.x, h0); h0 = fmaf(wf[1], m0a.y, h0); h0 = fmaf(wf[2], m0a.z, h0); h0 = fmaf(wf[3], m0a.w, h0);
+                            h0 = fmaf(wf[4], m0b.x, h0); h0 = fmaf(wf[5], m0b.y, h0); h0 = fmaf(wf[6], m0b.z, h0); h0 = fmaf(wf[7], m0b.w, h0);
+                            h1 = fmaf(wf[0], m1a.x, h1); h1 = fmaf(wf[1], m1a.y, h1); h1 = fmaf(wf[2], m1a.z, h1); h1 = fmaf(wf[3], m1a.w, h1);
+                            h1 = fmaf(wf[4], m1b.x, h1); h1 = fmaf(wf[5], m1b.y, h1); h1 = fmaf(wf[6], m1b.z, h1); h1 = fmaf(wf[7], m1b.w, h1);
+                        }
+                        s_hidp[(hc * 2 + 0) * HJ + j] = h0;
+                        s_hidp[(hc * 2 + 1) * HJ + j] = h1;
+                    }
+                    lat_epi_sync();
+                    if (te < 2 * HJ) {
+                        const int b = te / HJ, j = te % HJ;
+                        const int jg = (int)rank * HJ + j;
+                        const float h = se_hidden(L.se_b1[jg], s_hidp[b * HJ + j], s_hidp[(2 + b) * HJ + j]);
+                        const uint32_t dst = smem_u32(s_hid + b * 128 + jg);
+#pragma unroll
+                        for (int cc = 0; cc < CL; cc++) st_cluster_f32(map_to_cta(dst, (uint32_t)cc), h);
+                    }
+                    signal_all<CL>(bar_hid, lane);
+                    mbar_wait_cluster(bar_hid, (uint32_t)n_se & 1u);
+                    // ---- FC2 + sigmoid for this CTA's channels: thread = (board, channel) ----
+                    if (te < 2 * NC) {
+                        const int b = te / NC, c = te % NC;
+                        float g = L.se_b2[c0 + c];
+#pragma unroll 4
+                        for (int q = 0; q < 16; q++) {
+                            float wf[8];
+                            bf16x8_to_float(s_w2s[q * NC + c], wf);
+                            const float4 ha = *reinterpret_cast<const float4 *>(s_hid + b * 128 + q * 8);
+                            const float4 hb = *reinterpret_cast<const float4 *>(s_hid + b * 128 + q * 8 + 4);
+                            g = fmaf(wf[0], ha.x, g); g = fmaf(wf[1], ha.y, g); g = fmaf(wf[2], ha.z, g); g = fmaf(wf[3], ha.w, g);
+                            g = fmaf(wf[4], hb.x, g); g = fmaf(wf[5], hb.y, g); g = fmaf(wf[6], hb.z, g); g = fmaf(wf[7], hb.w, g);
+                        }
+                        s_gate[b * NC + c] = se_sigmoid(g);
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_sewe);  // the SE weight buffers may be refilled
+                    lat_epi_sync();
+                    n_se++;
+                }
+                // ---- out = relu(gate * bf16(y) + x), in place over the block input ----
+                const float *gate = s_gate + board * NC;
+#pragma unroll
+                for (int i = 0; i < NC / 8; i++) {
+                    const uint32_t xw[4] = {xres[i].x, xres[i].y, xres[i].z, xres[i].w};
+                    uint32_t pw[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int c = 8 * i + 2 * k;
+                        const float yb0 = __bfloat162float(__float2bfloat16_rn(a[c]));
+                        const float yb1 = __bfloat162float(__float2bfloat16_rn(a[c + 1]));
+                        const float g0 = L.se == 1 ? gate[c] : 1.f, g1 = L.se == 1 ? gate[c + 1] : 1.f;
+                        const float o0 = fmaxf(fmaf(g0, yb0, __uint_as_float(xw[k] << 16)), 0.f);
+                        const float o1 = fmaxf(fmaf(g1, yb1, __uint_as_float(xw[k] & 0xffff0000u)), 0.f);
+                        __nv_bfloat162 h = __floats2bfloat162_rn(o0, o1);
+                        pw[k] = *reinterpret_cast<uint32_t *>(&h);
+                    }
+                    reinterpret_cast<uint4 *>(og)[i] = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+                }
+            }
+            // ---- hand the layer's output to the TMA loads of the whole cluster ----
+            __threadfence();
+            asm volatile("fence.proxy.async;" ::: "memory");
+            signal_all<CL>(bar_ready, lane);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // no CTA leaves while a peer may still signal it
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "r"((uint32_t)(NC < 32 ? 32 : NC))
+                     : "memory");
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------
+struct LatTower {
+    LatLayer *d_layers[2] = {nullptr, nullptr};  // [0]: CL = 8, [1]: CL = 4
+    int n_layers = 0;
+    int max_tiles[2] = {0, 0};                   // co-resident clusters of 8 / 4 CTAs
+};
+
+template <int CL> static int lat_max_clusters(int *out)
+{
+    SCB_CUDA(cudaFuncSetAttribute(lat_tower_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, LatCfg<CL>::SMEM_BYTES));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(CL * 64);
+    cfg.blockDim = dim3(LAT_THREADS);
+    cfg.dynamicSmemBytes = LatCfg<CL>::SMEM_BYTES;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    SCB_CUDA(cudaOccupancyMaxActiveClusters(&n, lat_tower_kernel<CL>, &cfg));
+    *out = n;
+    return SC_OK;
+}
+
+int lat_tower_create(LatTower **out, const LatLayerDesc *descs, int n, int boards_alloc)
+{
+    LatTower *t = new LatTower();
+    t->n_layers = n;
+    for (int v = 0; v < 2; v++) {
+        const int CL = v == 0 ? 8 : 4, NC = 256 / CL;
+        std::vector<LatLayer> h((size_t)n);
+        for (int i = 0; i < n; i++) {
+            const LatLayerDesc &d = descs[i];
+            LatLayer &L = h[i];
+            memset(&L, 0, sizeof(L));
+            int rc = tc_make_act_map_hbw(d.in, boards_alloc, d.cin_pad, &L.map_a);
+            if (rc == SC_OK) {
+                // weights [tap = dy * 3 + dx][256][cin_pad] as {cin, cout, dx, dy}
+                const int nd = d.taps == 9 ? 3 : 1;
+                cuuint64_t dims[4] = {(cuuint64_t)d.cin_pad, 256, (cuuint64_t)nd, (cuuint64_t)nd};
+                cuuint64_t strides[3] = {(cuuint64_t)d.cin_pad * 2, (cuuint64_t)d.cin_pad * 2 * 256,
+                                         (cuuint64_t)d.cin_pad * 2 * 256 * 3};
+                cuuint32_t box[4] = {TC_BK, (cuuint32_t)NC, 1, (cuuint32_t)nd};
+                rc = tc_encode_map(&L.map_w, d.w, 4, dims, strides, box, "weights (cluster slice)");
+            }
+            if (rc != SC_OK) {
+                lat_tower_destroy(t);
+                return rc;
+            }
+            L.out = d.out;
+            L.resid = d.resid;
+            L.bias = d.bias;
+            L.gamma = d.gamma;
+            L.beta = d.beta;
+            L.se_w1s = static_cast<const uint4 *>(v == 0 ? d.se_w1s8 : d.se_w1s4);
+            L.se_w2s = static_cast<const uint4 *>(v == 0 ? d.se_w2s8 : d.se_w2s4);
+            L.se_b1 = d.se_b1;
+            L.se_b2 = d.se_b2;
+            L.taps = d.taps;
+            L.kchunks = d.cin_pad / TC_BK;
+            L.relu = d.relu;
+            L.se = d.se;
+            L.ln = d.ln;
+            if (d.se && !d.resid) {
+                set_error("lat_tower_create: residual layer without block input");
+                lat_tower_destroy(t);
+                return SC_E_INVAL;
+            }
+        }
+        if (cudaMalloc(&t->d_layers[v], sizeof(LatLayer) * (size_t)n) != cudaSuccess ||
+            cudaMemcpy(t->d_layers[v], h.data(), sizeof(LatLayer) * (size_t)n, cudaMemcpyHostToDevice) != cudaSuccess) {
+            lat_tower_destroy(t);
+            set_error("lat_tower_create: device allocation failed");
+            return SC_E_CUDA;
+        }
+    }
+    int rc = lat_max_clusters<8>(&t->max_tiles[0]);
+    if (rc == SC_OK) rc = lat_max_clusters<4>(&t->max_tiles[1]);
+    if (rc != SC_OK) {
+        lat_tower_destroy(t);
+        return rc;
+    }
+    if (getenv("SCB200_LAT_CLUSTER")) {  // A/B: force one cluster size
+        const int want = atoi(getenv("SCB200_LAT_CLUSTER"));
+        if (want == 4) t->max_tiles[0] = 0;
+        if (want == 8) t->max_tiles[1] = 0;
+    }
+    *out = t;
+    return SC_OK;
+}
+
+void lat_tower_destroy(LatTower *t)
+{
+    if (!t) return;
+    for (int v = 0; v < 2; v++)
+        if (t->d_layers[v]) cudaFree(t->d_layers[v]);
+    delete t;
+}
+
+int lat_tower_max_boards(const LatTower *t) { return t ? 2 * (t->max_tiles[0] > t->max_tiles[1] ? t->max_tiles[0] : t->max_tiles[1]) : 0; }
+
+template <int CL> static int lat_launch(const LatTower *t, int v, int n_tiles, cudaStream_t st, int max_layers)
+{
+    LatArgs a;
+    a.layers = t->d_layers[v];
+    a.n_layers = max_layers > 0 && max_layers < t->n_layers ? max_layers : t->n_layers;
+    a.n_tiles = n_tiles;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(n_tiles * CL);
+    cfg.blockDim = dim3(LAT_THREADS);
+    cfg.dynamicSmemBytes = LatCfg<CL>::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SCB_CUDA(cudaLaunchKernelEx(&cfg, lat_tower_kernel<CL>, a));
+    SCB_CUDA(cudaGetLastError());
+    return SC_OK;
+}
+
+// SC_E_STATE (no message): the batch does not fit one wave of clusters; the caller runs the throughput kernel
+int lat_tower_launch(LatTower *t, int n_boards, cudaStream_t st, int max_layers)
+{
+    if (n_boards <= 0) return SC_OK;
+    const int n_tiles = (n_boards + 1) / 2;
+    if (n_tiles <= t->max_tiles[0]) return lat_launch<8>(t, 0, n_tiles, st, max_layers);
+    if (n_tiles <= t->max_tiles[1]) return lat_launch<4>(t, 1, n_tiles, st, max_layers);
+    return SC_E_STATE;
+}
+
+}  // namespace scb

@@ -24,7 +24,7 @@ DECLARED_SYMBOLS = [
     "sc_eval_submit", "sc_eval_wait", "sc_selfplay_create", "sc_selfplay_run", "sc_selfplay_trace_json",
     "sc_selfplay_destroy", "sc_rules_probe", "sc_arena_create", "sc_encode_steps", "sc_timed_flops_per_leaf",
     "sc_random_positions", "sc_test_dirichlet", "sc_game_selfplay", "sc_rules_perft", "sc_device_info",
-    "sc_selfplay_run_many",
+    "sc_selfplay_run_many", "sc_debug_tower",
 ]
 
 
@@ -74,6 +74,7 @@ def load_library():
         L.sc_device_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.sc_selfplay_run_many.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int64, C.c_int64, C.c_double,
                                            C.POINTER(SelfPlayStats)]
+        L.sc_debug_tower.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.sc_eval.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 6
         L.sc_eval_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                      C.c_void_p, C.c_void_p]
@@ -257,6 +258,15 @@ class Engine:
                                               _ptr(planes), _ptr(meta), _ptr(dist), _ptr(index), _ptr(ioff)),
                "sc_encode_steps")
         return [(planes[i], meta[i], dist[i], index[ioff[i]:ioff[i + 1]].tolist()) for i in range(n)]
+
+    def debug_tower(self, positions, n_layers: int, which: int):
+        """test hook sc_debug_tower: (x, t, y) activation buffers as uint16 [n, 64, 256] after n_layers layers"""
+        n = len(positions)
+        positions = np.ascontiguousarray(positions, dtype=POSITION_DTYPE)
+        out = [np.zeros((n, 64, 256), dtype=np.uint16) for _ in range(3)]
+        _check(load_library().sc_debug_tower(self._h, n, _ptr(positions), n_layers, which, _ptr(out[0]), _ptr(out[1]),
+                                             _ptr(out[2])), "sc_debug_tower")
+        return out
 
     def launch_count(self) -> int:
         return int(load_library().sc_launch_count(self._h))

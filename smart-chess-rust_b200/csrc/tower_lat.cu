@@ -16,6 +16,8 @@
 //   * layer l+1 reads layer l's output through L2: after its stores a CTA signals the `ready` mbarrier of every CTA of
 //     the cluster, whose TMA warp then starts the next layer's activation loads.  Weight loads never wait for
 //     activations: their producer warp runs ahead through the layers as far as its ring allows.
+// A tile of ONE board (NB = 1: 64 rows, tcgen05.mma M64) halves the shared-memory operand traffic that bounds the MMA
+// phase at these narrow N; it is used while there are enough clusters for one board each.
 // Warp roles (256 threads): 0 = activation TMA, 1 = weight TMA, 2 = TMEM allocator + MMA issuer, 3 = SE weight
 // staging, 4..7 = epilogue (one thread per row of the tile).
 #include <cstdio>
@@ -33,7 +35,8 @@ constexpr int LAT_THREADS = 256;
 constexpr int LAT_A_BOX = 160 * TC_BK * 2;  // 10 ranks x 2 boards x 8 files rows of 128 B
 
 struct alignas(64) LatLayer {
-    CUtensorMap map_a;  // input activations {C, file, board, rank}
+    CUtensorMap map_a;   // input activations {C, file, board, rank}, box of two boards
+    CUtensorMap map_a1;  // the same tensor, box of one board
     CUtensorMap map_w;  // weights {cin, cout, dx, dy}, box {64, NC, 1, 3 | 1}
     void *out;
     const __nv_bfloat16 *resid;
@@ -47,16 +50,18 @@ struct LatArgs {
     const LatLayer *layers;
     int n_layers;
     int n_tiles;
+    long long *prof;  // optional [grid][16] cycle counters (SCB200_PHASE_PROFILE=1)
 };
 
-template <int CL> struct LatCfg {
+template <int CL, int NB = 2> struct LatCfg {
     static constexpr int NC = 256 / CL;  // output channels per CTA
     static constexpr int HJ = 128 / CL;  // SE hidden units per CTA
+    static constexpr int A_BOX = NB * 80 * TC_BK * 2;  // 10 ranks x NB boards x 8 files rows of 128 B
     static constexpr int NA = 3;         // activation boxes in flight
     static constexpr int B_TILE = 3 * NC * TC_BK * 2;
     static constexpr int NBS = CL == 8 ? 8 : 4;
     static constexpr int W1S_BYTES = 32 * HJ * 16, W2S_BYTES = 16 * NC * 16;
-    static constexpr int OFF_B = NA * LAT_A_BOX;
+    static constexpr int OFF_B = NA * LAT_A_BOX;  // (sized for two boards in both variants)
     static constexpr int OFF_W1S = OFF_B + NBS * B_TILE;
     static constexpr int OFF_W2S = OFF_W1S + W1S_BYTES;
     static constexpr int OFF_STAT = OFF_W2S + W2S_BYTES;  // float2 [8 chunks][128 rows]
@@ -77,13 +82,19 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t cta)
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
     return r;
 }
-__device__ __forceinline__ void st_cluster_f32x2(uint32_t addr, float a, float b)
+// store into the shared memory of a CTA of the cluster that also counts its bytes on an mbarrier of that CTA
+// (st.async): the receiver waits for the byte count, no fence and no separate arrive on the sender's side
+__device__ __forceinline__ void st_async_f32x2(uint32_t addr, float a, float b, uint32_t bar)
 {
-    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(addr),
+                 "f"(a), "f"(b), "r"(bar)
+                 : "memory");
 }
-__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float a)
+__device__ __forceinline__ void st_async_f32(uint32_t addr, float a, uint32_t bar)
 {
-    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(a) : "memory");
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];" ::"r"(addr), "f"(a),
+                 "r"(bar)
+                 : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
 {
@@ -110,20 +121,49 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
-__device__ __forceinline__ void lat_epi_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-
-// after the stores of a warp: lane c (< CL) signals barrier `bar` (same offset in every CTA) of CTA c
-template <int CL> __device__ __forceinline__ void signal_all(uint32_t bar, int lane)
+// Column sums over 16 lanes (lane bits 8, 4, 2, 1; bit 16 is not touched) of 32 per-lane values: the one-board tile's
+// form of warp_transpose_reduce_2boards -- same tree (rank pair first, then files 4, 2, 1), so the same bits.  Lane l
+// ends with the sums for indices i0, i0 + 1, i0 = 16 b8 + 8 b4 + 4 b2 + 2 b1.
+__device__ __forceinline__ float2 warp_transpose_reduce_16(float (&v)[32], int lane, int &i0)
 {
-    asm volatile("fence.acq_rel.cluster;" ::: "memory");  // this thread's (remote) stores are ordered before the signal
-    __syncwarp();
-    if (lane < CL) mbar_arrive_cluster(map_to_cta(bar, (uint32_t)lane));
+    const bool b8 = lane & 8, b4 = lane & 4, b2 = lane & 2, b1 = lane & 1;
+    float w16[16], w8[8], w4[4], w2[2];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        float send = b8 ? v[i] : v[i + 16];
+        float keep = b8 ? v[i + 16] : v[i];
+        w16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        float send = b4 ? w16[i] : w16[i + 8];
+        float keep = b4 ? w16[i + 8] : w16[i];
+        w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float send = b2 ? w8[i] : w8[i + 4];
+        float keep = b2 ? w8[i + 4] : w8[i];
+        w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        float send = b1 ? w4[i] : w4[i + 2];
+        float keep = b1 ? w4[i + 2] : w4[i];
+        w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+    }
+    i0 = (b8 ? 16 : 0) + (b4 ? 8 : 0) + (b2 ? 4 : 0) + (b1 ? 2 : 0);
+    return make_float2(w2[0], w2[1]);
 }
 
-template <int CL>
+__device__ __forceinline__ void lat_epi_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+
+template <int CL, int NB>
 __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs args)
 {
-    using Cfg = LatCfg<CL>;
+    using Cfg = LatCfg<CL, NB>;
+    constexpr int A_BOX = Cfg::A_BOX, DY_STEP = NB * 1024;  // bytes between the dy taps inside an activation box
     constexpr int NC = Cfg::NC, HJ = Cfg::HJ, NA = Cfg::NA, NBS = Cfg::NBS, B_TILE = Cfg::B_TILE;
     constexpr int NCH = NC / 32;  // 32-channel chunks per CTA
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -158,10 +198,10 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2 * NA + 2 * NBS; s++) mbar_init(bar_base + 8u * s, 1);
         mbar_init(bar_tfull, 1);
-        mbar_init(bar_ready, CL * 4);
-        mbar_init(bar_stat, CL * 4);
-        mbar_init(bar_mean, CL * 4);
-        mbar_init(bar_hid, CL * 4);
+        mbar_init(bar_ready, CL);  // one arrival per CTA of the cluster
+        mbar_init(bar_stat, 1);    // armed per layer with the bytes every CTA pushes (st.async)
+        mbar_init(bar_mean, 1);
+        mbar_init(bar_hid, 1);
         mbar_init(bar_sewf, 1);
         mbar_init(bar_sewe, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -182,19 +222,25 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs
         // ---- activation boxes: wait until the whole cluster has written the previous layer ----
         int st = 0;
         uint32_t ph = 0;
+        long long pa_ready = 0, pa_empty = 0;
         for (int l = 0; l < n_layers; l++) {
             const LatLayer &L = args.layers[l];
             const int nd = L.taps == 9 ? 3 : 1;
             if (l > 0) {
+                const long long t0 = args.prof ? clock64() : 0;
                 mbar_wait_cluster(bar_ready, (uint32_t)(l - 1) & 1u);
+                if (args.prof) pa_ready += clock64() - t0;
                 asm volatile("fence.proxy.async;" ::: "memory");
             }
             for (int kc = 0; kc < L.kchunks; kc++)
                 for (int dxi = 0; dxi < nd; dxi++) {
+                    const long long t1 = args.prof ? clock64() : 0;
                     mbar_wait(aempty(st), ph ^ 1u);
+                    if (args.prof) pa_empty += clock64() - t1;
                     if (elect_one()) {
-                        mbar_expect_tx(afull(st), LAT_A_BOX);
-                        tma_load_4d(abox(st), &L.map_a, afull(st), kc * TC_BK, nd == 3 ? dxi - 1 : 0, tile * 2, -1);
+                        mbar_expect_tx(afull(st), A_BOX);
+                        tma_load_4d(abox(st), NB == 2 ? &L.map_a : &L.map_a1, afull(st), kc * TC_BK, nd == 3 ? dxi - 1 : 0,
+                                    tile * NB, -1);
                     }
                     __syncwarp();
                     if (++st == NA) {
@@ -202,6 +248,10 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs
                         ph ^= 1u;
                     }
                 }
+        }
+        if (args.prof && lane == 0) {
+            args.prof[blockIdx.x * 16 + 0] = pa_ready;
+            args.prof[blockIdx.x * 16 + 1] = pa_empty;
         }
     } else if (warp == 1) {
         // ---- this CTA's slice of the weights; independent of the activations, runs ahead ----
@@ -226,21 +276,28 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs
         }
     } else if (warp == 2) {
         // ---- MMA issuer: k order (channel chunk, dx, dy, 16-element step) as in tower_bf16.cu ----
-        constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, NC);
+        constexpr uint32_t idesc = umma_idesc_bf16(64 * NB, NC);
         int ra = 0, rb = 0;
         uint32_t rap = 0, rbp = 0;
+        long long pm_a = 0, pm_a0 = 0, pm_b = 0, pm_total = args.prof ? clock64() : 0;
         for (int l = 0; l < n_layers; l++) {
             const LatLayer &L = args.layers[l];
             const int nd = L.taps == 9 ? 3 : 1;
             uint32_t acc = 0;
             for (int g = 0; g < L.kchunks * nd; g++) {
+                const long long t0 = args.prof ? clock64() : 0;
                 mbar_wait(afull(ra), rap);
+                const long long t1 = args.prof ? clock64() : 0;
                 mbar_wait(bfull(rb), rbp);
+                if (args.prof) {
+                    (g == 0 ? pm_a0 : pm_a) += t1 - t0;
+                    pm_b += clock64() - t1;
+                }
                 tc_fence_after();
                 const uint32_t a0 = abox(ra), b0 = btile(rb);
                 if (elect_one()) {
                     for (int dyi = 0; dyi < nd; dyi++) {
-                        const uint64_t da = umma_desc_sw128(a0 + (uint32_t)((nd == 3 ? dyi : 1) * 2048));
+                        const uint64_t da = umma_desc_sw128(a0 + (uint32_t)((nd == 3 ? dyi : 1) * DY_STEP));
                         const uint64_t db = umma_desc_sw128(b0 + (uint32_t)(dyi * NC * TC_BK * 2));
 #pragma unroll
                         for (int k = 0; k < TC_BK / 16; k++)
@@ -264,6 +321,12 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs
             if (elect_one()) tc_commit(bar_tfull);
             __syncwarp();
         }
+        if (args.prof && lane == 0) {
+            args.prof[blockIdx.x * 16 + 2] = pm_a0;
+            args.prof[blockIdx.x * 16 + 3] = pm_a;
+            args.prof[blockIdx.x * 16 + 4] = pm_b;
+            args.prof[blockIdx.x * 16 + 5] = clock64() - pm_total;
+        }
     } else if (warp == 3) {
         // ---- SE weights of this CTA's hidden units (fc1) and channels (fc2) -> shared memory, one SE layer ahead ----
         int k = 0;
@@ -280,33 +343,50 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs
             k++;
         }
     } else {
-        // ---- epilogue: thread = accumulator row (rank, board, file) of the tile ----
+        // ---- epilogue.  NB = 2: thread = accumulator row (rank, board, file), TMEM lane = row.  NB = 1 (M64): the 64
+        //      rows (rank, file) sit in lanes 0..15 of each 32-lane TMEM quadrant (row = 16 quad + lane); lanes 16..31
+        //      carry nothing but take part in the warp-wide instructions. ----
         const int quad = warp & 3;
-        const int te = quad * 32 + lane;               // 0..127 = accumulator row
-        const int board = (te >> 3) & 1;
-        const int orow = board * 64 + (te >> 4) * 8 + (te & 7);  // the row's place in memory
+        const int tid = quad * 32 + lane;  // 0..127: index for the work that is not tied to a row
+        const bool active = NB == 2 || lane < 16;
+        const int row = NB == 2 ? tid : quad * 16 + (lane & 15);
+        const int board = NB == 2 ? (row >> 3) & 1 : 0;
+        const int orow = NB == 2 ? board * 64 + (row >> 4) * 8 + (row & 7) : row;  // the row's place in memory
         const int c0 = (int)rank * NC;
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-        const size_t grow = (size_t)tile * TC_BM + orow;
+        const size_t grow = (size_t)tile * (64 * NB) + orow;
         int n_stat = 0, n_se = 0;
+        const bool prof = args.prof != nullptr && tid == 0;
+        long long pe_tfull = 0, pe_stat = 0, pe_se = 0, pe_work = 0, pe_ld = 0, pe_pfence = 0, pe_sync = 0, pe_gfence = 0;
         for (int l = 0; l < n_layers; l++) {
             const LatLayer &L = args.layers[l];
             // this layer's parameters; double-buffered, a slow warp may still be reading the previous layer's
             float *s_bias = s_par + (l & 1) * 3 * NC, *s_gamma = s_bias + NC, *s_beta = s_gamma + NC;
-            if (te < NC) {
-                s_bias[te] = L.bias[c0 + te];
-                s_gamma[te] = L.ln ? L.gamma[c0 + te] : 1.f;
-                s_beta[te] = L.ln ? L.beta[c0 + te] : 0.f;
+            if (tid < NC) {
+                s_bias[tid] = L.bias[c0 + tid];
+                s_gamma[tid] = L.ln ? L.gamma[c0 + tid] : 1.f;
+                s_beta[tid] = L.ln ? L.beta[c0 + tid] : 0.f;
             }
             // the residual does not depend on this layer: request it before anything else
             uint4 xres[NC / 8];
-            if (L.se) {
+            if (L.se && active) {
                 const uint4 *xg = reinterpret_cast<const uint4 *>(L.resid + grow * 256 + c0);
 #pragma unroll
                 for (int i = 0; i < NC / 8; i++) xres[i] = xg[i];
             }
+            if (tid == 0) {
+                // arm this layer's exchange barriers with the bytes the cluster will push into this CTA
+                if (L.ln) mbar_expect_tx(bar_stat, 8 * 64 * NB * 8);
+                if (L.se == 1) {
+                    mbar_expect_tx(bar_mean, NB * 256 * 4);
+                    mbar_expect_tx(bar_hid, NB * 128 * 4);
+                }
+            }
             lat_epi_sync();  // parameters visible
+            const long long tp0 = prof ? clock64() : 0;
             mbar_wait(bar_tfull, (uint32_t)l & 1u);
+            const long long tp1 = prof ? clock64() : 0;
+            pe_tfull += tp1 - tp0;
             tc_fence_after();
             float a[NC];
 #pragma unroll
@@ -317,24 +397,29 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs
                 for (int j = 0; j < 32; j++) a[ch * 32 + j] = __fadd_rn(__uint_as_float(r[j]), s_bias[ch * 32 + j]);
             }
             tc_fence_before();
+            if (prof) pe_ld += clock64() - tp1;
             float mean = 0.f, rstd = 1.f;
             if (L.ln) {
                 // per-chunk partial sums -> every CTA of the cluster
+                if (active) {
 #pragma unroll
-                for (int ch = 0; ch < NCH; ch++) {
-                    float av[32], s, q;
+                    for (int ch = 0; ch < NCH; ch++) {
+                        float av[32], sm, q;
 #pragma unroll
-                    for (int j = 0; j < 32; j++) av[j] = a[ch * 32 + j];
-                    ln_chunk_stats(av, s, q);
-                    const uint32_t mine = smem_u32(s_stat + ((int)rank * NCH + ch) * 128 + te);
+                        for (int j = 0; j < 32; j++) av[j] = a[ch * 32 + j];
+                        ln_chunk_stats(av, sm, q);
+                        const uint32_t mine = smem_u32(s_stat + ((int)rank * NCH + ch) * 128 + row);
 #pragma unroll
-                    for (int c = 0; c < CL; c++) st_cluster_f32x2(map_to_cta(mine, (uint32_t)c), s, q);
+                        for (int c = 0; c < CL; c++)
+                            st_async_f32x2(map_to_cta(mine, (uint32_t)c), sm, q, map_to_cta(bar_stat, (uint32_t)c));
+                    }
                 }
-                signal_all<CL>(bar_stat, lane);
+                const long long ts0 = prof ? clock64() : 0;
                 mbar_wait_cluster(bar_stat, (uint32_t)n_stat & 1u);
+                if (prof) pe_stat += clock64() - ts0;
                 n_stat++;
-                const float2 h0 = ln_half(s_stat[0 * 128 + te], s_stat[1 * 128 + te], s_stat[2 * 128 + te], s_stat[3 * 128 + te]);
-                const float2 h1 = ln_half(s_stat[4 * 128 + te], s_stat[5 * 128 + te], s_stat[6 * 128 + te], s_stat[7 * 128 + te]);
+                const float2 h0 = ln_half(s_stat[0 * 128 + row], s_stat[1 * 128 + row], s_stat[2 * 128 + row], s_stat[3 * 128 + row]);
+                const float2 h1 = ln_half(s_stat[4 * 128 + row], s_stat[5 * 128 + row], s_stat[6 * 128 + row], s_stat[7 * 128 + row]);
                 ln_finish(h0, h1, LN_EPS, mean, rstd);
             }
 #pragma unroll
@@ -342,22 +427,25 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs
             __nv_bfloat16 *og = static_cast<__nv_bfloat16 *>(L.out) + grow * 256 + c0;
             if (!L.se) {
                 // ---- bias + LayerNorm (+ReLU) -> bf16 ----
+                if (active) {
 #pragma unroll
-                for (int i = 0; i < NC / 8; i++) {
-                    uint32_t pw[4];
+                    for (int i = 0; i < NC / 8; i++) {
+                        uint32_t pw[4];
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        float y0 = a[8 * i + 2 * k], y1 = a[8 * i + 2 * k + 1];
-                        if (L.relu) {
-                            y0 = fmaxf(y0, 0.f);
-                            y1 = fmaxf(y1, 0.f);
+                        for (int k = 0; k < 4; k++) {
+                            float y0 = a[8 * i + 2 * k], y1 = a[8 * i + 2 * k + 1];
+                            if (L.relu) {
+                                y0 = fmaxf(y0, 0.f);
+                                y1 = fmaxf(y1, 0.f);
+                            }
+                            __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);
+                            pw[k] = *reinterpret_cast<uint32_t *>(&h);
                         }
-                        __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);
-                        pw[k] = *reinterpret_cast<uint32_t *>(&h);
+                        reinterpret_cast<uint4 *>(og)[i] = make_uint4(pw[0], pw[1], pw[2], pw[3]);
                     }
-                    reinterpret_cast<uint4 *>(og)[i] = make_uint4(pw[0], pw[1], pw[2], pw[3]);
                 }
             } else {
+                const long long tq0 = prof ? clock64() : 0;
                 if (L.se == 1) {
                     // ---- squeeze: channel sums of this warp's 16 rows per board, then over the four warps ----
 #pragma unroll
@@ -366,26 +454,26 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs
 #pragma unroll
                         for (int j = 0; j < 32; j++) y[j] = a[ch * 32 + j];
                         int i0;
-                        const float2 ps = warp_transpose_reduce_2boards(y, lane, i0);
-                        *reinterpret_cast<float2 *>(s_pool + (quad * 2 + board) * NC + ch * 32 + i0) = ps;
+                        const float2 ps = NB == 2 ? warp_transpose_reduce_2boards(y, lane, i0) : warp_transpose_reduce_16(y, lane, i0);
+                        if (active) *reinterpret_cast<float2 *>(s_pool + (quad * NB + board) * NC + ch * 32 + i0) = ps;
                     }
                     lat_epi_sync();
-                    if (te < 2 * NC) {
-                        const int b = te / NC, c = te % NC;
-                        const float m = __fmul_rn(__fadd_rn(__fadd_rn(s_pool[b * NC + c], s_pool[(2 + b) * NC + c]),
-                                                            __fadd_rn(s_pool[(4 + b) * NC + c], s_pool[(6 + b) * NC + c])),
+                    if (tid < NB * NC) {
+                        const int b = tid / NC, c = tid % NC;
+                        const float m = __fmul_rn(__fadd_rn(__fadd_rn(s_pool[b * NC + c], s_pool[(NB + b) * NC + c]),
+                                                            __fadd_rn(s_pool[(2 * NB + b) * NC + c], s_pool[(3 * NB + b) * NC + c])),
                                                   1.f / 64.f);
                         const uint32_t dst = smem_u32(s_mean + b * 256 + c0 + c);
 #pragma unroll
-                        for (int cc = 0; cc < CL; cc++) st_cluster_f32(map_to_cta(dst, (uint32_t)cc), m);
+                        for (int cc = 0; cc < CL; cc++)
+                            st_async_f32(map_to_cta(dst, (uint32_t)cc), m, map_to_cta(bar_mean, (uint32_t)cc));
                     }
-                    signal_all<CL>(bar_mean, lane);
                     mbar_wait(bar_sewf, (uint32_t)n_se & 1u);  // this layer's SE weights are in shared memory
                     mbar_wait_cluster(bar_mean, (uint32_t)n_se & 1u);
-                    // ---- excitation FC1, hidden units [rank * HJ, +HJ): thread = (unit, channel half), both boards,
-                    //      one sequential fma chain per (unit, half, board) as in tower_bf16.cu ----
-                    if (te < 2 * HJ) {
-                        const int j = te % HJ, hc = te / HJ;
+                    // ---- excitation FC1, hidden units [rank * HJ, +HJ): thread = (unit, channel half), all boards of the
+                    //      tile, one sequential fma chain per (unit, half, board) as in tower_bf16.cu ----
+                    if (tid < 2 * HJ) {
+                        const int j = tid % HJ, hc = tid / HJ;
                         float h0 = 0.f, h1 = 0.f;
 #pragma unroll 4
                         for (int u = 0; u < 16; u++) {
@@ -394,30 +482,32 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs
                             bf16x8_to_float(s_w1s[q * HJ + j], wf);
                             const float4 m0a = *reinterpret_cast<const float4 *>(s_mean + q * 8);
                             const float4 m0b = *reinterpret_cast<const float4 *>(s_mean + q * 8 + 4);
-                            const float4 m1a = *reinterpret_cast<const float4 *>(s_mean + 256 + q * 8);
-                            const float4 m1b = *reinterpret_cast<const float4 *>(s_mean + 256 + q * 8 + 4);
                             h0 = fmaf(wf[0], m0a.x, h0); h0 = fmaf(wf[1], m0a.y, h0); h0 = fmaf(wf[2], m0a.z, h0); h0 = fmaf(wf[3], m0a.w, h0);
                             h0 = fmaf(wf[4], m0b.x, h0); h0 = fmaf(wf[5], m0b.y, h0); h0 = fmaf(wf[6], m0b.z, h0); h0 = fmaf(wf[7], m0b.w, h0);
-                            h1 = fmaf(wf[0], m1a.x, h1); h1 = fmaf(wf[1], m1a.y, h1); h1 = fmaf(wf[2], m1a.z, h1); h1 = fmaf(wf[3], m1a.w, h1);
-                            h1 = fmaf(wf[4], m1b.x, h1); h1 = fmaf(wf[5], m1b.y, h1); h1 = fmaf(wf[6], m1b.z, h1); h1 = fmaf(wf[7], m1b.w, h1);
+                            if (NB == 2) {
+                                const float4 m1a = *reinterpret_cast<const float4 *>(s_mean + 256 + q * 8);
+                                const float4 m1b = *reinterpret_cast<const float4 *>(s_mean + 256 + q * 8 + 4);
+                                h1 = fmaf(wf[0], m1a.x, h1); h1 = fmaf(wf[1], m1a.y, h1); h1 = fmaf(wf[2], m1a.z, h1); h1 = fmaf(wf[3], m1a.w, h1);
+                                h1 = fmaf(wf[4], m1b.x, h1); h1 = fmaf(wf[5], m1b.y, h1); h1 = fmaf(wf[6], m1b.z, h1); h1 = fmaf(wf[7], m1b.w, h1);
+                            }
                         }
                         s_hidp[(hc * 2 + 0) * HJ + j] = h0;
-                        s_hidp[(hc * 2 + 1) * HJ + j] = h1;
+                        if (NB == 2) s_hidp[(hc * 2 + 1) * HJ + j] = h1;
                     }
                     lat_epi_sync();
-                    if (te < 2 * HJ) {
-                        const int b = te / HJ, j = te % HJ;
+                    if (tid < NB * HJ) {
+                        const int b = tid / HJ, j = tid % HJ;
                         const int jg = (int)rank * HJ + j;
                         const float h = se_hidden(L.se_b1[jg], s_hidp[b * HJ + j], s_hidp[(2 + b) * HJ + j]);
                         const uint32_t dst = smem_u32(s_hid + b * 128 + jg);
 #pragma unroll
-                        for (int cc = 0; cc < CL; cc++) st_cluster_f32(map_to_cta(dst, (uint32_t)cc), h);
+                        for (int cc = 0; cc < CL; cc++)
+                            st_async_f32(map_to_cta(dst, (uint32_t)cc), h, map_to_cta(bar_hid, (uint32_t)cc));
                     }
-                    signal_all<CL>(bar_hid, lane);
                     mbar_wait_cluster(bar_hid, (uint32_t)n_se & 1u);
                     // ---- FC2 + sigmoid for this CTA's channels: thread = (board, channel) ----
-                    if (te < 2 * NC) {
-                        const int b = te / NC, c = te % NC;
+                    if (tid < NB * NC) {
+                        const int b = tid / NC, c = tid % NC;
                         float g = L.se_b2[c0 + c];
 #pragma unroll 4
                         for (int q = 0; q < 16; q++) {
@@ -435,30 +525,54 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs
                     lat_epi_sync();
                     n_se++;
                 }
+                if (prof) pe_se += clock64() - tq0;
                 // ---- out = relu(gate * bf16(y) + x), in place over the block input ----
-                const float *gate = s_gate + board * NC;
+                if (active) {
+                    const float *gate = s_gate + board * NC;
 #pragma unroll
-                for (int i = 0; i < NC / 8; i++) {
-                    const uint32_t xw[4] = {xres[i].x, xres[i].y, xres[i].z, xres[i].w};
-                    uint32_t pw[4];
+                    for (int i = 0; i < NC / 8; i++) {
+                        const uint32_t xw[4] = {xres[i].x, xres[i].y, xres[i].z, xres[i].w};
+                        uint32_t pw[4];
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const int c = 8 * i + 2 * k;
-                        const float yb0 = __bfloat162float(__float2bfloat16_rn(a[c]));
-                        const float yb1 = __bfloat162float(__float2bfloat16_rn(a[c + 1]));
-                        const float g0 = L.se == 1 ? gate[c] : 1.f, g1 = L.se == 1 ? gate[c + 1] : 1.f;
-                        const float o0 = fmaxf(fmaf(g0, yb0, __uint_as_float(xw[k] << 16)), 0.f);
-                        const float o1 = fmaxf(fmaf(g1, yb1, __uint_as_float(xw[k] & 0xffff0000u)), 0.f);
-                        __nv_bfloat162 h = __floats2bfloat162_rn(o0, o1);
-                        pw[k] = *reinterpret_cast<uint32_t *>(&h);
+                        for (int k = 0; k < 4; k++) {
+                            const int c = 8 * i + 2 * k;
+                            const float yb0 = __bfloat162float(__float2bfloat16_rn(a[c]));
+                            const float yb1 = __bfloat162float(__float2bfloat16_rn(a[c + 1]));
+                            const float g0 = L.se == 1 ? gate[c] : 1.f, g1 = L.se == 1 ? gate[c + 1] : 1.f;
+                            const float o0 = fmaxf(fmaf(g0, yb0, __uint_as_float(xw[k] << 16)), 0.f);
+                            const float o1 = fmaxf(fmaf(g1, yb1, __uint_as_float(xw[k] & 0xffff0000u)), 0.f);
+                            __nv_bfloat162 h = __floats2bfloat162_rn(o0, o1);
+                            pw[k] = *reinterpret_cast<uint32_t *>(&h);
+                        }
+                        reinterpret_cast<uint4 *>(og)[i] = make_uint4(pw[0], pw[1], pw[2], pw[3]);
                     }
-                    reinterpret_cast<uint4 *>(og)[i] = make_uint4(pw[0], pw[1], pw[2], pw[3]);
                 }
             }
-            // ---- hand the layer's output to the TMA loads of the whole cluster ----
-            __threadfence();
+            // ---- hand the layer's output to the TMA loads of the whole cluster: every thread makes its stores visible
+            //      to the async proxy (this fence waits for them at GPU scope), block barrier, then ONE warp signals the
+            //      `ready` barrier of every CTA (release is cumulative over the barrier) ----
+            const long long tf0 = prof ? clock64() : 0;
             asm volatile("fence.proxy.async;" ::: "memory");
-            signal_all<CL>(bar_ready, lane);
+            const long long tf1 = prof ? clock64() : 0;
+            lat_epi_sync();
+            const long long tf2 = prof ? clock64() : 0;
+            if (quad == 0 && lane < CL) mbar_arrive_cluster(map_to_cta(bar_ready, (uint32_t)lane));
+            if (prof) {
+                pe_pfence += tf1 - tf0;
+                pe_sync += tf2 - tf1;
+                pe_gfence += clock64() - tf2;
+                pe_work += clock64() - tp1;
+            }
+        }
+        if (prof) {
+            args.prof[blockIdx.x * 16 + 6] = pe_tfull;
+            args.prof[blockIdx.x * 16 + 7] = pe_stat;
+            args.prof[blockIdx.x * 16 + 8] = pe_se;
+            args.prof[blockIdx.x * 16 + 9] = pe_work;
+            args.prof[blockIdx.x * 16 + 10] = pe_ld;
+            args.prof[blockIdx.x * 16 + 11] = pe_pfence;
+            args.prof[blockIdx.x * 16 + 12] = pe_sync;
+            args.prof[blockIdx.x * 16 + 13] = pe_gfence;
         }
     }
 
@@ -478,11 +592,13 @@ struct LatTower {
     LatLayer *d_layers[2] = {nullptr, nullptr};  // [0]: CL = 8, [1]: CL = 4
     int n_layers = 0;
     int max_tiles[2] = {0, 0};                   // co-resident clusters of 8 / 4 CTAs
+    bool one_board = true;                       // one-board tiles (M64) while there are clusters for them
 };
 
 template <int CL> static int lat_max_clusters(int *out)
 {
-    SCB_CUDA(cudaFuncSetAttribute(lat_tower_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, LatCfg<CL>::SMEM_BYTES));
+    SCB_CUDA(cudaFuncSetAttribute(lat_tower_kernel<CL, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, LatCfg<CL>::SMEM_BYTES));
+    SCB_CUDA(cudaFuncSetAttribute(lat_tower_kernel<CL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, LatCfg<CL>::SMEM_BYTES));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(CL * 64);
     cfg.blockDim = dim3(LAT_THREADS);
@@ -495,7 +611,7 @@ template <int CL> static int lat_max_clusters(int *out)
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int n = 0;
-    SCB_CUDA(cudaOccupancyMaxActiveClusters(&n, lat_tower_kernel<CL>, &cfg));
+    SCB_CUDA(cudaOccupancyMaxActiveClusters(&n, lat_tower_kernel<CL, 2>, &cfg));
     *out = n;
     return SC_OK;
 }
@@ -512,6 +628,13 @@ int lat_tower_create(LatTower **out, const LatLayerDesc *descs, int n, int board
             LatLayer &L = h[i];
             memset(&L, 0, sizeof(L));
             int rc = tc_make_act_map_hbw(d.in, boards_alloc, d.cin_pad, &L.map_a);
+            if (rc == SC_OK) {
+                // the same tensor {C, file, board, rank} with a box of ONE board: 80 rows ordered (rank, file)
+                cuuint64_t dims[4] = {(cuuint64_t)d.cin_pad, 8, (cuuint64_t)boards_alloc, 8};
+                cuuint64_t strides[3] = {(cuuint64_t)d.cin_pad * 2, (cuuint64_t)d.cin_pad * 128, (cuuint64_t)d.cin_pad * 16};
+                cuuint32_t box[4] = {TC_BK, 8, 1, 10};
+                rc = tc_encode_map(&L.map_a1, d.in, 4, dims, strides, box, "activations (rank, file), one board");
+            }
             if (rc == SC_OK) {
                 // weights [tap = dy * 3 + dx][256][cin_pad] as {cin, cout, dx, dy}
                 const int nd = d.taps == 9 ? 3 : 1;
@@ -563,6 +686,7 @@ int lat_tower_create(LatTower **out, const LatLayerDesc *descs, int n, int board
         if (want == 4) t->max_tiles[0] = 0;
         if (want == 8) t->max_tiles[1] = 0;
     }
+    t->one_board = !(getenv("SCB200_LAT_ONE_BOARD") && getenv("SCB200_LAT_ONE_BOARD")[0] == '0');  // A/B
     *out = t;
     return SC_OK;
 }
@@ -577,12 +701,18 @@ void lat_tower_destroy(LatTower *t)
 
 int lat_tower_max_boards(const LatTower *t) { return t ? 2 * (t->max_tiles[0] > t->max_tiles[1] ? t->max_tiles[0] : t->max_tiles[1]) : 0; }
 
-template <int CL> static int lat_launch(const LatTower *t, int v, int n_tiles, cudaStream_t st, int max_layers)
+template <int CL, int NB> static int lat_launch(const LatTower *t, int v, int n_tiles, cudaStream_t st, int max_layers)
 {
     LatArgs a;
     a.layers = t->d_layers[v];
     a.n_layers = max_layers > 0 && max_layers < t->n_layers ? max_layers : t->n_layers;
     a.n_tiles = n_tiles;
+    a.prof = nullptr;
+    static const bool want_prof = getenv("SCB200_PHASE_PROFILE") != nullptr;
+    if (want_prof) {
+        SCB_CUDA(cudaMalloc(&a.prof, (size_t)n_tiles * CL * 16 * sizeof(long long)));
+        SCB_CUDA(cudaMemsetAsync(a.prof, 0, (size_t)n_tiles * CL * 16 * sizeof(long long), st));
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(n_tiles * CL);
     cfg.blockDim = dim3(LAT_THREADS);
@@ -595,8 +725,24 @@ template <int CL> static int lat_launch(const LatTower *t, int v, int n_tiles, c
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    SCB_CUDA(cudaLaunchKernelEx(&cfg, lat_tower_kernel<CL>, a));
+    SCB_CUDA(cudaLaunchKernelEx(&cfg, lat_tower_kernel<CL, NB>, a));
     SCB_CUDA(cudaGetLastError());
+    if (want_prof) {
+        // debugging aid (synchronous): SM cycles per phase, summed over the layers, averaged over the CTAs
+        std::vector<long long> h((size_t)n_tiles * CL * 16);
+        SCB_CUDA(cudaStreamSynchronize(st));
+        SCB_CUDA(cudaMemcpy(h.data(), a.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(a.prof);
+        double acc[16] = {0};
+        for (int b = 0; b < n_tiles * CL; b++)
+            for (int k = 0; k < 16; k++) acc[k] += (double)h[(size_t)b * 16 + k] / (n_tiles * CL);
+        fprintf(stderr,
+                "[lat CL=%d NB=%d tiles=%d layers=%d] A-producer: wait_ready %.0f wait_empty %.0f | mma: total %.0f wait_A(first box) %.0f "
+                "wait_A(rest) %.0f wait_B %.0f | epilogue: wait_tmem_full %.0f work %.0f (tmem load %.0f, stat exchange %.0f, SE %.0f, "
+                "proxy fence %.0f, block barrier %.0f, gpu fence + signal %.0f)\n",
+                CL, NB, n_tiles, a.n_layers, acc[0], acc[1], acc[5], acc[2], acc[3], acc[4], acc[6], acc[9], acc[10], acc[7], acc[8],
+                acc[11], acc[12], acc[13]);
+    }
     return SC_OK;
 }
 
@@ -604,9 +750,12 @@ template <int CL> static int lat_launch(const LatTower *t, int v, int n_tiles, c
 int lat_tower_launch(LatTower *t, int n_boards, cudaStream_t st, int max_layers)
 {
     if (n_boards <= 0) return SC_OK;
+    // widest split first; one-board tiles (half the operand traffic per CTA) while every board can have a cluster
     const int n_tiles = (n_boards + 1) / 2;
-    if (n_tiles <= t->max_tiles[0]) return lat_launch<8>(t, 0, n_tiles, st, max_layers);
-    if (n_tiles <= t->max_tiles[1]) return lat_launch<4>(t, 1, n_tiles, st, max_layers);
+    if (t->one_board && n_boards <= t->max_tiles[0]) return lat_launch<8, 1>(t, 0, n_boards, st, max_layers);
+    if (n_tiles <= t->max_tiles[0]) return lat_launch<8, 2>(t, 0, n_tiles, st, max_layers);
+    if (t->one_board && n_boards <= t->max_tiles[1]) return lat_launch<4, 1>(t, 1, n_boards, st, max_layers);
+    if (n_tiles <= t->max_tiles[1]) return lat_launch<4, 2>(t, 1, n_tiles, st, max_layers);
     return SC_E_STATE;
 }
 

@@ -32,7 +32,7 @@ def leaves(co):
 def _eval_sizes(blob, pos, moves, off, sizes, env, monkeypatch):
     import scb200
 
-    for k in ("SCB200_LATENCY", "SCB200_LAT_CLUSTER"):
+    for k in ("SCB200_LATENCY", "SCB200_LAT_CLUSTER", "SCB200_LAT_ONE_BOARD"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
         monkeypatch.setenv(k, v)
@@ -52,7 +52,8 @@ def test_latency_kernel_bit_identical_to_throughput_kernel(net19, leaves, monkey
     games, (pos, moves, off, mv_all) = leaves
     sizes = (1, 2, 3, 7, 16, 33, 36, 37, 64, 74, 75, 96)      # both cluster sizes, odd tiles, and past the switch-over
     ref = _eval_sizes(net19[1], pos, moves, off, sizes, {"SCB200_LATENCY": "0"}, monkeypatch)
-    for env in ({}, {"SCB200_LAT_CLUSTER": "4"}, {"SCB200_LAT_CLUSTER": "8"}):
+    # default policy; clusters of 4 only; clusters of 8 only; two-board tiles only
+    for env in ({}, {"SCB200_LAT_CLUSTER": "4"}, {"SCB200_LAT_CLUSTER": "8"}, {"SCB200_LAT_ONE_BOARD": "0"}):
         got = _eval_sizes(net19[1], pos, moves, off, sizes, env, monkeypatch)
         for n in sizes:
             assert np.array_equal(got[n][1], ref[n][1]), (env, n, np.abs(got[n][1] - ref[n][1]).max())

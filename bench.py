@@ -529,6 +529,9 @@ def main():
                     "leaf_evals_per_s": sus["steps"] * B / sus["seconds"], "seconds": sus["seconds"], "steps": sus["steps"],
                     "avg_launch_ms": sus["conv_ms_total"] / sus["steps"] / conv_n}
             if args.mode == "fp32":
+                roof["kernel"] = ("tc_gemm_kernel<256, EPI_F32, pair>: 3x3 256->256 conv as a bf16x3 split GEMM (6 tcgen05 bf16 products "
+                                  "per fp32 product, fp32 accumulate in TMEM), one launch per layer; LayerNorm / SE in fp32 kernels")
+                roof["traffic"] = None
                 # FP32 parity mode: the same kernel runs the bf16x3 operand split (6 tensor-core products per fp32
                 # product), so its ceiling is the bf16 peak / 6; achieved counts fp32 FLOPs
                 roof["peak"] = peaks["tflops_burst"] / 6

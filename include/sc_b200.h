@@ -29,8 +29,10 @@ extern "C" {
 #define SC_E_NOGPU (-4)   /* no sm_100 device: there is NO CPU fallback */
 #define SC_E_STATE (-5)
 
-#define SC_MODE_FP32 0 /* parity mode: FP32 FFMA tower (1e-4 gate)                    */
+#define SC_MODE_FP32 0 /* parity mode (1e-4 gate): fp32 arithmetic; the 256-wide convolutions run on the tensor
+                          cores as bf16x3 split operands (6 bf16 products per fp32 product) with fp32 accumulate  */
 #define SC_MODE_BF16 1 /* throughput mode: tcgen05 bf16 operands, fp32 accumulate      */
+#define SC_MODE_FP32_FFMA 2 /* FP32 on the CUDA cores only (FFMA): the referee of the parity mode                */
 
 #define SC_LOOKBACK 8       /* src/chess.rs:23 */
 #define SC_N_PLANES 112     /* 8 x 14, py/module.py:118-121 */

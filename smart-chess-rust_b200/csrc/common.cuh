@@ -64,10 +64,12 @@ int launch_policy_logp_full(const float *logits, int n, float *d_logp /*[n][4672
 // C[M][N] = gather_taps(A)[M][TAPS*K] * W[TAPS*K][ldw] + bias ; A is [rows][lda] fp32
 int launch_gemm_f32(int taps, const float *A, int lda, const float *W, int ldw, const float *bias, float *out,
                     int ldo, int M, int N, int K, cudaStream_t st);
+// planes (optional): the result also as three bf16 planes [rows][3 * C] (hi | mid | lo), the operand format of the
+// tensor-core FP32 parity mode
 int launch_ln_f32(float *x, int rows, int C, int ld, const float *gamma, const float *beta, int relu,
-                  cudaStream_t st);
+                  cudaStream_t st, __nv_bfloat16 *planes = nullptr);
 int launch_se_res_f32(const float *y, const float *x, float *out, int n, const float *w1t, const float *b1,
-                      const float *w2t, const float *b2, cudaStream_t st);
+                      const float *w2t, const float *b2, cudaStream_t st, __nv_bfloat16 *planes = nullptr);
 int launch_value_finish(const float *hidden_pre, int n_split, int n, const float *meta, const float *w_meta,
                         const float *b1, const float *w2, const float *b2, float *value_out, cudaStream_t st);
 
@@ -78,6 +80,9 @@ enum { TC_EPI_LN = 0, TC_EPI_LN_SE = 1, TC_EPI_LN73 = 2, TC_EPI_RAW = 3 };
 // 80 (policy 256->73, rows 73..79 zero) or 128 (value FC, taps = 1, k_per_tap = 16384)
 int tc_conv_create(TcConv **out, const __nv_bfloat16 *w, int taps, int k_per_tap, int bn, int epi, const float *bias,
                    const float *gamma, const float *beta);
+// FP32 parity mode: conv to 256 channels as a bf16x3 split GEMM on the tensor cores, fp32 [boards * 64][256] out (+ bias).
+// w3 = bf16 [taps][256][3 * cin_pad] (three planes side by side along K), activations bf16 [boards][64][a_planes * cin_pad]
+int tc_split_conv_create(TcConv **out, const __nv_bfloat16 *w3, int taps, int cin_pad, int a_planes, const float *bias);
 // squeeze-excitation weights for TC_EPI_LN_SE: fc1 packed [32][128][8] bf16, fc2 packed [16][256][8] bf16
 void tc_conv_set_se(TcConv *c, const void *w1p, const float *b1, const void *w2p, const float *b2);
 void tc_conv_destroy(TcConv *c);

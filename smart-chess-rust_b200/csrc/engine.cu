@@ -111,6 +111,11 @@ using namespace scb;
 
 struct sc_engine {
     int device = 0, mode = 0, max_batch = 0, n_blocks = 0, num_sms = 148;
+    int mode_requested = 0;
+    // FP32 parity mode: the 256-wide convolutions as bf16x3 split GEMMs on the tensor cores (fp32 accumulate), LayerNorm /
+    // SE / the narrow head layers in fp32 on the CUDA cores.  SC_MODE_FP32_FFMA (or SCB200_FP32_TC=0) = everything FFMA.
+    bool fp32_tc = false;
+    __nv_bfloat16 *p_x = nullptr, *p_t = nullptr;  // fp32_tc: activations as three bf16 planes [boards][64][768]
     int alloc_boards = 0;
     cudaStream_t stream = nullptr;
     std::vector<void *> allocs;
@@ -167,6 +172,11 @@ struct sc_engine {
     } io[2];
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     int64_t n_submits = 0;
+    // small batches (sc_eval with n <= SC_SMALL_N): inputs are packed into ONE pinned staging buffer and travel in one
+    // copy, values + priors come back in one copy (a caller's Vec / numpy array is pageable memory, which would
+    // otherwise make every one of the five copies a staged, blocking one)
+    uint8_t *h_small_in = nullptr, *d_small_in = nullptr;
+    float *h_small_out = nullptr, *d_small_out = nullptr;
     std::vector<cudaEvent_t> kev;  // level-2 timing: event pairs around the 3x3 256->256 convs
     int kev_used = 0;
     float last_conv_avg_ms = 0.f;
@@ -174,6 +184,8 @@ struct sc_engine {
 };
 
 namespace scb {
+
+constexpr int SC_SMALL_N = 128;
 
 template <typename T> static int dev_alloc(sc_engine *e, T **p, size_t count)
 {
@@ -233,12 +245,36 @@ static int load_conv(sc_engine *e, const Blob &b, const std::string &wname, cons
     SCB_CHECK(upload_vec(e, b, lnname + ".weight", cout, &c.gamma));
     SCB_CHECK(upload_vec(e, b, lnname + ".bias", cout, &c.beta));
     if (e->mode == SC_MODE_FP32) {
-        std::vector<float> h((size_t)taps * cin * c.ldw, 0.f);
-        for (int co = 0; co < cout; co++)
-            for (int ci = 0; ci < cin; ci++)
-                for (int t = 0; t < taps; t++)
-                    h[((size_t)t * cin + ci) * c.ldw + co] = w->data[((size_t)co * cin + ci) * taps + t];
-        SCB_CHECK(upload(e, &c.w_f32, h));
+        if (!(e->fp32_tc && cout == C_TOWER)) {
+            std::vector<float> h((size_t)taps * cin * c.ldw, 0.f);
+            for (int co = 0; co < cout; co++)
+                for (int ci = 0; ci < cin; ci++)
+                    for (int t = 0; t < taps; t++)
+                        h[((size_t)t * cin + ci) * c.ldw + co] = w->data[((size_t)co * cin + ci) * taps + t];
+            SCB_CHECK(upload(e, &c.w_f32, h));
+        } else {
+            // tensor-core parity mode: the weights' three bf16 planes side by side along K, [tap][cout][3 * cin_pad]
+            const int kp = c.cin_pad;
+            std::vector<uint16_t> h((size_t)taps * cout * 3 * kp, 0);
+            for (int co = 0; co < cout; co++)
+                for (int ci = 0; ci < cin; ci++)
+                    for (int t = 0; t < taps; t++) {
+                        float x = w->data[((size_t)co * cin + ci) * taps + t];
+                        uint16_t *row = &h[((size_t)t * cout + co) * 3 * kp];
+                        for (int pl = 0; pl < 3; pl++) {
+                            const uint16_t b = f2bf(x);
+                            row[pl * kp + ci] = b;
+                            uint32_t u = (uint32_t)b << 16;
+                            float back;
+                            memcpy(&back, &u, 4);
+                            x -= back;
+                        }
+                    }
+            uint16_t *d = nullptr;
+            SCB_CHECK(upload(e, &d, h));
+            c.w_bf16 = reinterpret_cast<__nv_bfloat16 *>(d);
+            SCB_CHECK(tc_split_conv_create(&c.tc, c.w_bf16, taps, kp, cin == C_IN ? 1 : 3, c.bias));
+        }
     } else {
         // B operand, K-major: [tap][bn rows][cin_pad]; bn = 256, or 80 for the 73-wide policy conv
         const int bn = cout == C_TOWER ? C_TOWER : LD_POLICY;
@@ -380,7 +416,12 @@ static int alloc_buffers(sc_engine *e)
     const size_t act = (size_t)B * 64 * C_TOWER;
     if (e->mode == SC_MODE_FP32) {
         e->vsplit = 1;
-        SCB_CHECK(dev_alloc(e, &e->f_planes, (size_t)B * 64 * C_IN));
+        if (e->fp32_tc) {
+            SCB_CHECK(dev_alloc(e, &e->h_planes, (size_t)B * 64 * C_IN_PAD));
+            SCB_CHECK(dev_alloc(e, &e->p_x, act * 3));
+            SCB_CHECK(dev_alloc(e, &e->p_t, act * 3));
+        } else
+            SCB_CHECK(dev_alloc(e, &e->f_planes, (size_t)B * 64 * C_IN));
         SCB_CHECK(dev_alloc(e, &e->f_x, act));
         SCB_CHECK(dev_alloc(e, &e->f_t, act));
         SCB_CHECK(dev_alloc(e, &e->f_y, act));
@@ -392,6 +433,14 @@ static int alloc_buffers(sc_engine *e)
         SCB_CHECK(dev_alloc(e, &e->h_y, act));
     }
     SCB_CHECK(dev_alloc(e, &e->vpre, (size_t)e->vsplit * B * N_VALUE_HIDDEN));
+    {
+        const size_t in_bytes = (size_t)SC_SMALL_N * (sizeof(sc_position) + 4 + SC_MAX_MOVES * sizeof(sc_move)) + 64;
+        const size_t out_floats = (size_t)SC_SMALL_N * (1 + SC_MAX_MOVES);
+        SCB_CHECK(dev_alloc(e, &e->d_small_in, in_bytes));
+        SCB_CHECK(dev_alloc(e, &e->d_small_out, out_floats));
+        SCB_CUDA(cudaMallocHost(&e->h_small_in, in_bytes));
+        SCB_CUDA(cudaMallocHost(&e->h_small_out, out_floats * sizeof(float)));
+    }
     // scratch for the gates: max(int8 planes + meta, fp32 NCHW planes + logp)
     e->scratch_bytes = (size_t)B * ((size_t)SC_N_PLANES * 64 * 4 + (size_t)SC_N_POLICY * 4 + 64);
     SCB_CHECK(dev_alloc(e, reinterpret_cast<char **>(&e->d_scratch), e->scratch_bytes));
@@ -419,7 +468,37 @@ static int run_network(sc_engine *e, int n, cudaStream_t st, const TcGather *gat
     const int rows = n * 64;
     e->kev_used = 0;
     if (e->timing) SCB_CUDA(cudaEventRecord(e->ev[1], st));
-    if (e->mode == SC_MODE_FP32) {
+    if (e->mode == SC_MODE_FP32 && e->fp32_tc) {
+        const int nb = e->alloc_boards;
+        // 256-wide convolution: split GEMM on the tensor cores (fp32 out, + bias), then LayerNorm (+ReLU) in fp32;
+        // `planes` = also emit the result as bf16x3 operand planes for the next convolution
+        auto conv = [&](const ConvW &c, const __nv_bfloat16 *in, float *out, int relu, __nv_bfloat16 *planes, bool timed) -> int {
+            if (timed) SCB_CHECK(kev_mark(e, st));
+            SCB_CHECK(tc_conv_launch(c.tc, in, nb, n, out, nullptr, 0, 1, e->num_sms, st));
+            if (timed) SCB_CHECK(kev_mark(e, st));
+            SCB_CHECK(launch_ln_f32(out, rows, C_TOWER, C_TOWER, c.gamma, c.beta, relu, st, planes));
+            e->launches += 2;
+            return SC_OK;
+        };
+        SCB_CHECK(conv(e->stem, e->h_planes, e->f_x, 1, e->p_x, false));
+        for (int i = 0; i < e->n_blocks; i++) {
+            SCB_CHECK(conv(e->conv1[i], e->p_x, e->f_t, 1, e->p_t, true));
+            SCB_CHECK(conv(e->conv2[i], e->p_t, e->f_y, 0, nullptr, true));
+            SCB_CHECK(launch_se_res_f32(e->f_y, e->f_x, e->f_x, n, e->se[i].w1t, e->se[i].b1, e->se[i].w2t, e->se[i].b2, st,
+                                        e->p_x));
+            e->launches += 1;
+        }
+        e->timed_flops_per_leaf = 2.0 * 64 * 256 * 9.0 * 256 * 2 * e->n_blocks;
+        if (e->timing) SCB_CUDA(cudaEventRecord(e->ev[2], st));
+        SCB_CHECK(conv(e->pol1, e->p_x, e->f_t, 0, nullptr, false));
+        SCB_CHECK(launch_gemm_f32(1, e->f_t, C_TOWER, e->pol2.w_f32, e->pol2.ldw, e->pol2.bias, e->logits, LD_POLICY,
+                                  rows, C_POLICY, C_TOWER, st));
+        SCB_CHECK(launch_ln_f32(e->logits, rows, C_POLICY, LD_POLICY, e->pol2.gamma, e->pol2.beta, 0, st));
+        SCB_CHECK(conv(e->val1, e->p_x, e->f_y, 1, nullptr, false));
+        SCB_CHECK(launch_gemm_f32(1, e->f_y, 64 * C_TOWER, e->vfc_w_f32, N_VALUE_HIDDEN, nullptr, e->vpre,
+                                  N_VALUE_HIDDEN, n, N_VALUE_HIDDEN, 64 * C_TOWER, st));
+        e->launches += 3;
+    } else if (e->mode == SC_MODE_FP32) {
         auto conv = [&](const ConvW &c, const float *in, int lda, float *out, int relu) -> int {
             SCB_CHECK(launch_gemm_f32(c.taps, in, lda, c.w_f32, c.ldw, c.bias, out, C_TOWER, rows, c.cout, c.cin, st));
             SCB_CHECK(launch_ln_f32(out, rows, c.cout, C_TOWER, c.gamma, c.beta, relu, st));
@@ -519,7 +598,7 @@ static int run_network(sc_engine *e, int n, cudaStream_t st, const TcGather *gat
 static int encode_for_mode(sc_engine *e, const sc_position *d_pos, int n, cudaStream_t st)
 {
     e->launches += 1;
-    if (e->mode == SC_MODE_FP32) return launch_encode_f32(d_pos, n, e->f_planes, e->d_meta, st);
+    if (e->mode == SC_MODE_FP32 && !e->fp32_tc) return launch_encode_f32(d_pos, n, e->f_planes, e->d_meta, st);
     return launch_encode_bf16(d_pos, n, e->h_planes, e->d_meta, st);
 }
 
@@ -551,7 +630,8 @@ const char *sc_last_error(void) { return g_err.c_str(); }
 
 int sc_create(const char *weights_blob_path, int device, int mode, int max_batch, sc_engine **out)
 {
-    if (!out || !weights_blob_path || max_batch <= 0 || (mode != SC_MODE_FP32 && mode != SC_MODE_BF16)) {
+    if (!out || !weights_blob_path || max_batch <= 0 ||
+        (mode != SC_MODE_FP32 && mode != SC_MODE_BF16 && mode != SC_MODE_FP32_FFMA)) {
         set_error("sc_create: bad argument");
         return SC_E_INVAL;
     }
@@ -572,7 +652,9 @@ int sc_create(const char *weights_blob_path, int device, int mode, int max_batch
     SCB_CHECK(read_blob(weights_blob_path, blob));
     sc_engine *e = new sc_engine();
     e->device = device;
-    e->mode = mode;
+    e->mode_requested = mode;
+    e->mode = mode == SC_MODE_FP32_FFMA ? SC_MODE_FP32 : mode;
+    e->fp32_tc = mode == SC_MODE_FP32 && !(getenv("SCB200_FP32_TC") && getenv("SCB200_FP32_TC")[0] == '0');
     e->max_batch = max_batch;
     e->num_sms = prop.multiProcessorCount;
     int rc = SC_OK;
@@ -654,6 +736,8 @@ int sc_destroy(sc_engine *e)
     for (auto &c : e->conv1) kill(c);
     for (auto &c : e->conv2) kill(c);
     for (void *p : e->allocs) cudaFree(p);
+    if (e->h_small_in) cudaFreeHost(e->h_small_in);
+    if (e->h_small_out) cudaFreeHost(e->h_small_out);
     for (int i = 0; i < 4; i++)
         if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     for (cudaEvent_t ev : e->kev) cudaEventDestroy(ev);
@@ -676,7 +760,7 @@ int sc_info(const sc_engine *e, int *n_res_blocks, int *max_batch, int *mode)
     if (!e) return SC_E_INVAL;
     if (n_res_blocks) *n_res_blocks = e->n_blocks;
     if (max_batch) *max_batch = e->max_batch;
-    if (mode) *mode = e->mode;
+    if (mode) *mode = e->mode_requested;
     return SC_OK;
 }
 
@@ -735,6 +819,22 @@ int sc_eval(sc_engine *e, int n, const sc_position *pos, const sc_move *moves, c
     }
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
     SCB_CUDA(cudaSetDevice(e->device));
+    if (n <= SC_SMALL_N) {
+        // latency path: [positions | offsets | moves] in one copy, [values | priors] back in one copy
+        const size_t pos_b = sizeof(sc_position) * (size_t)n, off_b = sizeof(int32_t) * (size_t)(n + 1);
+        const size_t mv_b = sizeof(sc_move) * (size_t)total;
+        memcpy(e->h_small_in, pos, pos_b);
+        memcpy(e->h_small_in + pos_b, move_off, off_b);
+        memcpy(e->h_small_in + pos_b + off_b, moves, mv_b);
+        SCB_CUDA(cudaMemcpyAsync(e->d_small_in, e->h_small_in, pos_b + off_b + mv_b, cudaMemcpyHostToDevice, st));
+        SCB_CHECK(sc_eval_device(e, n, e->d_small_in, e->d_small_in + pos_b + off_b, e->d_small_in + pos_b, total,
+                                 e->d_small_out + n, e->d_small_out, st));
+        SCB_CUDA(cudaMemcpyAsync(e->h_small_out, e->d_small_out, sizeof(float) * (size_t)(n + total), cudaMemcpyDeviceToHost, st));
+        SCB_CUDA(cudaStreamSynchronize(st));
+        memcpy(value_out, e->h_small_out, sizeof(float) * (size_t)n);
+        memcpy(priors_out, e->h_small_out + n, sizeof(float) * (size_t)total);
+        return SC_OK;
+    }
     SCB_CUDA(cudaMemcpyAsync(e->d_pos, pos, sizeof(sc_position) * (size_t)n, cudaMemcpyHostToDevice, st));
     SCB_CUDA(cudaMemcpyAsync(e->d_off, move_off, sizeof(int32_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
     if (total) SCB_CUDA(cudaMemcpyAsync(e->d_moves, moves, sizeof(sc_move) * (size_t)total, cudaMemcpyHostToDevice, st));
@@ -1016,7 +1116,7 @@ int sc_forward_only(sc_engine *e, int n, const float *planes, const float *meta,
     // meta rows are padded to 8 floats on the device
     SCB_CUDA(cudaMemsetAsync(e->d_meta, 0, (size_t)n * 8 * 4, st));
     SCB_CUDA(cudaMemcpy2DAsync(e->d_meta, 8 * 4, meta, SC_N_META * 4, SC_N_META * 4, (size_t)n, cudaMemcpyHostToDevice, st));
-    if (e->mode == SC_MODE_FP32)
+    if (e->mode == SC_MODE_FP32 && !e->fp32_tc)
         SCB_CHECK(launch_nchw_to_nhwc_f32(d_nchw, n, e->f_planes, st));
     else
         SCB_CHECK(launch_nchw_to_nhwc_bf16(d_nchw, n, e->h_planes, st));

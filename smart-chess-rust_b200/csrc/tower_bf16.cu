@@ -68,7 +68,9 @@ constexpr int TC_THREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilo
 //   EPI_RAW    split-K partial sums of the value FC               -> fp32 [split][M][128]
 //   EPI_LN73_GATHER  EPI_LN73, but the 64 x 73 logits of a leaf stay in shared memory: log-softmax over the
 //              4672 entries, gather at the legal moves' indices, renormalise            -> priors
-enum { EPI_LN = 0, EPI_LN_SE = 1, EPI_LN73 = 2, EPI_RAW = 3, EPI_LN73_GATHER = 4 };
+//   EPI_F32    bias only, fp32 accumulator out                    -> fp32 [rows][256]   (FP32 parity mode: the GEMM
+//              runs the bf16x3 operand split, LayerNorm / SE follow in tower_f32.cu's fp32 kernels)
+enum { EPI_LN = 0, EPI_LN_SE = 1, EPI_LN73 = 2, EPI_RAW = 3, EPI_LN73_GATHER = 4, EPI_F32 = 5 };
 
 // One convolution layer of the whole-tower kernel (device array, written once at engine creation)
 struct alignas(64) TowerLayer {
@@ -95,6 +97,12 @@ struct TcArgs {
     int ln;                              // 0: the layer has no LayerNorm (y = acc + bias)
     int n_splits;                        // EPI_RAW: work items = n_tiles * n_splits
     int m_rows;                          // EPI_RAW: valid rows
+    // FP32 parity mode (bf16x3 split): an fp32 product a * b is the sum of bf16 products a_i * b_j of the operands'
+    // three bf16 planes (a = a_0 + a_1 + a_2, |a_k| ~ 2^-8k |a|); the planes are concatenated along the channel
+    // dimension of both tensors and the k loop walks `split_pairs` (A plane, B plane) pairs of `split_kreal` channel
+    // chunks each, smallest terms first, all into the same fp32 accumulator.  0 = plain bf16 GEMM.
+    int split_pairs, split_kreal;
+    uint8_t split_ap[8], split_bp[8];
     long long *prof;                     // optional [grid][16] phase cycle counters (SCB200_PHASE_PROFILE=1)
     const TowerLayer *layers;            // TOWER: all conv layers of the residual tower, run back to back
     int n_layers;
@@ -199,7 +207,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     using Cfg = TcCfg<BN, CTA2, YSMEM>;
     constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
     constexpr int NSTAGES = Cfg::STAGES;
-    static_assert(!CTA2 || (A4D && BN == 256 && (EPI == EPI_LN || EPI == EPI_LN_SE)), "pair mode: tower convs only");
+    static_assert(!CTA2 || (A4D && BN == 256 && (EPI == EPI_LN || EPI == EPI_LN_SE || EPI == EPI_F32)),
+                  "pair mode: tower convs only");
     const uint32_t cta_rank = CTA2 ? __shfl_sync(0xffffffffu, cluster_ctarank(), 0) : 0u;
     const int work0 = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int work_stride = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -283,7 +292,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int s = 0; s < TC_MAX_SLOTS; s++) mbar_init(ready_bar(s), 256);
         for (int s = 0; s < 2; s++) {
             mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), ((EPI == EPI_LN || EPI == EPI_LN_SE) ? 256 : 128) * (CTA2 ? 2 : 1));
+            mbar_init(tempty_bar(s), ((EPI == EPI_LN || EPI == EPI_LN_SE || EPI == EPI_F32) ? 256 : 128) * (CTA2 ? 2 : 1));
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -335,7 +344,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const int split = EPI == EPI_RAW ? work % args.n_splits : 0;
                 if constexpr (AREUSE) {
                     const int nd = P.taps == 9 ? 3 : 1;
-                    for (int kc = 0; kc < P.kchunks; kc++)
+                    for (int kc = 0; kc < P.kchunks; kc++) {
+                        // channel chunk of the A / B tensor this k step reads (the same one unless the operands are split)
+                        int ca = kc, cb = kc;
+                        if (!TOWER && args.split_pairs > 0) {
+                            const int pr = kc / args.split_kreal, kk = kc % args.split_kreal;
+                            ca = args.split_ap[pr] * args.split_kreal + kk;
+                            cb = args.split_bp[pr] * args.split_kreal + kk;
+                        }
                         for (int dxi = 0; dxi < nd; dxi++) {
                             const long long t0 = args.prof ? clock64() : 0;
                             mbar_wait(aempty_bar(astage), aphase ^ 1u);
@@ -344,7 +360,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                 // both CTAs load into their own shared memory and complete on the LEADER's barrier,
                                 // which the leader alone arms with the bytes of both
                                 if (cta_rank == 0) mbar_expect_tx(afull_bar(astage), 2 * A_BOX);
-                                tma2_load_4d(abox_addr(astage), P.ma, afull_bar(astage), kc * TC_BK, nd == 3 ? dxi - 1 : 0, tile * 2, -1);
+                                tma2_load_4d(abox_addr(astage), P.ma, afull_bar(astage), ca * TC_BK, nd == 3 ? dxi - 1 : 0, tile * 2, -1);
                             }
                             __syncwarp();
                             for (int dyi = 0; dyi < nd; dyi++) {
@@ -354,7 +370,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                 if (args.prof) pc_wait_empty += clock64() - t1;
                                 if (elect_one()) {
                                     if (cta_rank == 0) mbar_expect_tx(bfull_bar(bstage), 2 * B_TILE);
-                                    tma2_load_2d(btile_addr(bstage), P.mw, bfull_bar(bstage), kc * TC_BK,
+                                    tma2_load_2d(btile_addr(bstage), P.mw, bfull_bar(bstage), cb * TC_BK,
                                                  tap * BN + (int)cta_rank * (BN / 2));
                                 }
                                 __syncwarp();
@@ -368,6 +384,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                 aphase ^= 1u;
                             }
                         }
+                    }
                     continue;
                 }
                 for (int tap = 0; tap < P.taps; tap++) {
@@ -506,7 +523,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 args.prof[blockIdx.x * 16 + 4] = it;
             }
         }
-    } else if ((EPI == EPI_LN || EPI == EPI_LN_SE || EPI == EPI_LN73_GATHER) || warp < 6) {
+    } else if ((EPI == EPI_LN || EPI == EPI_LN_SE || EPI == EPI_LN73_GATHER || EPI == EPI_F32) || warp < 6) {
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
         // pair mode with the shared activation box: accumulator row = (rank, board, file); orow = its row in memory
@@ -557,7 +574,31 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256);
 
-            if constexpr (EPI == EPI_RAW) {
+            if constexpr (EPI == EPI_F32) {
+                // ---- bias only: the fp32 accumulator goes to memory (this warp: 128 columns of its 32 rows) ----
+                static_assert(EPI != EPI_F32 || AREUSE, "fp32 output: pair mode only");
+                uint32_t r[32];
+                const int c0 = chalf * 128;
+                uint8_t *stg = s_stage + (warp - 2) * 2048;
+                uint8_t *gtile = reinterpret_cast<uint8_t *>(static_cast<float *>(P.out) + (size_t)tile * TC_BM * BN + c0);
+#pragma unroll 1
+                for (int ch = 0; ch < 4; ch++) {
+                    tmem_ld32(taddr + (uint32_t)(c0 + ch * 32), r);
+#pragma unroll
+                    for (int hf = 0; hf < 2; hf++) {
+                        uint4 v[4];
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            float y[4];
+#pragma unroll
+                            for (int i = 0; i < 4; i++)
+                                y[i] = __fadd_rn(__uint_as_float(r[hf * 16 + 4 * q + i]), s_bias[c0 + ch * 32 + hf * 16 + 4 * q + i]);
+                            v[q] = make_uint4(__float_as_uint(y[0]), __float_as_uint(y[1]), __float_as_uint(y[2]), __float_as_uint(y[3]));
+                        }
+                        staged_store_64B_hbw(stg, lane, v, gtile + (ch * 32 + hf * 16) * 4, (size_t)BN * 4, quad);
+                    }
+                }
+            } else if constexpr (EPI == EPI_RAW) {
                 uint32_t r[32];
                 uint8_t *stg = s_stage + (warp - 2) * 2048;
                 const int wrow0 = tile * TC_BM + quad * 32;  // first global row of this warp
@@ -1043,6 +1084,8 @@ struct TcConv {
     CUtensorMap map_w_half;  // box {64, 128}: the half of the weight rows one CTA of a pair stages
     bool pair_ok = false;
     int taps, k_per_tap, bn, epi;
+    int split_pairs = 0, split_kreal = 0;  // FP32 parity mode: (A plane, B plane) pairs of the bf16x3 split
+    uint8_t split_ap[8] = {0}, split_bp[8] = {0};
     const float *bias, *gamma, *beta;
     const uint4 *se_w1p = nullptr, *se_w2p = nullptr;
     const float *se_b1 = nullptr, *se_b2 = nullptr;
@@ -1151,6 +1194,53 @@ int tc_conv_create(TcConv **out, const __nv_bfloat16 *w, int taps, int k_per_tap
         SCB_CHECK((set_smem_attr<N_VALUE_HIDDEN, EPI_RAW, false>()));
         attr_set = true;
     }
+    *out = c;
+    return SC_OK;
+}
+
+// FP32 parity mode: a 3x3 / 1x1 convolution to 256 channels as a bf16x3 split GEMM with fp32 output (EPI_F32).
+// w3: bf16 [taps][256][3 * cin_pad], the weights' three bf16 planes side by side along K; the activations come as
+// bf16 [boards][64][a_planes * cin_pad] (a_planes = 3, or 1 for inputs that are exact in bf16: the 0/1 input planes).
+// Terms kept: a_i * b_j with i + j <= 2 (error ~2^-24 relative, i.e. fp32 level), smallest first.
+int tc_split_conv_create(TcConv **out, const __nv_bfloat16 *w3, int taps, int cin_pad, int a_planes, const float *bias)
+{
+    if (a_planes != 1 && a_planes != 3) {
+        set_error("tc_split_conv_create: a_planes must be 1 or 3");
+        return SC_E_INVAL;
+    }
+    TcConv *c = new TcConv();
+    c->taps = taps;
+    c->k_per_tap = a_planes * cin_pad;  // channels of the activation tensor
+    c->bn = 256;
+    c->epi = EPI_F32;
+    c->bias = bias;
+    c->gamma = nullptr;
+    c->beta = nullptr;
+    cuuint64_t dims[2] = {(cuuint64_t)3 * cin_pad, (cuuint64_t)taps * 256};
+    cuuint64_t strides[1] = {(cuuint64_t)3 * cin_pad * 2};
+    cuuint32_t box2[2] = {TC_BK, 128};
+    int rc = tc_encode_map(&c->map_w_half, w3, 2, dims, strides, box2, "split weights (pair half)");
+    if (rc != SC_OK) {
+        delete c;
+        return rc;
+    }
+    c->pair_ok = true;
+    c->split_kreal = cin_pad / TC_BK;
+    if (a_planes == 3) {
+        static const uint8_t ap[6] = {0, 1, 2, 0, 1, 0}, bp[6] = {2, 1, 0, 1, 0, 0};
+        c->split_pairs = 6;
+        memcpy(c->split_ap, ap, 6);
+        memcpy(c->split_bp, bp, 6);
+    } else {
+        static const uint8_t bp[3] = {2, 1, 0};
+        c->split_pairs = 3;
+        memcpy(c->split_bp, bp, 3);
+    }
+    int dev = 0;
+    SCB_CUDA(cudaGetDevice(&dev));
+    (void)dev;
+    SCB_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<256, EPI_F32, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  TcCfg<256, true>::SMEM_BYTES));
     *out = c;
     return SC_OK;
 }
@@ -1355,6 +1445,13 @@ int tc_conv_launch(TcConv *c, const __nv_bfloat16 *in, int rows_alloc, int n_uni
         a.n_tiles = (n_units + 1) / 2;  // units = boards, two per tile
         a.taps = c->taps;
         a.kchunks = c->k_per_tap / TC_BK;
+        if (c->split_pairs > 0) {
+            a.split_pairs = c->split_pairs;
+            a.split_kreal = c->split_kreal;
+            memcpy(a.split_ap, c->split_ap, 8);
+            memcpy(a.split_bp, c->split_bp, 8);
+            a.kchunks = c->split_pairs * c->split_kreal;
+        }
     } else {
         a.n_tiles = (n_units + TC_BM - 1) / TC_BM;  // units = rows
         a.taps = 1;
@@ -1378,6 +1475,10 @@ int tc_conv_launch(TcConv *c, const __nv_bfloat16 *in, int rows_alloc, int n_uni
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
+        if (c->epi == EPI_F32) {
+            SCB_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<256, EPI_F32, true, true>, *ma, c->map_w_half, a));
+            goto launched;
+        }
         if (c->epi == EPI_LN)
             SCB_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<256, EPI_LN, true, true>, *ma, c->map_w_half, a));
         else {

@@ -18,6 +18,19 @@ namespace scb {
 // ---------------------------------------------------------------------------------------
 constexpr int GBM = 128, GBN = 128, GBK = 16;
 
+// x = hi + mid + lo with three bf16 (8 significant bits each, successive round-to-nearest residuals): the operand
+// planes of the tensor-core FP32 parity mode (tower_bf16.cu, EPI_F32)
+__device__ __forceinline__ void split3_store(float x, __nv_bfloat16 *row, int c, int C)
+{
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    float r = x - __bfloat162float(h);
+    const __nv_bfloat16 m = __float2bfloat16_rn(r);
+    r -= __bfloat162float(m);
+    row[c] = h;
+    row[C + c] = m;
+    row[2 * C + c] = __float2bfloat16_rn(r);
+}
+
 template <int TAPS>
 __global__ void __launch_bounds__(256) gemm_f32_kernel(const float *__restrict__ A, int lda,
                                                        const float *__restrict__ W, int ldw,
@@ -120,7 +133,8 @@ int launch_gemm_f32(int taps, const float *A, int lda, const float *W, int ldw, 
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ln_f32_kernel(float *__restrict__ x, int rows, int C, int ld,
                                                      const float *__restrict__ gamma,
-                                                     const float *__restrict__ beta, int relu)
+                                                     const float *__restrict__ beta, int relu,
+                                                     __nv_bfloat16 *__restrict__ planes)
 {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -151,20 +165,22 @@ __global__ void __launch_bounds__(256) ln_f32_kernel(float *__restrict__ x, int 
         int c = lane + 32 * i;
         if (c < C) {
             float y = (v[i] - mean) * rstd * gamma[c] + beta[c];
-            p[c] = relu ? fmaxf(y, 0.f) : y;
+            y = relu ? fmaxf(y, 0.f) : y;
+            p[c] = y;
+            if (planes) split3_store(y, planes + (size_t)row * 3 * C, c, C);
         }
     }
 }
 
 int launch_ln_f32(float *x, int rows, int C, int ld, const float *gamma, const float *beta, int relu,
-                  cudaStream_t st)
+                  cudaStream_t st, __nv_bfloat16 *planes)
 {
     if (rows <= 0) return SC_OK;
     if (C > 256) {
         set_error("ln_f32: C > 256");
         return SC_E_INVAL;
     }
-    ln_f32_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, rows, C, ld, gamma, beta, relu);
+    ln_f32_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, rows, C, ld, gamma, beta, relu, planes);
     SCB_CUDA(cudaGetLastError());
     return SC_OK;
 }
@@ -180,7 +196,8 @@ __global__ void __launch_bounds__(256) se_res_f32_kernel(const float *__restrict
                                                          float *__restrict__ out, const float *__restrict__ w1t,
                                                          const float *__restrict__ b1,
                                                          const float *__restrict__ w2t,
-                                                         const float *__restrict__ b2)
+                                                         const float *__restrict__ b2,
+                                                         __nv_bfloat16 *__restrict__ planes)
 {
     __shared__ float s_mean[C_TOWER];
     __shared__ float s_hid[C_SE];
@@ -201,14 +218,18 @@ __global__ void __launch_bounds__(256) se_res_f32_kernel(const float *__restrict
     g = 1.f / (1.f + expf(-g));
     const float *xb = x + (size_t)b * 64 * C_TOWER;
     float *ob = out + (size_t)b * 64 * C_TOWER;
-    for (int s = 0; s < 64; s++) ob[s * C_TOWER + c] = fmaxf(fmaf(g, yb[s * C_TOWER + c], xb[s * C_TOWER + c]), 0.f);
+    for (int s = 0; s < 64; s++) {
+        const float o = fmaxf(fmaf(g, yb[s * C_TOWER + c], xb[s * C_TOWER + c]), 0.f);
+        ob[s * C_TOWER + c] = o;
+        if (planes) split3_store(o, planes + ((size_t)b * 64 + s) * 3 * C_TOWER, c, C_TOWER);
+    }
 }
 
 int launch_se_res_f32(const float *y, const float *x, float *out, int n, const float *w1t, const float *b1,
-                      const float *w2t, const float *b2, cudaStream_t st)
+                      const float *w2t, const float *b2, cudaStream_t st, __nv_bfloat16 *planes)
 {
     if (n <= 0) return SC_OK;
-    se_res_f32_kernel<<<n, 256, 0, st>>>(y, x, out, w1t, b1, w2t, b2);
+    se_res_f32_kernel<<<n, 256, 0, st>>>(y, x, out, w1t, b1, w2t, b2, planes);
     SCB_CUDA(cudaGetLastError());
     return SC_OK;
 }

@@ -16,6 +16,7 @@ from .binding import (  # noqa: F401
     SCError,
     SC_MODE_BF16,
     SC_MODE_FP32,
+    SC_MODE_FP32_FFMA,
     POSITION_DTYPE,
     MOVE_DTYPE,
     lib_path,

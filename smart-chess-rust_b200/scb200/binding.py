@@ -8,6 +8,7 @@ import numpy as np
 
 SC_MODE_FP32 = 0
 SC_MODE_BF16 = 1
+SC_MODE_FP32_FFMA = 2
 SC_N_PLANES = 112
 SC_N_META = 7
 SC_N_POLICY = 4672

@@ -295,6 +295,8 @@ def main():
                     help="also time the leader-board mode (BASELINE configs[4]: two random-init nets, rollout 100, "
                          "temperature-switch 8, both colour assignments) for this many seconds per rank (0 = skip)")
     ap.add_argument("--threads", type=int, default=0, help="host worker threads for self-play (0 = cores / ranks)")
+    ap.add_argument("--one-leaf-plies", type=int, default=40,
+                    help="plies of one game through the one-leaf interface (BASELINE configs[0] settings) to time (0 = skip)")
     ap.add_argument("--sustain", type=float, default=5.0,
                     help="seconds of back-to-back steps for the sustained roofline leg and the clock samples (0 = skip)")
     args = ap.parse_args()
@@ -355,6 +357,31 @@ def main():
 
     def dev_step():
         eng.eval_device(B, d_pos, d_moves, d_off, n_moves, d_pri, d_val, sh)
+
+    # ---- small-batch latency of the host-buffer call (what the one-leaf `Game::predict` shim sees, src/backends/torch.rs:115-125)
+    #      and BASELINE configs[0] through the one-leaf interface.  Measured BEFORE the throughput legs: a single game does
+    #      not run next to a saturated, power-capped GPU, and the SM clock takes seconds to come back after such a leg.
+    latency, one_leaf = {}, None
+    if rank == 0:
+        pos_np = h_pos.numpy().view(scb200.POSITION_DTYPE)
+        for nb in (1, 2, 8, 16, 64, 128):
+            if nb > B:
+                continue
+            for it in range(10 + 50):
+                if it == 10:
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                eng.eval(pos_np[:nb], h_moves[: int(h_off[nb])], h_off[: nb + 1], h_pri, h_val, sh)
+            latency["n%d_ms" % nb] = (time.perf_counter() - t0) / 50 * 1e3
+        if args.one_leaf_plies > 0:
+            t0 = time.perf_counter()
+            tr = scb200.game_selfplay(eng, rollout_num=20, num_steps=args.one_leaf_plies, cpuct=2.5, with_noise=False,
+                                      temperature_switch=0, temperature=0.0)
+            el = time.perf_counter() - t0
+            one_leaf = {"plies_per_s": len(tr["steps"]) / el, "plies": len(tr["steps"]), "seconds": el,
+                        "config": "BASELINE configs[0] through the reference's one-leaf interface (sc_game_selfplay: predict at "
+                                  "every level of every descent, one sc_eval(n=1) per predict): rollout-num 20, cpuct 2.5, "
+                                  "first %d plies, %s" % (args.one_leaf_plies, args.mode)}
 
     # ---- device-resident leg (value) --------------------------------------------------------
     with torch.cuda.stream(stream):
@@ -417,20 +444,6 @@ def main():
         eng.eval(h_pos.numpy().view(scb200.POSITION_DTYPE), h_moves, h_off, h_pri, h_val, sh)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-
-    # ---- small-batch latency of the same call (what the one-leaf `Game::predict` shim sees) -----------
-    latency = {}
-    if rank == 0:
-        pos_np = h_pos.numpy().view(scb200.POSITION_DTYPE)
-        for nb in (1, 8, 64):
-            if nb > B:
-                continue
-            for it in range(3 + 30):
-                if it == 3:
-                    torch.cuda.synchronize()
-                    t0 = time.perf_counter()
-                eng.eval(pos_np[:nb], h_moves[: int(h_off[nb])], h_off[: nb + 1], h_pri, h_val, sh)
-            latency["n%d_ms" % nb] = (time.perf_counter() - t0) / 30 * 1e3
 
     # ---- batched self-play at 180 rollouts (BASELINE configs[2]: 2048 concurrent trees) ---------------
     sp_stats = None
@@ -556,7 +569,7 @@ def main():
             "vs_baseline": None, "dtype": args.mode, "data": "synthetic", "config": workload_config(B),
             "e2e": {"value": e2e, "unit": "leaf evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-            "wall_s_timed_region": t_wall, "call_latency": latency,
+            "wall_s_timed_region": t_wall, "call_latency": latency, "one_leaf_game": one_leaf,
         }
         if sp_stats:
             line["selfplay"] = {

@@ -98,11 +98,28 @@ def main():
     out["value2"] = v.numpy().reshape(-1)
     digest2 = net.state_dict_digest(sd2)
 
+    # NormTable / use_se variants (module.py:6-9, 28-36): 2-block nets, weights from oracle.net.init_variant_state_dict
+    # loaded INTO the reference module (strict: keys and shapes are the reference's), outputs from the reference forward
+    variants = {}
+    for tag, norm, use_se, seed in (("bn_se", "BatchNorm", True, 21), ("ln_nose", "LayerNorm", False, 22),
+                                    ("bn_nose", "BatchNorm", False, 23)):
+        refv = module.ChessModule(n_res_blocks=2, use_se=use_se, norm=norm).eval()
+        sdv = net.init_variant_state_dict(2, seed, norm, use_se)
+        refv.load_state_dict(sdv, strict=True)
+        with torch.no_grad():
+            lp, v = refv(x, meta)
+        lpo, vo = net.forward(sdv, x, meta)
+        assert torch.equal(lp, lpo) and torch.equal(v, vo), tag
+        out["logp_" + tag] = lp.numpy()
+        out["value_" + tag] = v.numpy().reshape(-1)
+        variants[tag] = {"norm": norm, "use_se": use_se, "seed": seed, "n_res_blocks": 2,
+                         "digest": net.state_dict_digest({k: t for k, t in sdv.items() if t.ndim > 0})}
+
     dst = os.path.join(HERE, "..", "tests", "golden", "net_golden.npz")
     np.savez_compressed(dst, **out)
     with open(os.path.join(HERE, "..", "tests", "golden", "net_golden.json"), "w") as f:
         json.dump({"torch": torch.__version__, "digest19": digest19, "digest2": digest2,
-                   "net2": {"n_res_blocks": 2, "seed": 7, "perturb_seed": 1234}}, f, indent=1)
+                   "net2": {"n_res_blocks": 2, "seed": 7, "perturb_seed": 1234}, "variants": variants}, f, indent=1)
     print("ok", os.path.getsize(dst), digest19, digest2)
 
 

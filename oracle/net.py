@@ -107,6 +107,62 @@ def perturb_norm_params(sd, seed: int = 1234, scale: float = 0.25):
     return out
 
 
+def init_variant_state_dict(n_res_blocks: int, seed: int, norm: str = "LayerNorm", use_se: bool = True):
+    """Weights of `ChessModule(n_res_blocks, use_se=use_se, norm=norm)` (module.py:109-133): with norm="BatchNorm" the
+    convolutions carry no bias (module.py:18, 69, 88, 117) and every norm layer has running statistics; with
+    use_se=False the blocks have no SqueezeExcitation (module.py:28-36).  Keys and shapes are the reference module's
+    (`oracle/make_golden_net.py` loads the result INTO it with strict=True); the values are a seeded draw of this
+    function's own (norm parameters and running statistics non-trivial), not the reference's initialisation order."""
+    g = torch.Generator().manual_seed(seed)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    bn = norm == "BatchNorm"
+
+    def conv(name, cin, cout, k):
+        bound = 1.0 / math.sqrt(cin * k * k)
+        sd[name + ".weight"] = (2 * torch.rand((cout, cin, k, k), generator=g) - 1) * bound
+        if not bn:
+            sd[name + ".bias"] = (2 * torch.rand((cout,), generator=g) - 1) * bound
+
+    def nrm(name, c):
+        sd[name + ".weight"] = 1.0 + 0.25 * (2 * torch.rand((c,), generator=g) - 1)
+        sd[name + ".bias"] = 0.25 * (2 * torch.rand((c,), generator=g) - 1)
+        if bn:
+            sd[name + ".running_mean"] = 0.1 * (2 * torch.rand((c,), generator=g) - 1)
+            sd[name + ".running_var"] = 0.05 + 0.2 * torch.rand((c,), generator=g)
+            sd[name + ".num_batches_tracked"] = torch.tensor(100)
+
+    def lin(name, din, dout):
+        bound = 1.0 / math.sqrt(din)
+        sd[name + ".weight"] = (2 * torch.rand((dout, din), generator=g) - 1) * bound
+        sd[name + ".bias"] = (2 * torch.rand((dout,), generator=g) - 1) * bound
+
+    def se_conv(name, cin, cout):      # SqueezeExcitation's 1x1 convs always have a bias (torchvision)
+        bound = 1.0 / math.sqrt(cin)
+        sd[name + ".weight"] = (2 * torch.rand((cout, cin, 1, 1), generator=g) - 1) * bound
+        sd[name + ".bias"] = (2 * torch.rand((cout,), generator=g) - 1) * bound
+
+    conv("conv_block.0", N_PLANES, C, 3)
+    nrm("conv_block.1", C)
+    for i in range(n_res_blocks):
+        p = f"res_blocks.{i}."
+        conv(p + "conv1", C, C, 3)
+        nrm(p + "bn1", C)
+        conv(p + "conv2", C, C, 3)
+        nrm(p + "bn2", C)
+        if use_se:
+            se_conv(p + "se.fc1", C, C // 2)
+            se_conv(p + "se.fc2", C // 2, C)
+    conv("value_head.conv.0", C, C, 1)
+    nrm("value_head.conv.1", C)
+    lin("value_head.ffn.0", 64 * C + N_META, 128)
+    lin("value_head.ffn.2", 128, 1)
+    conv("policy_head.model.0", C, C, 1)
+    nrm("policy_head.model.1", C)
+    conv("policy_head.model.2", C, 73, 1)
+    nrm("policy_head.model.3", 73)
+    return sd
+
+
 def n_res_blocks_of(sd) -> int:
     n = 0
     while f"res_blocks.{n}.conv1.weight" in sd:
@@ -137,7 +193,20 @@ def layer_norm_2d(x, w, b):
     return y.permute(0, 3, 1, 2)
 
 
+BN_EPS = 1e-5          # torch.nn.BatchNorm2d default
+
+
+def norm_2d(sd, name, x):
+    """NormTable (module.py:6-9): timm LayerNorm2d, or BatchNorm2d in eval mode (running statistics)."""
+    if name + ".running_mean" in sd:
+        return F.batch_norm(x, sd[name + ".running_mean"], sd[name + ".running_var"], sd[name + ".weight"],
+                            sd[name + ".bias"], training=False, eps=BN_EPS)
+    return layer_norm_2d(x, sd[name + ".weight"], sd[name + ".bias"])
+
+
 def squeeze_excite(sd, p, x):
+    if p + "fc1.weight" not in sd:      # use_se=False: torch.nn.Identity (module.py:35)
+        return x
     s = F.adaptive_avg_pool2d(x, 1)
     s = F.relu(F.conv2d(s, sd[p + "fc1.weight"], sd[p + "fc1.bias"]))
     s = torch.sigmoid(F.conv2d(s, sd[p + "fc2.weight"], sd[p + "fc2.bias"]))
@@ -146,17 +215,17 @@ def squeeze_excite(sd, p, x):
 
 def res_block(sd, p, x):
     """module.py:38-46."""
-    out = F.conv2d(x, sd[p + "conv1.weight"], sd[p + "conv1.bias"], padding=1)
-    out = F.relu(layer_norm_2d(out, sd[p + "bn1.weight"], sd[p + "bn1.bias"]))
-    out = F.conv2d(out, sd[p + "conv2.weight"], sd[p + "conv2.bias"], padding=1)
-    out = layer_norm_2d(out, sd[p + "bn2.weight"], sd[p + "bn2.bias"])
+    out = F.conv2d(x, sd[p + "conv1.weight"], sd.get(p + "conv1.bias"), padding=1)
+    out = F.relu(norm_2d(sd, p + "bn1", out))
+    out = F.conv2d(out, sd[p + "conv2.weight"], sd.get(p + "conv2.bias"), padding=1)
+    out = norm_2d(sd, p + "bn2", out)
     out = squeeze_excite(sd, p + "se.", out)
     return F.relu(out + x)
 
 
 def tower(sd, planes):
-    x = F.conv2d(planes, sd["conv_block.0.weight"], sd["conv_block.0.bias"], padding=1)
-    x = F.relu(layer_norm_2d(x, sd["conv_block.1.weight"], sd["conv_block.1.bias"]))
+    x = F.conv2d(planes, sd["conv_block.0.weight"], sd.get("conv_block.0.bias"), padding=1)
+    x = F.relu(norm_2d(sd, "conv_block.1", x))
     for i in range(n_res_blocks_of(sd)):
         x = res_block(sd, f"res_blocks.{i}.", x)
     return x
@@ -166,18 +235,18 @@ def policy_head(sd, latent):
     """module.py:70-80: conv1x1 -> LN(256) -> conv1x1(->73) -> LN(73) -> Flatten (NCHW:
     index = c*64 + h*8 + w) -> log_softmax over all 4672."""
     p = "policy_head.model."
-    x = F.conv2d(latent, sd[p + "0.weight"], sd[p + "0.bias"])
-    x = layer_norm_2d(x, sd[p + "1.weight"], sd[p + "1.bias"])
-    x = F.conv2d(x, sd[p + "2.weight"], sd[p + "2.bias"])
-    x = layer_norm_2d(x, sd[p + "3.weight"], sd[p + "3.bias"])
+    x = F.conv2d(latent, sd[p + "0.weight"], sd.get(p + "0.bias"))
+    x = norm_2d(sd, p + "1", x)
+    x = F.conv2d(x, sd[p + "2.weight"], sd.get(p + "2.bias"))
+    x = norm_2d(sd, p + "3", x)
     return F.log_softmax(x.flatten(1), dim=1)
 
 
 def value_head(sd, latent, meta):
     """module.py:89-106 and the white-perspective flip at module.py:147-149."""
     p = "value_head."
-    x = F.conv2d(latent, sd[p + "conv.0.weight"], sd[p + "conv.0.bias"])
-    x = F.relu(layer_norm_2d(x, sd[p + "conv.1.weight"], sd[p + "conv.1.bias"])).flatten(1)
+    x = F.conv2d(latent, sd[p + "conv.0.weight"], sd.get(p + "conv.0.bias"))
+    x = F.relu(norm_2d(sd, p + "conv.1", x)).flatten(1)
     x = torch.cat((x, meta), dim=1)
     x = F.relu(F.linear(x, sd[p + "ffn.0.weight"], sd[p + "ffn.0.bias"]))
     v = torch.tanh(F.linear(x, sd[p + "ffn.2.weight"], sd[p + "ffn.2.bias"]))

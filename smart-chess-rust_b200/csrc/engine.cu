@@ -30,6 +30,9 @@ struct Blob {
     std::vector<char> raw;
     std::map<std::string, Tensor> t;
     int n_blocks = 0;
+    // network variant (`NormTable`, `use_se`, py/module.py:6-9, 14-36), from the exporter's `__config__` tensor
+    bool norm_folded = false;  // BatchNorm folded into conv weights + bias: the layers have no normalisation
+    bool use_se = true;
 };
 
 static int read_blob(const char *path, Blob &b)
@@ -74,6 +77,13 @@ static int read_blob(const char *path, Blob &b)
         for (auto &e : ents) {
             if (e.off + e.numel * 4 > data_bytes) goto bad;
             b.t[e.name] = Tensor{e.dims, reinterpret_cast<const float *>(p + e.off), (size_t)e.numel};
+        }
+    }
+    {
+        auto it = b.t.find("__config__");
+        if (it != b.t.end() && it->second.numel >= 2) {
+            b.norm_folded = it->second.data[0] != 0.f;
+            b.use_se = it->second.data[1] != 0.f;
         }
     }
     return SC_OK;
@@ -242,8 +252,10 @@ static int load_conv(sc_engine *e, const Blob &b, const std::string &wname, cons
     c.cin_pad = (cin + 63) / 64 * 64;
     c.ldw = (cout + 127) / 128 * 128;
     SCB_CHECK(upload_vec(e, b, wname + ".bias", cout, &c.bias));
-    SCB_CHECK(upload_vec(e, b, lnname + ".weight", cout, &c.gamma));
-    SCB_CHECK(upload_vec(e, b, lnname + ".bias", cout, &c.beta));
+    if (!b.norm_folded) {  // folded BatchNorm: gamma == nullptr means "no normalisation" everywhere below
+        SCB_CHECK(upload_vec(e, b, lnname + ".weight", cout, &c.gamma));
+        SCB_CHECK(upload_vec(e, b, lnname + ".bias", cout, &c.beta));
+    }
     if (e->mode == SC_MODE_FP32) {
         if (!(e->fp32_tc && cout == C_TOWER)) {
             std::vector<float> h((size_t)taps * cin * c.ldw, 0.f);
@@ -302,6 +314,7 @@ static int load_weights(sc_engine *e, const Blob &b)
         std::string p = "res_blocks." + std::to_string(i) + ".";
         SCB_CHECK(load_conv(e, b, p + "conv1", p + "bn1", 9, C_TOWER, C_TOWER, e->conv1[i]));
         SCB_CHECK(load_conv(e, b, p + "conv2", p + "bn2", 9, C_TOWER, C_TOWER, e->conv2[i], TC_EPI_LN_SE));
+        if (!b.use_se) continue;  // residual-only blocks: out = relu(norm(conv2) + x)
         const Tensor *f1 = find(b, p + "se.fc1.weight"), *f2 = find(b, p + "se.fc2.weight");
         if (!f1 || !f2) return SC_E_IO;
         if (f1->numel != (size_t)C_SE * C_TOWER || f2->numel != (size_t)C_SE * C_TOWER) {
@@ -691,7 +704,7 @@ int sc_create(const char *weights_blob_path, int device, int mode, int max_batch
                 L.gamma = c.gamma;
                 L.beta = c.beta;
                 L.relu = relu;
-                L.ln = 1;
+                L.ln = c.gamma != nullptr;
                 L.se = se;
                 if (sw) {
                     L.se_w1s8 = sw->w1s[0];
@@ -706,7 +719,8 @@ int sc_create(const char *weights_blob_path, int device, int mode, int max_batch
             lat_layer(e->stem, e->h_planes, e->h_x, nullptr, 1, 0, nullptr);
             for (int i = 0; i < e->n_blocks; i++) {
                 lat_layer(e->conv1[i], e->h_x, e->h_t, nullptr, 1, 0, nullptr);
-                lat_layer(e->conv2[i], e->h_t, e->h_x, e->h_x, 0, 1, &e->se[i]);
+                const bool has_se = e->se[i].w1p != nullptr;
+                lat_layer(e->conv2[i], e->h_t, e->h_x, e->h_x, 0, has_se ? 1 : 2, has_se ? &e->se[i] : nullptr);
             }
             lat_layer(e->pol1, e->h_x, e->h_t, nullptr, 0, 0, nullptr);
             lat_layer(e->val1, e->h_x, e->h_y, nullptr, 1, 0, nullptr);

@@ -641,14 +641,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 float sum = 0.f;
 #pragma unroll
                 for (int c = 0; c < C_POLICY; c++) sum += v[c];
-                const float mean = sum * (1.f / C_POLICY);
+                float mean = sum * (1.f / C_POLICY);
                 float sq = 0.f;
 #pragma unroll
                 for (int c = 0; c < C_POLICY; c++) {
                     const float d = v[c] - mean;
                     sq = fmaf(d, d, sq);
                 }
-                const float rstd = rsqrtf(sq * (1.f / C_POLICY) + LN_EPS);
+                float rstd = rsqrtf(sq * (1.f / C_POLICY) + LN_EPS);
+                if (!args.ln) {  // no normalisation (folded BatchNorm): gamma = 1, beta = 0 were loaded above
+                    mean = 0.f;
+                    rstd = 1.f;
+                }
                 float *mine = s_logit + row * LDL;
                 float mx = -INFINITY;
 #pragma unroll
@@ -707,7 +711,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     for (int j = 0; j < 16; j++)
                         if (ch * 16 + j < C_POLICY) sum += __uint_as_float(r[j]) + s_bias[ch * 16 + j];
                 }
-                const float mean = sum * (1.f / C_POLICY);
+                const float mean = args.ln ? sum * (1.f / C_POLICY) : 0.f;
                 float sq = 0.f;
 #pragma unroll 1
                 for (int ch = 0; ch < BN / 16; ch++) {
@@ -719,7 +723,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             sq = fmaf(d, d, sq);
                         }
                 }
-                const float rstd = rsqrtf(sq * (1.f / C_POLICY) + LN_EPS);
+                const float rstd = args.ln ? rsqrtf(sq * (1.f / C_POLICY) + LN_EPS) : 1.f;
                 uint8_t *stg = s_stage + (warp - 2) * 2048;
                 uint8_t *gbase = reinterpret_cast<uint8_t *>(static_cast<float *>(args.out) +
                                                              ((size_t)tile * TC_BM + quad * 32) * BN);

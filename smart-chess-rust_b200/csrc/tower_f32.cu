@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(256) ln_f32_kernel(float *__restrict__ x, int 
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s / (float)C;
+    float mean = s / (float)C;
     float q = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
@@ -159,12 +159,16 @@ __global__ void __launch_bounds__(256) ln_f32_kernel(float *__restrict__ x, int 
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    const float rstd = rsqrtf(q / (float)C + LN_EPS);
+    float rstd = rsqrtf(q / (float)C + LN_EPS);
+    if (!gamma) {  // layer without normalisation (BatchNorm folded into the convolution at export)
+        mean = 0.f;
+        rstd = 1.f;
+    }
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         int c = lane + 32 * i;
         if (c < C) {
-            float y = (v[i] - mean) * rstd * gamma[c] + beta[c];
+            float y = gamma ? (v[i] - mean) * rstd * gamma[c] + beta[c] : v[i];
             y = relu ? fmaxf(y, 0.f) : y;
             p[c] = y;
             if (planes) split3_store(y, planes + (size_t)row * 3 * C, c, C);
@@ -203,19 +207,22 @@ __global__ void __launch_bounds__(256) se_res_f32_kernel(const float *__restrict
     __shared__ float s_hid[C_SE];
     const int b = blockIdx.x, c = threadIdx.x;
     const float *yb = y + (size_t)b * 64 * C_TOWER;
-    float sum = 0.f;
-    for (int s = 0; s < 64; s++) sum += yb[s * C_TOWER + c];
-    s_mean[c] = sum * (1.f / 64.f);
-    __syncthreads();
-    if (c < C_SE) {
-        float a = b1[c];
-        for (int k = 0; k < C_TOWER; k++) a = fmaf(w1t[k * C_SE + c], s_mean[k], a);
-        s_hid[c] = fmaxf(a, 0.f);
+    float g = 1.f;  // w1t == nullptr: `use_se=False`, the block is relu(y + x)
+    if (w1t) {
+        float sum = 0.f;
+        for (int s = 0; s < 64; s++) sum += yb[s * C_TOWER + c];
+        s_mean[c] = sum * (1.f / 64.f);
+        __syncthreads();
+        if (c < C_SE) {
+            float a = b1[c];
+            for (int k = 0; k < C_TOWER; k++) a = fmaf(w1t[k * C_SE + c], s_mean[k], a);
+            s_hid[c] = fmaxf(a, 0.f);
+        }
+        __syncthreads();
+        g = b2[c];
+        for (int k = 0; k < C_SE; k++) g = fmaf(w2t[k * C_TOWER + c], s_hid[k], g);
+        g = 1.f / (1.f + expf(-g));
     }
-    __syncthreads();
-    float g = b2[c];
-    for (int k = 0; k < C_SE; k++) g = fmaf(w2t[k * C_TOWER + c], s_hid[k], g);
-    g = 1.f / (1.f + expf(-g));
     const float *xb = x + (size_t)b * 64 * C_TOWER;
     float *ob = out + (size_t)b * 64 * C_TOWER;
     for (int s = 0; s < 64; s++) {

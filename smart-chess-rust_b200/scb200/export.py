@@ -13,6 +13,12 @@ Blob layout (little endian):
     per tensor: u32 name_len, name, u32 ndim, u32 dims[ndim], u64 offset, u64 numel
     u64  data_bytes
     data: fp32, each tensor 64-byte aligned, `offset` relative to the start of data
+
+Network variants (`NormTable`, `use_se`, py/module.py:6-9, 14-36): a BatchNorm network is exported with every
+BatchNorm folded into the convolution before it (inference uses the running statistics, so
+`bn(conv(x)) = conv(x) * g / sqrt(var + eps) + (beta - mean * g / sqrt(var + eps))` is a convolution with scaled
+weights and a bias); the norm tensors are dropped and the engine runs those layers without normalisation.  A
+`use_se=False` network simply has no `se.*` tensors.  The tensor `__config__` = [norm folded, use_se] tells the engine.
 """
 from __future__ import annotations
 
@@ -31,11 +37,7 @@ def _normalise_state_dict(obj):
     if isinstance(obj, dict) and "pytorch-lightning_version" in obj:
         obj = {k.split(".", 1)[1]: v for k, v in obj["state_dict"].items()}
     sd = {(k[len("_orig_mod."):] if k.startswith("_orig_mod.") else k): v for k, v in obj.items()}
-    if any(k.endswith("running_mean") for k in sd):
-        # NormTable["BatchNorm"] (py/module.py:6-9) is never built by load_model (py/module.py:199)
-        raise ValueError("BatchNorm checkpoints are not supported: the engine implements the LayerNorm network "
-                         "that the reference's load_model builds")
-    required = ["conv_block.0.weight", "conv_block.0.bias", "conv_block.1.weight", "policy_head.model.2.weight",
+    required = ["conv_block.0.weight", "conv_block.1.weight", "policy_head.model.2.weight",
                 "value_head.ffn.0.weight", "value_head.ffn.2.weight"]
     missing = [k for k in required if k not in sd]
     if missing:
@@ -43,11 +45,45 @@ def _normalise_state_dict(obj):
     return sd
 
 
+BN_EPS = 1e-5  # torch.nn.BatchNorm2d default
+
+
+def _fold_batchnorm(sd, n_blocks):
+    """NormTable["BatchNorm"] (py/module.py:6-9): conv (bias=False, py/module.py:18) + BatchNorm2d in eval mode ->
+    conv with bias.  Returns a new dict without the norm tensors."""
+    import torch
+
+    pairs = [("conv_block.0", "conv_block.1"), ("value_head.conv.0", "value_head.conv.1"),
+             ("policy_head.model.0", "policy_head.model.1"), ("policy_head.model.2", "policy_head.model.3")]
+    for i in range(n_blocks):
+        pairs += [(f"res_blocks.{i}.conv1", f"res_blocks.{i}.bn1"), (f"res_blocks.{i}.conv2", f"res_blocks.{i}.bn2")]
+    out = {k: v for k, v in sd.items()}
+    for conv, norm in pairs:
+        w = sd[conv + ".weight"].detach().double()
+        g, b = sd[norm + ".weight"].detach().double(), sd[norm + ".bias"].detach().double()
+        mean, var = sd[norm + ".running_mean"].detach().double(), sd[norm + ".running_var"].detach().double()
+        scale = g / torch.sqrt(var + BN_EPS)
+        bias = sd[conv + ".bias"].detach().double() if conv + ".bias" in sd else torch.zeros_like(mean)
+        out[conv + ".weight"] = (w * scale.view(-1, 1, 1, 1)).float()
+        out[conv + ".bias"] = ((bias - mean) * scale + b).float()
+        for suffix in (".weight", ".bias", ".running_mean", ".running_var", ".num_batches_tracked"):
+            out.pop(norm + suffix, None)
+    return out
+
+
 def write_blob(state_dict, path: str) -> int:
+    import numpy as _np
+
     sd = _normalise_state_dict(state_dict)
     n_blocks = 0
     while f"res_blocks.{n_blocks}.conv1.weight" in sd:
         n_blocks += 1
+    folded = any(k.endswith("running_mean") for k in sd)
+    use_se = "res_blocks.0.se.fc1.weight" in sd or n_blocks == 0
+    if folded:
+        sd = _fold_batchnorm(sd, n_blocks)
+    sd = dict(sd)
+    sd["__config__"] = _np.array([1.0 if folded else 0.0, 1.0 if use_se else 0.0], dtype=_np.float32)
     entries = []
     chunks = []
     off = 0

@@ -64,7 +64,7 @@ def test_blob_roundtrip(tmp_path):
     raw = open(p, "rb").read()
     assert raw[:8] == b"SCB2WTS1"
     nb, nt = struct.unpack("<II", raw[8:16])
-    assert nb == 1 and nt == len(sd) and nbytes >= sum(v.numel() for v in sd.values()) * 4
+    assert nb == 1 and nt == len(sd) + 1 and nbytes >= sum(v.numel() for v in sd.values()) * 4   # + `__config__`
     # lightning-style checkpoints are unwrapped like _load_ckpt (py/module.py:170-176)
     wrapped = {"pytorch-lightning_version": "2", "state_dict": {"model." + k: v for k, v in sd.items()}}
     p2 = str(tmp_path / "w2.scw")
@@ -81,9 +81,50 @@ def test_blob_roundtrip(tmp_path):
     scb200.export_checkpoint(ck, p4)
     assert open(p4, "rb").read() == raw
     # inputs the engine cannot run are refused at export time, not at load time
-    bn = dict(sd)
-    bn["conv_block.1.running_mean"] = torch.zeros(256)
-    with pytest.raises(ValueError, match="BatchNorm"):
-        scb200.write_blob(bn, p3)
     with pytest.raises(ValueError, match="missing"):
         scb200.write_blob({"foo": torch.zeros(1)}, p3)
+
+
+def test_oracle_variants_match_reference_goldens(net_golden):
+    """`NormTable["BatchNorm"]` and `use_se=False` (py/module.py:6-9, 28-36): the oracle's forward for the three variant
+    nets equals the outputs the reference's own module.py produced for the same weights (oracle/make_golden_net.py)."""
+    import net
+
+    x = net.planes_i8_hwc_to_nchw(net_golden["planes_i8"])
+    meta = torch.from_numpy(net_golden["meta_i32"]).float()
+    for tag, info in net_golden["info"]["variants"].items():
+        sd = net.init_variant_state_dict(info["n_res_blocks"], info["seed"], info["norm"], info["use_se"])
+        d = net.state_dict_digest({k: t for k, t in sd.items() if t.ndim > 0})
+        if abs(d["sum"] - info["digest"]["sum"]) > 1e-6:
+            pytest.skip("seeded variant net differs on this machine; golden vectors not comparable")
+        assert ("res_blocks.0.se.fc1.weight" in sd) == info["use_se"]
+        assert ("conv_block.1.running_mean" in sd) == (info["norm"] == "BatchNorm")
+        assert ("conv_block.0.bias" in sd) == (info["norm"] != "BatchNorm")
+        lp, v = net.forward(sd, x, meta)
+        assert np.abs(lp.numpy() - net_golden["logp_" + tag]).max() < 1e-6
+        assert np.abs(v.numpy().reshape(-1) - net_golden["value_" + tag]).max() < 1e-6
+
+
+def test_exporter_folds_batchnorm_and_marks_variants(tmp_path):
+    """scb200.export: a BatchNorm checkpoint becomes conv + bias tensors without norm layers (folding identity checked
+    in fp64 on one layer), and `__config__` = [norm folded, use_se]."""
+    import struct
+
+    import net
+    import scb200
+    from scb200 import export
+
+    sd = net.init_variant_state_dict(1, 5, "BatchNorm", False)
+    folded = export._fold_batchnorm(sd, 1)
+    assert "conv_block.1.weight" not in folded and "conv_block.0.bias" in folded
+    xin = torch.randn(2, 112, 8, 8, dtype=torch.float64)
+    ref = torch.nn.functional.batch_norm(
+        torch.nn.functional.conv2d(xin, sd["conv_block.0.weight"].double(), None, padding=1),
+        sd["conv_block.1.running_mean"].double(), sd["conv_block.1.running_var"].double(),
+        sd["conv_block.1.weight"].double(), sd["conv_block.1.bias"].double(), training=False, eps=1e-5)
+    got = torch.nn.functional.conv2d(xin, folded["conv_block.0.weight"].double(), folded["conv_block.0.bias"].double(), padding=1)
+    assert (ref - got).abs().max() < 1e-5
+    p = str(tmp_path / "v.scw")
+    scb200.write_blob(sd, p)
+    raw = open(p, "rb").read()
+    assert b"__config__" in raw and b"running_mean" not in raw and b"se.fc1" not in raw

@@ -262,6 +262,9 @@ int sc_rules_perft(const char *fen, int depth, uint64_t *nodes);
  * 0, winner 1/0/-1).  Returns SC_E_INVAL if a history move is not legal. */
 int sc_rules_probe(const sc_move *history, int n_history, sc_move *legal_out, int *n_legal, sc_position *packed_out,
                    int *termination, int *winner);
+/* the same from an arbitrary start position (`chess.Board(fen)`; NULL = the initial position) */
+int sc_rules_probe_fen(const char *fen, const sc_move *history, int n_history, sc_move *legal_out, int *n_legal,
+                       sc_position *packed_out, int *termination, int *winner);
 
 #ifdef __cplusplus
 }

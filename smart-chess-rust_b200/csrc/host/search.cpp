@@ -1015,12 +1015,22 @@ int sc_rules_perft(const char *fen, int depth, uint64_t *nodes)
 int sc_rules_probe(const sc_move *history, int n_history, sc_move *legal_out, int *n_legal, sc_position *packed_out,
                    int *termination, int *winner)
 {
+    return sc_rules_probe_fen(nullptr, history, n_history, legal_out, n_legal, packed_out, termination, winner);
+}
+
+int sc_rules_probe_fen(const char *fen, const sc_move *history, int n_history, sc_move *legal_out, int *n_legal,
+                       sc_position *packed_out, int *termination, int *winner)
+{
     if (n_history < 0 || (n_history > 0 && !history)) {
         set_error("sc_rules_probe: bad argument");
         return SC_E_INVAL;
     }
     Tree t;
     t.new_game(0);
+    if (fen && !t.game.cur.set_fen(fen)) {
+        set_error("sc_rules_probe_fen: bad FEN");
+        return SC_E_INVAL;
+    }
     MoveList l;
     for (int i = 0; i < n_history; i++) {
         t.game.cur.legal_moves(l);

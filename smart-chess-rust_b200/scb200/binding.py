@@ -25,7 +25,7 @@ DECLARED_SYMBOLS = [
     "sc_eval_submit", "sc_eval_wait", "sc_selfplay_create", "sc_selfplay_run", "sc_selfplay_trace_json",
     "sc_selfplay_destroy", "sc_rules_probe", "sc_arena_create", "sc_encode_steps", "sc_timed_flops_per_leaf",
     "sc_random_positions", "sc_test_dirichlet", "sc_game_selfplay", "sc_rules_perft", "sc_device_info",
-    "sc_selfplay_run_many", "sc_debug_tower",
+    "sc_selfplay_run_many", "sc_debug_tower", "sc_rules_probe_fen",
 ]
 
 
@@ -105,6 +105,7 @@ def load_library():
         L.sc_rules_perft.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_uint64)]
         L.sc_rules_probe.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.c_void_p,
                                      C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.sc_rules_probe_fen.argtypes = [C.c_char_p] + L.sc_rules_probe.argtypes
         _LIB = L
     return _LIB
 
@@ -375,16 +376,17 @@ def rules_perft(fen, depth: int) -> int:
     return int(n.value)
 
 
-def rules_probe(history):
-    """history: list of (from, to, promo) -> (legal moves [n,3] uint8, sc_position record, (termination, winner))."""
+def rules_probe(history, fen=None):
+    """history: list of (from, to, promo) [from `fen`, default the initial position] -> (legal moves [n,3] uint8,
+    sc_position record, (termination, winner))."""
     h = np.zeros(len(history), dtype=MOVE_DTYPE)
     for i, m in enumerate(history):
         h[i] = (int(m[0]), int(m[1]), int(m[2]), 0)
     legal = np.zeros(256, dtype=MOVE_DTYPE)
     n, term, win = C.c_int(), C.c_int(), C.c_int()
     pos = np.zeros(1, dtype=POSITION_DTYPE)
-    _check(load_library().sc_rules_probe(_ptr(h) if len(h) else None, len(h), _ptr(legal), C.byref(n), _ptr(pos),
-                                         C.byref(term), C.byref(win)), "sc_rules_probe")
+    _check(load_library().sc_rules_probe_fen(fen.encode() if fen else None, _ptr(h) if len(h) else None, len(h), _ptr(legal),
+                                             C.byref(n), _ptr(pos), C.byref(term), C.byref(win)), "sc_rules_probe")
     mv = np.stack([legal["from"][: n.value], legal["to"][: n.value], legal["promo"][: n.value]], axis=1)
     return mv, pos[0], (term.value, win.value)
 

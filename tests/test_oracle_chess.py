@@ -257,3 +257,101 @@ def test_encode_steps_literal_restatement(co):
         assert i0 == [int(x) for x in g.move_indices()]
         assert abs(d0.sum() - 1.0) < 1e-4 or d0.sum() == 0
         g.push(mv)
+
+
+PYCHESS_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pychess_golden.json.gz")
+
+
+def _check_games(co, games, check_oracle: bool):
+    """Holds the product's native rules (and, with check_oracle, the C oracle) to per-ply records in the format of
+    oracle/make_golden_pychess.py."""
+    import scb200
+
+    n = 0
+    for game in games:
+        fen = game["fen"]
+        g = co.Game(fen) if fen else co.Game()
+        hist = []
+        for ply, rec in enumerate(game["plies"]):
+            where = (game["source"], fen, ply)
+            if check_oracle:
+                assert g.legal_uci() == rec["legal"], where
+                assert g.is_repetition(2) == rec["rep2"] and g.is_repetition(3) == rec["rep3"], where
+                assert [int(v) for v in g.encode()[1]] == rec["meta"], where
+                oc = g.outcome(True)
+                assert (None if oc is None else [int(oc[0]), int(oc[1])]) == rec["outcome"], where
+            mv, pos, (term, win) = scb200.rules_probe(hist, fen)
+            assert [co.uci(m) for m in mv] == rec["legal"], where
+            assert [int(v) for v in pos["meta"]] == rec["meta"], where
+            assert bool(int(pos["slot"][0][7]) & 1) == rec["rep2"] and bool(int(pos["slot"][0][7]) & 2) == rec["rep3"], where
+            assert (None if term == 0 else [term, win]) == rec["outcome"], where
+            n += 1
+            if ply < len(game["moves"]):
+                g.push(game["moves"][ply])
+                hist.append(tuple(int(v) for v in co.parse_uci(game["moves"][ply])))
+    return n
+
+
+def _edge_fens():
+    import re
+
+    src = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle", "make_golden_pychess.py")).read()
+    block = src[src.index("EDGE_FENS = ["):src.index("]", src.index("EDGE_FENS = ["))]
+    return re.findall(r'"([^"]+ [wb] [KQkq-]+ [a-h1-8-]+ \d+ \d+)"', block)
+
+
+def test_native_rules_equal_oracle_on_the_golden_generators_cases(co):
+    """The same games the python-chess generator plays (edge-case FENs, repetition shuffle, a long rook ending), recorded
+    with the C ORACLE instead, in the generator's format: the product's independent rules engine must agree ply by ply
+    on move order, repetition flags, meta and outcome(claim_draw=True).  (Differential test; the python-chess pin itself
+    is test_rules_against_python_chess_goldens.)"""
+    fens = _edge_fens()
+    assert len(fens) >= 20
+    rng = np.random.RandomState(12)
+
+    def rec(g):
+        oc = g.outcome(True)
+        return {"legal": g.legal_uci(), "rep2": g.is_repetition(2), "rep3": g.is_repetition(3),
+                "meta": [int(v) for v in g.encode()[1]], "outcome": None if oc is None else [int(oc[0]), int(oc[1])]}
+
+    def play(fen, n_plies, moves=None):
+        g = co.Game(fen) if fen else co.Game()
+        plies, ucis = [rec(g)], []
+        for k in range(n_plies):
+            legal = g.legal_uci()
+            if not legal:
+                break
+            u = moves[k] if moves else legal[rng.randint(len(legal))]
+            ucis.append(u)
+            g.push(u)
+            plies.append(rec(g))
+        return {"fen": fen, "moves": ucis, "plies": plies, "source": "oracle"}
+
+    games = [play(f, 50) for f in fens for _ in range(2)]
+    games.append(play(None, 20, ["g1f3", "g8f6", "f3g1", "f6g8"] * 5))
+    games.append(play("8/8/8/4k3/8/8/3RK3/8 w - - 0 1", 320))
+    n = _check_games(co, games, check_oracle=False)
+    assert n > 2000
+    outcomes = {tuple(p["outcome"]) for g in games for p in g["plies"] if p["outcome"]}
+    assert {1, 2, 3, 5, 6, 7} <= {o[0] for o in outcomes} | {4}      # every termination kind but (maybe) 75-move is met
+    assert any(p["rep3"] for g in games for p in g["plies"])
+
+
+def test_rules_against_python_chess_goldens(co):
+    """Rows a6 / c of SURVEY section 8: everything the hot path takes from python-chess (legal-move ORDER,
+    is_repetition(2/3), castling-rights view, clocks, outcome(claim_draw=True)) for both rule engines -- the C oracle and
+    the product's native rules -- against a dump made by python-chess itself (oracle/make_golden_pychess.py).
+    python-chess cannot be installed in the offline build container; until somebody with python-chess runs the generator
+    and commits its output this test reports the rules as UNPINNED (an expected failure, not a pass)."""
+    import gzip
+    import json
+
+    if not os.path.exists(PYCHESS_GOLDEN):
+        pytest.xfail("PARITY UNPINNED: tests/golden/pychess_golden.json.gz is absent -- run oracle/make_golden_pychess.py "
+                     "where python-chess 1.11.1 is installed; until then move order, repetition flags and draw claims of "
+                     "both rule engines are checked only against each other, perft tables and the reference's two "
+                     "notebook move lists")
+    with gzip.open(PYCHESS_GOLDEN, "rt") as f:
+        gold = json.load(f)
+    assert gold["n_plies"] >= 13000
+    assert _check_games(co, gold["games"], check_oracle=True) == gold["n_plies"]

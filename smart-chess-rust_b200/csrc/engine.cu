@@ -12,10 +12,19 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 #include "host/chess_rules.hpp"
 
 namespace scb {
+
+// NVTX ranges around the phases of a call (visible in Nsight Systems / ncu --nvtx; no cost without a profiler
+// attached).  The reference's hook for this is profiling/rocprof-selfplay:5-8.
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 static thread_local std::string g_err;
 void set_error(const std::string &msg) { g_err = msg; }
@@ -478,6 +487,7 @@ static int kev_mark(sc_engine *e, cudaStream_t st)
 // then skips launch_policy_gather.  Returns through *fused whether that happened.
 static int run_network(sc_engine *e, int n, cudaStream_t st, const TcGather *gather = nullptr)
 {
+    NvtxRange nv_net("scb200: network (tower + heads)");
     const int rows = n * 64;
     e->kev_used = 0;
     if (e->timing) SCB_CUDA(cudaEventRecord(e->ev[1], st));
@@ -593,6 +603,7 @@ static int run_network(sc_engine *e, int n, cudaStream_t st, const TcGather *gat
             e->timed_flops_per_leaf = 2.0 * 64 * 256 * 9.0 * 256 * 2 * e->n_blocks;
         }
         if (e->timing) SCB_CUDA(cudaEventRecord(e->ev[2], st));
+        NvtxRange nv_heads("scb200: policy + value heads");
         if (trc != SC_OK) {
             SCB_CHECK(tc_conv_launch(e->pol1.tc, e->h_x, nb, n, e->h_t, nullptr, 0, 1, e->num_sms, st));
             SCB_CHECK(tc_conv_launch(e->val1.tc, e->h_x, nb, n, e->h_y, nullptr, 1, 1, e->num_sms, st));
@@ -610,6 +621,7 @@ static int run_network(sc_engine *e, int n, cudaStream_t st, const TcGather *gat
 
 static int encode_for_mode(sc_engine *e, const sc_position *d_pos, int n, cudaStream_t st)
 {
+    NvtxRange nv("scb200: encode planes");
     e->launches += 1;
     if (e->mode == SC_MODE_FP32 && !e->fp32_tc) return launch_encode_f32(d_pos, n, e->f_planes, e->d_meta, st);
     return launch_encode_bf16(d_pos, n, e->h_planes, e->d_meta, st);
@@ -824,6 +836,7 @@ int sc_eval(sc_engine *e, int n, const sc_position *pos, const sc_move *moves, c
         return SC_E_INVAL;
     }
     if (n == 0) return SC_OK;
+    NvtxRange nv_call("sc_eval");
     const int total = move_off[n];
     bool mono = move_off[0] == 0 && total >= 0 && total <= e->max_moves_total;
     for (int i = 0; mono && i < n; i++) mono = move_off[i + 1] >= move_off[i];
@@ -867,6 +880,7 @@ int sc_eval_submit(sc_engine *e, int n, const sc_position *pos, const sc_move *m
         set_error("sc_eval_submit: bad argument");
         return SC_E_INVAL;
     }
+    NvtxRange nv_call("sc_eval_submit");
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
     SCB_CUDA(cudaSetDevice(e->device));
     const int t = e->next_ticket;
@@ -943,6 +957,7 @@ int sc_eval_wait(sc_engine *e, int ticket)
         set_error("sc_eval_wait: bad ticket");
         return SC_E_INVAL;
     }
+    NvtxRange nv_call("sc_eval_wait");
     SCB_CUDA(cudaEventSynchronize(e->tickets[ticket]));
     return SC_OK;
 }

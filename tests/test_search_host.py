@@ -385,3 +385,21 @@ def test_auto_leaves_per_tree_fills_the_tail(co):
         for mv, q, ch in t["steps"]:
             assert [c[0] for c in ch] == g.legal_uci() and sum(c[1] for c in ch) == 39
             g.push(mv)
+
+
+def test_host_search_is_clean_under_thread_sanitizer():
+    """`make tsan`: the batched driver (self-play with 1 and 4 leaves per tree, arena; 8 worker threads, stand-in
+    evaluator) built with -fsanitize=thread; any data race makes the harness exit non-zero.  (The reference's tree is
+    `unsafe impl Send` and single-threaded, src/mcts.rs:26.)"""
+    import os
+    import shutil
+    import subprocess
+
+    if not shutil.which("g++"):
+        pytest.skip("no g++")
+    csrc = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "smart-chess-rust_b200", "csrc")
+    r = subprocess.run(["make", "-C", csrc, "tsan"], capture_output=True, text=True, timeout=600)
+    if r.returncode != 0 and "unrecognized" in r.stderr and "sanitize" in r.stderr:
+        pytest.skip("toolchain without ThreadSanitizer")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "tsan harness ok" in r.stdout and "WARNING: ThreadSanitizer" not in r.stderr

@@ -355,17 +355,17 @@ static int load_weights(sc_engine *e, const Blob &b)
                         w2p[((size_t)q * C_TOWER + c) * 8 + k] = f2bf(f2->data[(size_t)c * C_SE + 8 * q + k]);
             SCB_CHECK(upload(e, &e->se[i].w1p, w1p));
             SCB_CHECK(upload(e, &e->se[i].w2p, w2p));
-            // latency kernel: the same numbers sliced per cluster rank r -- fc1 rows (hidden units) [r * HJ, +HJ) as
-            // [r][q][j][8], fc2 rows (channels) [r * NC, +NC) as [r][q][c][8]
+            // latency kernel: the same numbers sliced per cluster rank r -- fc1 COLUMNS (input channels) [r * NC, +NC)
+            // for all 128 hidden units as [r][q][j][8], fc2 ROWS (output channels) [r * NC, +NC) as [r][q][c][8]
             for (int v = 0; v < 2; v++) {
-                const int CL = v == 0 ? 8 : 4, HJ = C_SE / CL, NC = C_TOWER / CL;
+                const int CL = v == 0 ? 8 : 4, NC = C_TOWER / CL;
                 std::vector<uint16_t> a((size_t)C_TOWER * C_SE), b((size_t)C_SE * C_TOWER);
                 for (int r = 0; r < CL; r++) {
-                    for (int q = 0; q < C_TOWER / 8; q++)
-                        for (int j = 0; j < HJ; j++)
+                    for (int q = 0; q < NC / 8; q++)
+                        for (int j = 0; j < C_SE; j++)
                             for (int k = 0; k < 8; k++)
-                                a[(((size_t)r * (C_TOWER / 8) + q) * HJ + j) * 8 + k] =
-                                    f2bf(f1->data[(size_t)(r * HJ + j) * C_TOWER + 8 * q + k]);
+                                a[(((size_t)r * (NC / 8) + q) * C_SE + j) * 8 + k] =
+                                    f2bf(f1->data[(size_t)j * C_TOWER + r * NC + 8 * q + k]);
                     for (int q = 0; q < C_SE / 8; q++)
                         for (int c = 0; c < NC; c++)
                             for (int k = 0; k < 8; k++)

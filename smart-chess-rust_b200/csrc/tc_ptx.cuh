@@ -303,18 +303,20 @@ __device__ __forceinline__ float2 warp_transpose_reduce_2boards(float (&v)[32], 
 // ---- LayerNorm arithmetic shared by both kernels -------------------------------------------------------------
 // Written with explicit round-to-nearest intrinsics so that the compiler cannot contract / reassociate it
 // differently in different kernels: the latency kernel must produce the bits of the throughput kernel.
-// Statistics: per 32-channel chunk k the sequential sums (s_k, q_k) of a = acc + bias and a * a; combined as
+// Statistics: per 32-channel chunk k the sums (s_k, q_k) of a = acc + bias and a * a (ln_chunk_stats); combined as
 //   half0 = (p0 + p1) + (p2 + p3), half1 = (p4 + p5) + (p6 + p7), total = half0 + half1
 // -- a fixed tree, so the chunks may be computed by different threads / CTAs.
 __device__ __forceinline__ void ln_chunk_stats(const float (&a)[32], float &s, float &q)
 {
-    s = 0.f;
-    q = 0.f;
+    // four interleaved sequential chains (j mod 4) and a fixed tree: a quarter of the dependent-add latency of one chain
+    float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < 32; j++) {
-        s = __fadd_rn(s, a[j]);
-        q = __fmaf_rn(a[j], a[j], q);
+        s4[j & 3] = __fadd_rn(s4[j & 3], a[j]);
+        q4[j & 3] = __fmaf_rn(a[j], a[j], q4[j & 3]);
     }
+    s = __fadd_rn(__fadd_rn(s4[0], s4[1]), __fadd_rn(s4[2], s4[3]));
+    q = __fadd_rn(__fadd_rn(q4[0], q4[1]), __fadd_rn(q4[2], q4[3]));
 }
 __device__ __forceinline__ float2 ln_half(const float2 p0, const float2 p1, const float2 p2, const float2 p3)
 {
@@ -337,6 +339,23 @@ __device__ __forceinline__ float ln_apply(float a, float mean, float rstd, float
 __device__ __forceinline__ float se_hidden(float b1, float half0, float half1)
 {
     return fmaxf(__fadd_rn(__fadd_rn(b1, half0), half1), 0.f);
+}
+// Both SE matrix-vector products are defined chunk-wise so that the chunks can be computed by different threads / CTAs:
+// per 32-input chunk one sequential fma chain from 0 (se_chain8 = 8 inputs of it), the chunk sums combined in fixed trees.
+__device__ __forceinline__ float se_chain8(const float (&w)[8], const float4 a, const float4 b, float acc)
+{
+    acc = fmaf(w[0], a.x, acc); acc = fmaf(w[1], a.y, acc); acc = fmaf(w[2], a.z, acc); acc = fmaf(w[3], a.w, acc);
+    acc = fmaf(w[4], b.x, acc); acc = fmaf(w[5], b.y, acc); acc = fmaf(w[6], b.z, acc); acc = fmaf(w[7], b.w, acc);
+    return acc;
+}
+__device__ __forceinline__ float se_tree4(float p0, float p1, float p2, float p3)
+{
+    return __fadd_rn(__fadd_rn(p0, p1), __fadd_rn(p2, p3));
+}
+// FC2 pre-activation: bias + the four 32-hidden-unit chunk sums
+__device__ __forceinline__ float se_fc2_sum(float b2, float c0, float c1, float c2, float c3)
+{
+    return __fadd_rn(b2, se_tree4(c0, c1, c2, c3));
 }
 __device__ __forceinline__ float se_sigmoid(float g) { return __fdiv_rn(1.f, __fadd_rn(1.f, __expf(-g))); }
 

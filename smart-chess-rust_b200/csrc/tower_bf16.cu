@@ -870,21 +870,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     uint4 w2v[16];
                     {
                         const int j = te & 127, hc = te >> 7;
-                        float h0 = 0.f, h1 = 0.f;
+                        // four 32-channel chunk chains per board, then the fixed tree (tc_ptx.cuh)
+                        auto chunk1 = [&](int k, float &a0, float &a1) {
+                            a0 = 0.f;
+                            a1 = 0.f;
 #pragma unroll
-                        for (int u = 0; u < 16; u++) {
-                            const int q = hc * 16 + u;
-                            float wf[8];
-                            bf16x8_to_float(w1v[u], wf);
-                            const float4 m0a = *reinterpret_cast<const float4 *>(s_mean + q * 8);
-                            const float4 m0b = *reinterpret_cast<const float4 *>(s_mean + q * 8 + 4);
-                            const float4 m1a = *reinterpret_cast<const float4 *>(s_mean + 256 + q * 8);
-                            const float4 m1b = *reinterpret_cast<const float4 *>(s_mean + 256 + q * 8 + 4);
-                            h0 = fmaf(wf[0], m0a.x, h0); h0 = fmaf(wf[1], m0a.y, h0); h0 = fmaf(wf[2], m0a.z, h0); h0 = fmaf(wf[3], m0a.w, h0);
-                            h0 = fmaf(wf[4], m0b.x, h0); h0 = fmaf(wf[5], m0b.y, h0); h0 = fmaf(wf[6], m0b.z, h0); h0 = fmaf(wf[7], m0b.w, h0);
-                            h1 = fmaf(wf[0], m1a.x, h1); h1 = fmaf(wf[1], m1a.y, h1); h1 = fmaf(wf[2], m1a.z, h1); h1 = fmaf(wf[3], m1a.w, h1);
-                            h1 = fmaf(wf[4], m1b.x, h1); h1 = fmaf(wf[5], m1b.y, h1); h1 = fmaf(wf[6], m1b.z, h1); h1 = fmaf(wf[7], m1b.w, h1);
-                        }
+                            for (int uu = 0; uu < 4; uu++) {
+                                const int u = 4 * k + uu, q = hc * 16 + u;
+                                float wf[8];
+                                bf16x8_to_float(w1v[u], wf);
+                                a0 = se_chain8(wf, *reinterpret_cast<const float4 *>(s_mean + q * 8),
+                                               *reinterpret_cast<const float4 *>(s_mean + q * 8 + 4), a0);
+                                a1 = se_chain8(wf, *reinterpret_cast<const float4 *>(s_mean + 256 + q * 8),
+                                               *reinterpret_cast<const float4 *>(s_mean + 256 + q * 8 + 4), a1);
+                            }
+                        };
+                        float xa0, xa1, xb0, xb1;
+                        chunk1(0, xa0, xa1);
+                        chunk1(1, xb0, xb1);
+                        const float l0 = __fadd_rn(xa0, xb0), l1 = __fadd_rn(xa1, xb1);
+                        chunk1(2, xa0, xa1);
+                        chunk1(3, xb0, xb1);
+                        // se_tree4: (p0 + p1) + (p2 + p3)
+                        const float h0 = __fadd_rn(l0, __fadd_rn(xa0, xb0)), h1 = __fadd_rn(l1, __fadd_rn(xa1, xb1));
                         s_hidp[(hc * 2 + 0) * 128 + j] = h0;
                         s_hidp[(hc * 2 + 1) * 128 + j] = h1;
                     }
@@ -907,20 +915,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     epi_bar_sync();
                     // ---- FC2 (128 -> 256) + sigmoid: thread te owns channel te for both boards
                     {
-                        float g0 = P.b2[te], g1 = g0;
+                        auto chunk2 = [&](int k, float &a0, float &a1) {
+                            a0 = 0.f;
+                            a1 = 0.f;
 #pragma unroll
-                        for (int q = 0; q < 16; q++) {
-                            float wf[8];
-                            bf16x8_to_float(w2v[q], wf);
-                            const float4 h0a = *reinterpret_cast<const float4 *>(s_hid + q * 8);
-                            const float4 h0b = *reinterpret_cast<const float4 *>(s_hid + q * 8 + 4);
-                            const float4 h1a = *reinterpret_cast<const float4 *>(s_hid + 128 + q * 8);
-                            const float4 h1b = *reinterpret_cast<const float4 *>(s_hid + 128 + q * 8 + 4);
-                            g0 = fmaf(wf[0], h0a.x, g0); g0 = fmaf(wf[1], h0a.y, g0); g0 = fmaf(wf[2], h0a.z, g0); g0 = fmaf(wf[3], h0a.w, g0);
-                            g0 = fmaf(wf[4], h0b.x, g0); g0 = fmaf(wf[5], h0b.y, g0); g0 = fmaf(wf[6], h0b.z, g0); g0 = fmaf(wf[7], h0b.w, g0);
-                            g1 = fmaf(wf[0], h1a.x, g1); g1 = fmaf(wf[1], h1a.y, g1); g1 = fmaf(wf[2], h1a.z, g1); g1 = fmaf(wf[3], h1a.w, g1);
-                            g1 = fmaf(wf[4], h1b.x, g1); g1 = fmaf(wf[5], h1b.y, g1); g1 = fmaf(wf[6], h1b.z, g1); g1 = fmaf(wf[7], h1b.w, g1);
-                        }
+                            for (int qq = 0; qq < 4; qq++) {
+                                const int q = 4 * k + qq;
+                                float wf[8];
+                                bf16x8_to_float(w2v[q], wf);
+                                a0 = se_chain8(wf, *reinterpret_cast<const float4 *>(s_hid + q * 8),
+                                               *reinterpret_cast<const float4 *>(s_hid + q * 8 + 4), a0);
+                                a1 = se_chain8(wf, *reinterpret_cast<const float4 *>(s_hid + 128 + q * 8),
+                                               *reinterpret_cast<const float4 *>(s_hid + 128 + q * 8 + 4), a1);
+                            }
+                        };
+                        float ya0, ya1, yb0, yb1;
+                        chunk2(0, ya0, ya1);
+                        chunk2(1, yb0, yb1);
+                        const float m0 = __fadd_rn(ya0, yb0), m1 = __fadd_rn(ya1, yb1);
+                        chunk2(2, ya0, ya1);
+                        chunk2(3, yb0, yb1);
+                        // se_fc2_sum: b2 + ((c0 + c1) + (c2 + c3))
+                        const float g0 = __fadd_rn(P.b2[te], __fadd_rn(m0, __fadd_rn(ya0, yb0)));
+                        const float g1 = __fadd_rn(P.b2[te], __fadd_rn(m1, __fadd_rn(ya1, yb1)));
                         s_gate[te] = se_sigmoid(g0);
                         s_gate[256 + te] = se_sigmoid(g1);
                     }

@@ -11,8 +11,10 @@
 //   * LayerNorm needs statistics over all 256 channels of a row: every CTA pushes its per-32-channel partial sums into
 //     the shared memory of all CTAs of the cluster (st.shared::cluster) and signals their mbarriers; the partials are
 //     combined in the fixed tree of tc_ptx.cuh, which is what makes the result identical to the throughput kernel;
-//   * squeeze-excitation: channel means are pushed the same way, FC1 is split by hidden unit over the CTAs (each
-//     pushes its 128/CL hidden activations), FC2 and the gate are per channel, i.e. local;
+//   * squeeze-excitation: the channel means of a CTA's own channels stay local; FC1 is defined per 32-channel chunk
+//     (tc_ptx.cuh), so every CTA computes ITS chunks' partial sums for all 128 hidden units and pushes them to the
+//     cluster -- one exchange -- and everybody adds the eight partials in the fixed tree; FC2 and the gate are per
+//     channel, i.e. local;
 //   * layer l+1 reads layer l's output through L2: after its stores a CTA signals the `ready` mbarrier of every CTA of
 //     the cluster, whose TMA warp then starts the next layer's activation loads.  Weight loads never wait for
 //     activations: their producer warp runs ahead through the layers as far as its ring allows.
@@ -32,7 +34,6 @@
 namespace scb {
 
 constexpr int LAT_THREADS = 256;
-constexpr int LAT_A_BOX = 160 * TC_BK * 2;  // 10 ranks x 2 boards x 8 files rows of 128 B
 
 struct alignas(64) LatLayer {
     CUtensorMap map_a;   // input activations {C, file, board, rank}, box of two boards
@@ -41,7 +42,7 @@ struct alignas(64) LatLayer {
     void *out;
     const __nv_bfloat16 *resid;
     const float *bias, *gamma, *beta;
-    const uint4 *se_w1s, *se_w2s;  // per cluster rank: fc1 slice [32][HJ] x 8 bf16, fc2 slice [16][NC] x 8 bf16
+    const uint4 *se_w1s, *se_w2s;  // per cluster rank: fc1 columns [NC / 8][128] x 8 bf16, fc2 rows [16][NC] x 8 bf16
     const float *se_b1, *se_b2;
     int taps, kchunks, relu, se, ln;
 };
@@ -57,22 +58,23 @@ template <int CL, int NB = 2> struct LatCfg {
     static constexpr int NC = 256 / CL;  // output channels per CTA
     static constexpr int HJ = 128 / CL;  // SE hidden units per CTA
     static constexpr int A_BOX = NB * 80 * TC_BK * 2;  // 10 ranks x NB boards x 8 files rows of 128 B
-    static constexpr int NA = 3;         // activation boxes in flight
+    static constexpr int NA = 6 / NB;    // activation boxes in flight (the ring is 3 two-board boxes either way)
     static constexpr int B_TILE = 3 * NC * TC_BK * 2;
     static constexpr int NBS = CL == 8 ? 8 : 4;
     static constexpr int W1S_BYTES = 32 * HJ * 16, W2S_BYTES = 16 * NC * 16;
-    static constexpr int OFF_B = NA * LAT_A_BOX;  // (sized for two boards in both variants)
+    static constexpr int OFF_B = NA * A_BOX;
     static constexpr int OFF_W1S = OFF_B + NBS * B_TILE;
     static constexpr int OFF_W2S = OFF_W1S + W1S_BYTES;
     static constexpr int OFF_STAT = OFF_W2S + W2S_BYTES;  // float2 [8 chunks][128 rows]
     static constexpr int OFF_PAR = OFF_STAT + 8 * 128 * 8;  // bias, gamma, beta [NC]
     static constexpr int OFF_POOL = OFF_PAR + 2 * 3 * NC * 4;  // (parameters double-buffered by layer parity) [4 quads][2 boards][NC]
-    static constexpr int OFF_MEAN = OFF_POOL + 8 * NC * 4;  // [2][256]
-    static constexpr int OFF_HIDP = OFF_MEAN + 2 * 256 * 4;  // [2 halves][2 boards][HJ]
-    static constexpr int OFF_HID = OFF_HIDP + 4 * HJ * 4;    // [2][128]
-    static constexpr int OFF_GATE = OFF_HID + 2 * 128 * 4;   // [2][NC]
+    static constexpr int OFF_MEAN = OFF_POOL + 8 * NC * 4;   // [NB][NC] means of this CTA's channels
+    static constexpr int OFF_HIDP = OFF_MEAN + 2 * NC * 4;   // [8 chunks][2 boards][128] FC1 chunk partials (pushed by the cluster)
+    static constexpr int OFF_HID = OFF_HIDP + 8 * 2 * 128 * 4;  // [2][128]
+    static constexpr int OFF_FC2P = OFF_HID + 2 * 128 * 4;      // [2 * NC outputs][4 chunk sums]
+    static constexpr int OFF_GATE = OFF_FC2P + 2 * NC * 4 * 4;  // [2][NC]
     static constexpr int OFF_BARS = (OFF_GATE + 2 * NC * 4 + 7) & ~7;
-    static constexpr int N_BARS = 2 * NA + 2 * NBS + 7;
+    static constexpr int N_BARS = 2 * 6 + 2 * NBS + 7;  // sized for the deeper (one-board) activation ring in both variants
     static constexpr int SMEM_BYTES = OFF_BARS + N_BARS * 8 + 16;
 };
 
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs
 {
     using Cfg = LatCfg<CL, NB>;
     constexpr int A_BOX = Cfg::A_BOX, DY_STEP = NB * 1024;  // bytes between the dy taps inside an activation box
-    constexpr int NC = Cfg::NC, HJ = Cfg::HJ, NA = Cfg::NA, NBS = Cfg::NBS, B_TILE = Cfg::B_TILE;
+    constexpr int NC = Cfg::NC, NA = Cfg::NA, NBS = Cfg::NBS, B_TILE = Cfg::B_TILE;
     constexpr int NCH = NC / 32;  // 32-channel chunks per CTA
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t smem_base = smem_u32(smem);
@@ -176,6 +178,7 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs
     float *s_hidp = reinterpret_cast<float *>(smem + Cfg::OFF_HIDP);
     float *s_hid = reinterpret_cast<float *>(smem + Cfg::OFF_HID);
     float *s_gate = reinterpret_cast<float *>(smem + Cfg::OFF_GATE);
+    float *s_fc2p = reinterpret_cast<float *>(smem + Cfg::OFF_FC2P);
     const uint4 *s_w1s = reinterpret_cast<const uint4 *>(smem + Cfg::OFF_W1S);
     const uint4 *s_w2s = reinterpret_cast<const uint4 *>(smem + Cfg::OFF_W2S);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::OFF_BARS);
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs
     auto bempty = [&](int s) { return bar_base + 8u * (2 * NA + NBS + s); };
     const uint32_t bar_tfull = bar_base + 8u * (2 * NA + 2 * NBS), bar_ready = bar_tfull + 8, bar_stat = bar_tfull + 16,
                    bar_mean = bar_tfull + 24, bar_hid = bar_tfull + 32, bar_sewf = bar_tfull + 40, bar_sewe = bar_tfull + 48;
-    auto abox = [&](int s) { return smem_base + (uint32_t)(s * LAT_A_BOX); };
+    auto abox = [&](int s) { return smem_base + (uint32_t)(s * A_BOX); };
     auto btile = [&](int s) { return smem_base + (uint32_t)(Cfg::OFF_B + s * B_TILE); };
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -377,10 +380,7 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs
             if (tid == 0) {
                 // arm this layer's exchange barriers with the bytes the cluster will push into this CTA
                 if (L.ln) mbar_expect_tx(bar_stat, 8 * 64 * NB * 8);
-                if (L.se == 1) {
-                    mbar_expect_tx(bar_mean, NB * 256 * 4);
-                    mbar_expect_tx(bar_hid, NB * 128 * 4);
-                }
+                if (L.se == 1) mbar_expect_tx(bar_hid, 8 * NB * 128 * 4);
             }
             lat_epi_sync();  // parameters visible
             const long long tp0 = prof ? clock64() : 0;
@@ -460,68 +460,73 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs
                     lat_epi_sync();
                     if (tid < NB * NC) {
                         const int b = tid / NC, c = tid % NC;
-                        const float m = __fmul_rn(__fadd_rn(__fadd_rn(s_pool[b * NC + c], s_pool[(NB + b) * NC + c]),
-                                                            __fadd_rn(s_pool[(2 * NB + b) * NC + c], s_pool[(3 * NB + b) * NC + c])),
-                                                  1.f / 64.f);
-                        const uint32_t dst = smem_u32(s_mean + b * 256 + c0 + c);
-#pragma unroll
-                        for (int cc = 0; cc < CL; cc++)
-                            st_async_f32(map_to_cta(dst, (uint32_t)cc), m, map_to_cta(bar_mean, (uint32_t)cc));
+                        s_mean[b * NC + c] = __fmul_rn(__fadd_rn(__fadd_rn(s_pool[b * NC + c], s_pool[(NB + b) * NC + c]),
+                                                                 __fadd_rn(s_pool[(2 * NB + b) * NC + c], s_pool[(3 * NB + b) * NC + c])),
+                                                       1.f / 64.f);
                     }
                     mbar_wait(bar_sewf, (uint32_t)n_se & 1u);  // this layer's SE weights are in shared memory
-                    mbar_wait_cluster(bar_mean, (uint32_t)n_se & 1u);
-                    // ---- excitation FC1, hidden units [rank * HJ, +HJ): thread = (unit, channel half), all boards of the
-                    //      tile, one sequential fma chain per (unit, half, board) as in tower_bf16.cu ----
-                    if (tid < 2 * HJ) {
-                        const int j = tid % HJ, hc = tid / HJ;
-                        float h0 = 0.f, h1 = 0.f;
-#pragma unroll 4
-                        for (int u = 0; u < 16; u++) {
-                            const int q = hc * 16 + u;
-                            float wf[8];
-                            bf16x8_to_float(s_w1s[q * HJ + j], wf);
-                            const float4 m0a = *reinterpret_cast<const float4 *>(s_mean + q * 8);
-                            const float4 m0b = *reinterpret_cast<const float4 *>(s_mean + q * 8 + 4);
-                            h0 = fmaf(wf[0], m0a.x, h0); h0 = fmaf(wf[1], m0a.y, h0); h0 = fmaf(wf[2], m0a.z, h0); h0 = fmaf(wf[3], m0a.w, h0);
-                            h0 = fmaf(wf[4], m0b.x, h0); h0 = fmaf(wf[5], m0b.y, h0); h0 = fmaf(wf[6], m0b.z, h0); h0 = fmaf(wf[7], m0b.w, h0);
-                            if (NB == 2) {
-                                const float4 m1a = *reinterpret_cast<const float4 *>(s_mean + 256 + q * 8);
-                                const float4 m1b = *reinterpret_cast<const float4 *>(s_mean + 256 + q * 8 + 4);
-                                h1 = fmaf(wf[0], m1a.x, h1); h1 = fmaf(wf[1], m1a.y, h1); h1 = fmaf(wf[2], m1a.z, h1); h1 = fmaf(wf[3], m1a.w, h1);
-                                h1 = fmaf(wf[4], m1b.x, h1); h1 = fmaf(wf[5], m1b.y, h1); h1 = fmaf(wf[6], m1b.z, h1); h1 = fmaf(wf[7], m1b.w, h1);
+                    lat_epi_sync();
+                    // ---- excitation FC1: thread = hidden unit; the chunk sums of THIS CTA's channels (one sequential fma
+                    //      chain per chunk and board, as in tower_bf16.cu) go to every CTA of the cluster ----
+                    {
+                        const int j = tid;
+#pragma unroll
+                        for (int ch = 0; ch < NCH; ch++) {
+                            float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+                            for (int uu = 0; uu < 4; uu++) {
+                                float wf[8];
+                                bf16x8_to_float(s_w1s[(ch * 4 + uu) * 128 + j], wf);
+                                const float *m = s_mean + ch * 32 + uu * 8;
+                                p0 = se_chain8(wf, *reinterpret_cast<const float4 *>(m), *reinterpret_cast<const float4 *>(m + 4), p0);
+                                if (NB == 2)
+                                    p1 = se_chain8(wf, *reinterpret_cast<const float4 *>(m + NC),
+                                                   *reinterpret_cast<const float4 *>(m + NC + 4), p1);
+                            }
+                            const int kg = (int)rank * NCH + ch;  // global chunk index 0..7
+                            const uint32_t dst = smem_u32(s_hidp + (kg * 2 + 0) * 128 + j);
+#pragma unroll
+                            for (int cc = 0; cc < CL; cc++) {
+                                st_async_f32(map_to_cta(dst, (uint32_t)cc), p0, map_to_cta(bar_hid, (uint32_t)cc));
+                                if (NB == 2)
+                                    st_async_f32(map_to_cta(dst + 128 * 4, (uint32_t)cc), p1, map_to_cta(bar_hid, (uint32_t)cc));
                             }
                         }
-                        s_hidp[(hc * 2 + 0) * HJ + j] = h0;
-                        if (NB == 2) s_hidp[(hc * 2 + 1) * HJ + j] = h1;
-                    }
-                    lat_epi_sync();
-                    if (tid < NB * HJ) {
-                        const int b = tid / HJ, j = tid % HJ;
-                        const int jg = (int)rank * HJ + j;
-                        const float h = se_hidden(L.se_b1[jg], s_hidp[b * HJ + j], s_hidp[(2 + b) * HJ + j]);
-                        const uint32_t dst = smem_u32(s_hid + b * 128 + jg);
-#pragma unroll
-                        for (int cc = 0; cc < CL; cc++)
-                            st_async_f32(map_to_cta(dst, (uint32_t)cc), h, map_to_cta(bar_hid, (uint32_t)cc));
                     }
                     mbar_wait_cluster(bar_hid, (uint32_t)n_se & 1u);
-                    // ---- FC2 + sigmoid for this CTA's channels: thread = (board, channel) ----
-                    if (tid < NB * NC) {
-                        const int b = tid / NC, c = tid % NC;
-                        float g = L.se_b2[c0 + c];
-#pragma unroll 4
-                        for (int q = 0; q < 16; q++) {
+                    {
+                        const int j = tid;
+#pragma unroll
+                        for (int b = 0; b < NB; b++) {
+                            const float *p = s_hidp + b * 128 + j;  // chunk k at p[k * 256]
+                            s_hid[b * 128 + j] = se_hidden(L.se_b1[j], se_tree4(p[0], p[256], p[512], p[768]),
+                                                           se_tree4(p[1024], p[1280], p[1536], p[1792]));
+                        }
+                    }
+                    lat_epi_sync();
+                    // ---- FC2: one 32-hidden-unit chain per (board, channel, chunk), spread over the 128 threads ----
+#pragma unroll
+                    for (int i = 0; i < NB * NC * 4 / 128; i++) {
+                        const int id = tid + 128 * i, o = id >> 2, k = id & 3;
+                        const int b = o / NC, c = o % NC;
+                        float acc = 0.f;
+#pragma unroll
+                        for (int qq = 0; qq < 4; qq++) {
+                            const int q = 4 * k + qq;
                             float wf[8];
                             bf16x8_to_float(s_w2s[q * NC + c], wf);
-                            const float4 ha = *reinterpret_cast<const float4 *>(s_hid + b * 128 + q * 8);
-                            const float4 hb = *reinterpret_cast<const float4 *>(s_hid + b * 128 + q * 8 + 4);
-                            g = fmaf(wf[0], ha.x, g); g = fmaf(wf[1], ha.y, g); g = fmaf(wf[2], ha.z, g); g = fmaf(wf[3], ha.w, g);
-                            g = fmaf(wf[4], hb.x, g); g = fmaf(wf[5], hb.y, g); g = fmaf(wf[6], hb.z, g); g = fmaf(wf[7], hb.w, g);
+                            acc = se_chain8(wf, *reinterpret_cast<const float4 *>(s_hid + b * 128 + q * 8),
+                                            *reinterpret_cast<const float4 *>(s_hid + b * 128 + q * 8 + 4), acc);
                         }
-                        s_gate[b * NC + c] = se_sigmoid(g);
+                        s_fc2p[o * 4 + k] = acc;
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_sewe);  // the SE weight buffers may be refilled
+                    lat_epi_sync();
+                    if (tid < NB * NC) {
+                        const float *c4 = s_fc2p + tid * 4;
+                        s_gate[tid] = se_sigmoid(se_fc2_sum(L.se_b2[c0 + tid % NC], c4[0], c4[1], c4[2], c4[3]));
+                    }
                     lat_epi_sync();
                     n_se++;
                 }

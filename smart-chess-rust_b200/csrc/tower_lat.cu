@@ -58,12 +58,14 @@ template <int CL, int NB = 2> struct LatCfg {
     static constexpr int NC = 256 / CL;  // output channels per CTA
     static constexpr int HJ = 128 / CL;  // SE hidden units per CTA
     static constexpr int A_BOX = NB * 80 * TC_BK * 2;  // 10 ranks x NB boards x 8 files rows of 128 B
-    static constexpr int NA = 6 / NB;    // activation boxes in flight (the ring is 3 two-board boxes either way)
     static constexpr int B_TILE = 3 * NC * TC_BK * 2;
-    static constexpr int NBS = CL == 8 ? 8 : 4;
+    // one pipeline stage = the activation box and the weight tile of a (channel chunk, dx) step; both loads complete on
+    // the stage's one `full` barrier (a wait on an already complete mbarrier still costs ~90 cycles, and a layer has
+    // only 12 steps), but they are issued by two warps so that the weights can run ahead of the activations
+    static constexpr int STAGE = A_BOX + B_TILE;
+    static constexpr int NS = (160 * 1024) / STAGE;
     static constexpr int W1S_BYTES = 32 * HJ * 16, W2S_BYTES = 16 * NC * 16;
-    static constexpr int OFF_B = NA * A_BOX;
-    static constexpr int OFF_W1S = OFF_B + NBS * B_TILE;
+    static constexpr int OFF_W1S = NS * STAGE;
     static constexpr int OFF_W2S = OFF_W1S + W1S_BYTES;
     static constexpr int OFF_STAT = OFF_W2S + W2S_BYTES;  // float2 [8 chunks][128 rows]
     static constexpr int OFF_PAR = OFF_STAT + 8 * 128 * 8;  // bias, gamma, beta [NC]
@@ -74,7 +76,7 @@ template <int CL, int NB = 2> struct LatCfg {
     static constexpr int OFF_FC2P = OFF_HID + 2 * 128 * 4;      // [2 * NC outputs][4 chunk sums]
     static constexpr int OFF_GATE = OFF_FC2P + 2 * NC * 4 * 4;  // [2][NC]
     static constexpr int OFF_BARS = (OFF_GATE + 2 * NC * 4 + 7) & ~7;
-    static constexpr int N_BARS = 2 * 6 + 2 * NBS + 7;  // sized for the deeper (one-board) activation ring in both variants
+    static constexpr int N_BARS = 2 * 8 + 7;  // up to 8 stages (full, empty) + 7 single barriers, the same in every variant
     static constexpr int SMEM_BYTES = OFF_BARS + N_BARS * 8 + 16;
 };
 
@@ -166,7 +168,8 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs
 {
     using Cfg = LatCfg<CL, NB>;
     constexpr int A_BOX = Cfg::A_BOX, DY_STEP = NB * 1024;  // bytes between the dy taps inside an activation box
-    constexpr int NC = Cfg::NC, NA = Cfg::NA, NBS = Cfg::NBS, B_TILE = Cfg::B_TILE;
+    constexpr int NC = Cfg::NC, NS = Cfg::NS;
+    static_assert(NS >= 3 && NS <= 8, "stage count");
     constexpr int NCH = NC / 32;  // 32-channel chunks per CTA
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t smem_base = smem_u32(smem);
@@ -184,14 +187,12 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::OFF_BARS);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + Cfg::N_BARS);
     const uint32_t bar_base = smem_u32(bars);
-    auto afull = [&](int s) { return bar_base + 8u * s; };
-    auto aempty = [&](int s) { return bar_base + 8u * (NA + s); };
-    auto bfull = [&](int s) { return bar_base + 8u * (2 * NA + s); };
-    auto bempty = [&](int s) { return bar_base + 8u * (2 * NA + NBS + s); };
-    const uint32_t bar_tfull = bar_base + 8u * (2 * NA + 2 * NBS), bar_ready = bar_tfull + 8, bar_stat = bar_tfull + 16,
+    auto full = [&](int s) { return bar_base + 8u * s; };
+    auto empty = [&](int s) { return bar_base + 8u * (8 + s); };
+    const uint32_t bar_tfull = bar_base + 8u * 16, bar_ready = bar_tfull + 8, bar_stat = bar_tfull + 16,
                    bar_mean = bar_tfull + 24, bar_hid = bar_tfull + 32, bar_sewf = bar_tfull + 40, bar_sewe = bar_tfull + 48;
-    auto abox = [&](int s) { return smem_base + (uint32_t)(s * A_BOX); };
-    auto btile = [&](int s) { return smem_base + (uint32_t)(Cfg::OFF_B + s * B_TILE); };
+    auto abox = [&](int s) { return smem_base + (uint32_t)(s * Cfg::STAGE); };
+    auto btile = [&](int s) { return smem_base + (uint32_t)(s * Cfg::STAGE + A_BOX); };
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const uint32_t rank = __shfl_sync(0xffffffffu, cluster_ctarank(), 0);
@@ -199,7 +200,10 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs
     const int n_layers = args.n_layers;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < 2 * NA + 2 * NBS; s++) mbar_init(bar_base + 8u * s, 1);
+        for (int s = 0; s < 8; s++) {
+            mbar_init(full(s), 2);   // the activation producer's and the weight producer's expect_tx arrivals
+            mbar_init(empty(s), 1);  // the MMA warp's commit
+        }
         mbar_init(bar_tfull, 1);
         mbar_init(bar_ready, CL);  // one arrival per CTA of the cluster
         mbar_init(bar_stat, 1);    // armed per layer with the bytes every CTA pushes (st.async)
@@ -233,20 +237,21 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs
                 const long long t0 = args.prof ? clock64() : 0;
                 mbar_wait_cluster(bar_ready, (uint32_t)(l - 1) & 1u);
                 if (args.prof) pa_ready += clock64() - t0;
-                asm volatile("fence.proxy.async;" ::: "memory");
+                // (no proxy fence on this side: the writers fenced generic -> async before they signalled, and the
+                //  acquire above orders the TMA issue after the signal -- the same hand-over as tower_bf16.cu's)
             }
             for (int kc = 0; kc < L.kchunks; kc++)
                 for (int dxi = 0; dxi < nd; dxi++) {
                     const long long t1 = args.prof ? clock64() : 0;
-                    mbar_wait(aempty(st), ph ^ 1u);
+                    mbar_wait(empty(st), ph ^ 1u);
                     if (args.prof) pa_empty += clock64() - t1;
                     if (elect_one()) {
-                        mbar_expect_tx(afull(st), A_BOX);
-                        tma_load_4d(abox(st), NB == 2 ? &L.map_a : &L.map_a1, afull(st), kc * TC_BK, nd == 3 ? dxi - 1 : 0,
+                        mbar_expect_tx(full(st), A_BOX);
+                        tma_load_4d(abox(st), NB == 2 ? &L.map_a : &L.map_a1, full(st), kc * TC_BK, nd == 3 ? dxi - 1 : 0,
                                     tile * NB, -1);
                     }
                     __syncwarp();
-                    if (++st == NA) {
+                    if (++st == NS) {
                         st = 0;
                         ph ^= 1u;
                     }
@@ -265,13 +270,13 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs
             const int nd = L.taps == 9 ? 3 : 1;
             for (int kc = 0; kc < L.kchunks; kc++)
                 for (int dxi = 0; dxi < nd; dxi++) {
-                    mbar_wait(bempty(st), ph ^ 1u);
+                    mbar_wait(empty(st), ph ^ 1u);
                     if (elect_one()) {
-                        mbar_expect_tx(bfull(st), (uint32_t)(nd * NC * TC_BK * 2));
-                        tma_load_4d(btile(st), &L.map_w, bfull(st), kc * TC_BK, (int)rank * NC, dxi, 0);
+                        mbar_expect_tx(full(st), (uint32_t)(nd * NC * TC_BK * 2));
+                        tma_load_4d(btile(st), &L.map_w, full(st), kc * TC_BK, (int)rank * NC, dxi, 0);
                     }
                     __syncwarp();
-                    if (++st == NBS) {
+                    if (++st == NS) {
                         st = 0;
                         ph ^= 1u;
                     }
@@ -280,24 +285,19 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs
     } else if (warp == 2) {
         // ---- MMA issuer: k order (channel chunk, dx, dy, 16-element step) as in tower_bf16.cu ----
         constexpr uint32_t idesc = umma_idesc_bf16(64 * NB, NC);
-        int ra = 0, rb = 0;
-        uint32_t rap = 0, rbp = 0;
-        long long pm_a = 0, pm_a0 = 0, pm_b = 0, pm_total = args.prof ? clock64() : 0;
+        int rs = 0;
+        uint32_t rph = 0;
+        long long pm_a = 0, pm_a0 = 0, pm_total = args.prof ? clock64() : 0;
         for (int l = 0; l < n_layers; l++) {
             const LatLayer &L = args.layers[l];
             const int nd = L.taps == 9 ? 3 : 1;
             uint32_t acc = 0;
             for (int g = 0; g < L.kchunks * nd; g++) {
                 const long long t0 = args.prof ? clock64() : 0;
-                mbar_wait(afull(ra), rap);
-                const long long t1 = args.prof ? clock64() : 0;
-                mbar_wait(bfull(rb), rbp);
-                if (args.prof) {
-                    (g == 0 ? pm_a0 : pm_a) += t1 - t0;
-                    pm_b += clock64() - t1;
-                }
+                mbar_wait(full(rs), rph);
+                if (args.prof) (g == 0 ? pm_a0 : pm_a) += clock64() - t0;
                 tc_fence_after();
-                const uint32_t a0 = abox(ra), b0 = btile(rb);
+                const uint32_t a0 = abox(rs), b0 = btile(rs);
                 if (elect_one()) {
                     for (int dyi = 0; dyi < nd; dyi++) {
                         const uint64_t da = umma_desc_sw128(a0 + (uint32_t)((nd == 3 ? dyi : 1) * DY_STEP));
@@ -307,18 +307,13 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs
                             tc_mma_bf16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
                                         (acc | (uint32_t)dyi | (uint32_t)k) != 0);
                     }
-                    tc_commit(aempty(ra));
-                    tc_commit(bempty(rb));
+                    tc_commit(empty(rs));
                 }
                 __syncwarp();
                 acc = 1;
-                if (++ra == NA) {
-                    ra = 0;
-                    rap ^= 1u;
-                }
-                if (++rb == NBS) {
-                    rb = 0;
-                    rbp ^= 1u;
+                if (++rs == NS) {
+                    rs = 0;
+                    rph ^= 1u;
                 }
             }
             if (elect_one()) tc_commit(bar_tfull);
@@ -327,7 +322,7 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs
         if (args.prof && lane == 0) {
             args.prof[blockIdx.x * 16 + 2] = pm_a0;
             args.prof[blockIdx.x * 16 + 3] = pm_a;
-            args.prof[blockIdx.x * 16 + 4] = pm_b;
+            args.prof[blockIdx.x * 16 + 4] = 0;
             args.prof[blockIdx.x * 16 + 5] = clock64() - pm_total;
         }
     } else if (warp == 3) {
@@ -593,6 +588,11 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------
+template <int CL> constexpr int lat_smem_bytes()
+{
+    return LatCfg<CL, 1>::SMEM_BYTES > LatCfg<CL, 2>::SMEM_BYTES ? LatCfg<CL, 1>::SMEM_BYTES : LatCfg<CL, 2>::SMEM_BYTES;
+}
+
 struct LatTower {
     LatLayer *d_layers[2] = {nullptr, nullptr};  // [0]: CL = 8, [1]: CL = 4
     int n_layers = 0;
@@ -602,12 +602,12 @@ struct LatTower {
 
 template <int CL> static int lat_max_clusters(int *out)
 {
-    SCB_CUDA(cudaFuncSetAttribute(lat_tower_kernel<CL, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, LatCfg<CL>::SMEM_BYTES));
-    SCB_CUDA(cudaFuncSetAttribute(lat_tower_kernel<CL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, LatCfg<CL>::SMEM_BYTES));
+    SCB_CUDA(cudaFuncSetAttribute(lat_tower_kernel<CL, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lat_smem_bytes<CL>()));
+    SCB_CUDA(cudaFuncSetAttribute(lat_tower_kernel<CL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lat_smem_bytes<CL>()));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(CL * 64);
     cfg.blockDim = dim3(LAT_THREADS);
-    cfg.dynamicSmemBytes = LatCfg<CL>::SMEM_BYTES;
+    cfg.dynamicSmemBytes = lat_smem_bytes<CL>();
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL;
@@ -721,7 +721,7 @@ template <int CL, int NB> static int lat_launch(const LatTower *t, int v, int n_
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(n_tiles * CL);
     cfg.blockDim = dim3(LAT_THREADS);
-    cfg.dynamicSmemBytes = LatCfg<CL>::SMEM_BYTES;
+    cfg.dynamicSmemBytes = lat_smem_bytes<CL>();
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -743,7 +743,7 @@ template <int CL, int NB> static int lat_launch(const LatTower *t, int v, int n_
             for (int k = 0; k < 16; k++) acc[k] += (double)h[(size_t)b * 16 + k] / (n_tiles * CL);
         fprintf(stderr,
                 "[lat CL=%d NB=%d tiles=%d layers=%d] A-producer: wait_ready %.0f wait_empty %.0f | mma: total %.0f wait_A(first box) %.0f "
-                "wait_A(rest) %.0f wait_B %.0f | epilogue: wait_tmem_full %.0f work %.0f (tmem load %.0f, stat exchange %.0f, SE %.0f, "
+                "wait(rest) %.0f (%.0f) | epilogue: wait_tmem_full %.0f work %.0f (tmem load %.0f, stat exchange %.0f, SE %.0f, "
                 "proxy fence %.0f, block barrier %.0f, gpu fence + signal %.0f)\n",
                 CL, NB, n_tiles, a.n_layers, acc[0], acc[1], acc[5], acc[2], acc[3], acc[4], acc[6], acc[9], acc[10], acc[7], acc[8],
                 acc[11], acc[12], acc[13]);

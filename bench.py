@@ -527,9 +527,10 @@ def main():
                                  f"an L2 flush + sync, i.e. the kernel is timed alone",
                     # not measured by this run: dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed
                     # ncu --set full capture of this workload
-                    "traffic": (1.644e9 if tower else (95.4e6 + 161.0e6) / 2) if B == 2048 and args.mode == "bf16" else None,
-                    "traffic_source": "constant: ncu --set full capture profiles/r01m_step_full_raw.csv (237 MB read + 1407 MB "
-                                      "written per whole-tower launch); not re-measured by this run",
+                    "traffic": (0.750e9 if tower else (95.4e6 + 161.0e6) / 2) if B == 2048 and args.mode == "bf16" else None,
+                    "traffic_source": "constant: ncu --set full capture profiles/r02_tower_full_raw.csv (236 MB read + 514 MB "
+                                      "written per whole-tower launch; 1644 MB in round 1, profiles/r02_tile_groups.md); not "
+                                      "re-measured by this run",
                     "launches_timed_per_step": conv_n, "avg_launch_ms": conv_avg_ms,
                     "flops_per_launch": B * timed_flops / conv_n,
                     "whole_step_tflops": value / world * FLOP_PER_LEAF / 1e12}

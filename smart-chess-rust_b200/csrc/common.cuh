@@ -62,8 +62,9 @@ int launch_policy_logp_full(const float *logits, int n, float *d_logp /*[n][4672
 
 // ---- tower_f32.cu -------------------------------------------------------------------------
 // C[M][N] = gather_taps(A)[M][TAPS*K] * W[TAPS*K][ldw] + bias ; A is [rows][lda] fp32
+// n_splits > 1 (taps == 1, no bias): split-K over gridDim.z, partial sums to out[split][M][ldo]
 int launch_gemm_f32(int taps, const float *A, int lda, const float *W, int ldw, const float *bias, float *out,
-                    int ldo, int M, int N, int K, cudaStream_t st);
+                    int ldo, int M, int N, int K, cudaStream_t st, int n_splits = 1);
 // planes (optional): the result also as three bf16 planes [rows][3 * C] (hi | mid | lo), the operand format of the
 // tensor-core FP32 parity mode
 int launch_ln_f32(float *x, int rows, int C, int ld, const float *gamma, const float *beta, int relu,
@@ -97,9 +98,19 @@ struct TcGather {
     float *priors;           // same layout as moves
     int n;
 };
+// TC_EPI_RAW with `finish`: the value head's tail (tower_f32.cu's value_finish_kernel) runs inside the split-K GEMM --
+// the CTA that delivers the LAST of a row tile's split-K partial sums adds them up in split order, adds the meta columns
+// and the bias, ReLU, FC 128 -> 1, tanh, white-perspective flip, and writes the values (py/module.py:95-106, 147-149).
+struct TcValueFinish {
+    const float *meta;     // [n][8]
+    const float *w_meta;   // [7][128]
+    const float *b1, *w2, *b2;
+    float *value_out;      // [n]
+    unsigned int *counters;  // one per 128-row tile, zero between launches (the finishing CTA resets its tile's)
+};
 int tc_conv_launch(TcConv *c, const __nv_bfloat16 *in, int rows_alloc, int n_units, void *out,
                    const __nv_bfloat16 *resid, int relu, int n_splits, int num_sms, cudaStream_t st,
-                   const TcGather *gather = nullptr);
+                   const TcGather *gather = nullptr, const TcValueFinish *finish = nullptr);
 
 // whole-tower kernel: every 256-wide convolution of the residual tower in ONE launch (layers in order)
 struct TcTower;

@@ -180,6 +180,9 @@ struct sc_engine {
     cudaEvent_t tickets[SC_MAX_INFLIGHT] = {nullptr, nullptr, nullptr, nullptr};
     int next_ticket = 0;
     int32_t *d_cnt = nullptr;
+    unsigned int *d_vcount = nullptr;  // bf16 mode: arrival counters of the value FC's row tiles (value tail fused into the GEMM)
+    // SCB200_FUSE_VALUE=0 keeps the stand-alone value_finish kernel (A/B runs)
+    bool fuse_value = !(getenv("SCB200_FUSE_VALUE") && getenv("SCB200_FUSE_VALUE")[0] == '0');
     // asynchronous path (sc_eval_submit): two sets of device io buffers + copy streams, so the H2D of batch k+1
     // and the D2H of batch k-1 overlap the kernels of batch k
     struct IoSet {
@@ -430,6 +433,7 @@ static int alloc_buffers(sc_engine *e)
     SCB_CHECK(dev_alloc(e, &e->d_moves, (size_t)e->max_moves_total));
     SCB_CHECK(dev_alloc(e, &e->d_off, (size_t)B + 1));
     SCB_CHECK(dev_alloc(e, &e->d_cnt, (size_t)B + 1));
+    SCB_CHECK(dev_alloc(e, &e->d_vcount, (size_t)(B + 127) / 128 + 1));  // zero-initialised by dev_alloc
     SCB_CHECK(dev_alloc(e, &e->d_priors, (size_t)e->max_moves_total));
     SCB_CHECK(dev_alloc(e, &e->d_index, (size_t)e->max_moves_total));
     SCB_CHECK(dev_alloc(e, &e->d_value, (size_t)B));
@@ -437,7 +441,7 @@ static int alloc_buffers(sc_engine *e)
     SCB_CHECK(dev_alloc(e, &e->logits, (size_t)B * 64 * LD_POLICY));
     const size_t act = (size_t)B * 64 * C_TOWER;
     if (e->mode == SC_MODE_FP32) {
-        e->vsplit = 1;
+        e->vsplit = 16;  // the value FC has only n / 128 row tiles: split K over 16 CTAs each
         if (e->fp32_tc) {
             SCB_CHECK(dev_alloc(e, &e->h_planes, (size_t)B * 64 * C_IN_PAD));
             SCB_CHECK(dev_alloc(e, &e->p_x, act * 3));
@@ -519,7 +523,7 @@ static int run_network(sc_engine *e, int n, cudaStream_t st, const TcGather *gat
         SCB_CHECK(launch_ln_f32(e->logits, rows, C_POLICY, LD_POLICY, e->pol2.gamma, e->pol2.beta, 0, st));
         SCB_CHECK(conv(e->val1, e->p_x, e->f_y, 1, nullptr, false));
         SCB_CHECK(launch_gemm_f32(1, e->f_y, 64 * C_TOWER, e->vfc_w_f32, N_VALUE_HIDDEN, nullptr, e->vpre,
-                                  N_VALUE_HIDDEN, n, N_VALUE_HIDDEN, 64 * C_TOWER, st));
+                                  N_VALUE_HIDDEN, n, N_VALUE_HIDDEN, 64 * C_TOWER, st, e->vsplit));
         e->launches += 3;
     } else if (e->mode == SC_MODE_FP32) {
         auto conv = [&](const ConvW &c, const float *in, int lda, float *out, int relu) -> int {
@@ -555,7 +559,7 @@ static int run_network(sc_engine *e, int n, cudaStream_t st, const TcGather *gat
         // value head
         SCB_CHECK(conv(e->val1, e->f_x, C_TOWER, e->f_y, 1));
         SCB_CHECK(launch_gemm_f32(1, e->f_y, 64 * C_TOWER, e->vfc_w_f32, N_VALUE_HIDDEN, nullptr, e->vpre,
-                                  N_VALUE_HIDDEN, n, N_VALUE_HIDDEN, 64 * C_TOWER, st));
+                                  N_VALUE_HIDDEN, n, N_VALUE_HIDDEN, 64 * C_TOWER, st, e->vsplit));
         e->launches += 3;
     } else {
         const int nb = e->alloc_boards;
@@ -610,6 +614,14 @@ static int run_network(sc_engine *e, int n, cudaStream_t st, const TcGather *gat
             e->launches += 2;
         }
         SCB_CHECK(tc_conv_launch(e->pol2.tc, e->h_t, nb, n, e->logits, nullptr, 0, 1, e->num_sms, st, gather));
+        // one row tile (n <= 128): the GEMM finishes the value head itself and a launch is saved; with more tiles the
+        // stand-alone kernel spreads the tail over the whole chip and is faster (28 vs 53 us at 2048).  Same bits either way.
+        if (e->fuse_value && n <= 128) {
+            const TcValueFinish vf{e->d_meta, e->v_wmeta, e->v_b1, e->v_w2, e->v_b2, e->d_value, e->d_vcount};
+            SCB_CHECK(tc_conv_launch(e->vfc_tc, e->h_y, nb, n, e->vpre, nullptr, 0, e->vsplit, e->num_sms, st, nullptr, &vf));
+            e->launches += 2;
+            return SC_OK;
+        }
         SCB_CHECK(tc_conv_launch(e->vfc_tc, e->h_y, nb, n, e->vpre, nullptr, 0, e->vsplit, e->num_sms, st));
         e->launches += 2;
     }

@@ -108,6 +108,7 @@ struct TcArgs {
     int n_layers;
     int group;                           // TOWER: tiles per CTA carried through all layers together (0 = all)
     TcGather gather;                     // EPI_LN73_GATHER: legal moves in, priors out
+    TcValueFinish vfin;                  // EPI_RAW: value head tail fused into the split-K GEMM (counters != nullptr)
 };
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -621,6 +622,77 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         for (int q = 0; q < 4; q++)
                             v[q] = make_uint4(r[hf * 16 + 4 * q], r[hf * 16 + 4 * q + 1], r[hf * 16 + 4 * q + 2], r[hf * 16 + 4 * q + 3]);
                         staged_store_64B(stg, lane, v, gbase + (ch * 32 + hf * 16) * 4, (size_t)BN * 4, rows_valid);
+                    }
+                }
+                if (args.vfin.counters) {
+                    // ---- value head tail: the CTA that delivers the last split of this row tile finishes the tile.
+                    //      Everybody's partial sums are made visible (fence), one thread counts the tile's arrivals. ----
+                    const TcValueFinish &F = args.vfin;
+                    __threadfence();
+                    asm volatile("bar.sync 2, 128;" ::: "memory");
+                    unsigned int *s_flag = reinterpret_cast<unsigned int *>(s_stat);
+                    if (te == 0) {
+                        const unsigned int old = atomicAdd(F.counters + tile, 1u);
+                        const bool last = old == (unsigned int)args.n_splits - 1u;
+                        if (last) F.counters[tile] = 0u;  // ready for the next launch
+                        *s_flag = last ? 1u : 0u;
+                    }
+                    asm volatile("bar.sync 2, 128;" ::: "memory");
+                    const bool last = *s_flag != 0u;
+                    asm volatile("bar.sync 2, 128;" ::: "memory");  // the flag is read before the next work item overwrites it
+                    if (last) {
+                        // warp = rows quad, quad + 4, ... of the tile; lane = hidden units 4 lane .. 4 lane + 3 (one
+                        // coalesced 512-byte row per load instruction, eight splits and four rows in flight)
+                        __threadfence();
+                        const float *pre = static_cast<const float *>(args.out);
+                        const int nsp = args.n_splits;
+                        float wm[SC_N_META][4], b1v[4], w2v[4];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            b1v[i] = F.b1[4 * lane + i];
+                            w2v[i] = F.w2[4 * lane + i];
+#pragma unroll
+                            for (int k = 0; k < SC_N_META; k++) wm[k][i] = F.w_meta[k * BN + 4 * lane + i];
+                        }
+                        const float b2 = F.b2[0];
+                        const int wq = warp - 2;  // 0..3
+#pragma unroll 1
+                        for (int r0 = wq; r0 < TC_BM; r0 += 16) {
+                            float4 h[4];
+                            int grow[4];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                grow[u] = tile * TC_BM + r0 + 4 * u;
+                                h[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+                            for (int sp = 0; sp < nsp; sp++) {  // split order: a fixed fp32 sum
+#pragma unroll
+                                for (int u = 0; u < 4; u++)
+                                    if (grow[u] < args.m_rows) {
+                                        const float4 p = __ldcg(reinterpret_cast<const float4 *>(pre + ((size_t)sp * args.m_rows + grow[u]) * BN) + lane);
+                                        h[u].x += p.x;
+                                        h[u].y += p.y;
+                                        h[u].z += p.z;
+                                        h[u].w += p.w;
+                                    }
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                if (grow[u] >= args.m_rows) continue;  // warp-uniform
+                                const float *mt = F.meta + (size_t)grow[u] * 8;
+                                float hv[4] = {h[u].x, h[u].y, h[u].z, h[u].w};
+                                float acc = 0.f;
+#pragma unroll
+                                for (int i = 0; i < 4; i++) {
+#pragma unroll
+                                    for (int k = 0; k < SC_N_META; k++) hv[i] = fmaf(wm[k][i], mt[k], hv[i]);
+                                    acc = fmaf(w2v[i], fmaxf(hv[i] + b1v[i], 0.f), acc);
+                                }
+#pragma unroll
+                                for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                                if (lane == 0) F.value_out[grow[u]] = tanhf(acc + b2) * (mt[0] * 2.f - 1.f);
+                            }
+                        }
                     }
                 }
             } else if constexpr (EPI == EPI_LN73_GATHER) {
@@ -1420,7 +1492,8 @@ int tc_tower_launch(TcTower *t, int n_boards, int num_sms, int group, cudaStream
 }
 
 int tc_conv_launch(TcConv *c, const __nv_bfloat16 *in, int rows_alloc, int n_units, void *out,
-                   const __nv_bfloat16 *resid, int relu, int n_splits, int num_sms, cudaStream_t st, const TcGather *gather)
+                   const __nv_bfloat16 *resid, int relu, int n_splits, int num_sms, cudaStream_t st, const TcGather *gather,
+                   const TcValueFinish *finish)
 {
     if (n_units <= 0) return SC_OK;
     const bool a4d = c->epi != EPI_RAW;
@@ -1536,6 +1609,7 @@ int tc_conv_launch(TcConv *c, const __nv_bfloat16 *in, int rows_alloc, int n_uni
             tc_gemm_kernel<LD_POLICY, EPI_LN73, true><<<grid, TC_THREADS, TcCfg<LD_POLICY>::SMEM_BYTES, st>>>(*ma, c->map_w, a);
         break;
     case EPI_RAW:
+        if (finish) a.vfin = *finish;
         tc_gemm_kernel<N_VALUE_HIDDEN, EPI_RAW, false><<<grid, TC_THREADS, TcCfg<N_VALUE_HIDDEN>::SMEM_BYTES, st>>>(
             *ma, c->map_w, a);
         break;

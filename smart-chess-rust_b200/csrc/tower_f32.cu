@@ -41,6 +41,10 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float *__restrict__
     __shared__ __align__(16) float Bs[GBK][GBN];
     const int tid = threadIdx.x;
     const int m0 = blockIdx.x * GBM, n0 = blockIdx.y * GBN;
+    // split-K (TAPS == 1 only): slice blockIdx.z of the K range, partial sums to out[z][M][ldo]
+    A += (size_t)blockIdx.z * K;
+    W += (size_t)blockIdx.z * K * ldw;
+    out += (size_t)blockIdx.z * M * ldo;
     const int ty = tid >> 4, tx = tid & 15;
 
     // A loader: thread -> (row, 8 consecutive k)
@@ -111,14 +115,22 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float *__restrict__
 }
 
 int launch_gemm_f32(int taps, const float *A, int lda, const float *W, int ldw, const float *bias, float *out,
-                    int ldo, int M, int N, int K, cudaStream_t st)
+                    int ldo, int M, int N, int K, cudaStream_t st, int n_splits)
 {
     if (M <= 0) return SC_OK;
+    if (n_splits > 1) {
+        if (taps != 1 || bias || K % n_splits) {
+            set_error("gemm_f32: split-K needs taps == 1, no bias and K divisible by the split count");
+            return SC_E_INVAL;
+        }
+        K /= n_splits;
+    } else
+        n_splits = 1;
     if (K % GBK != 0 || ldw % GBN != 0 || (lda & 3)) {
         set_error("gemm_f32: K must be a multiple of 16, ldw of 128, lda of 4");
         return SC_E_INVAL;
     }
-    dim3 grid((M + GBM - 1) / GBM, (N + GBN - 1) / GBN);
+    dim3 grid((M + GBM - 1) / GBM, (N + GBN - 1) / GBN, n_splits);
     if (taps == 9)
         gemm_f32_kernel<9><<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, out, ldo, M, N, K);
     else
@@ -253,19 +265,29 @@ __global__ void __launch_bounds__(128) value_finish_kernel(const float *__restri
                                                            const float *__restrict__ b2,
                                                            float *__restrict__ value_out)
 {
+    // lane = hidden units 4 lane .. 4 lane + 3: one coalesced 512-byte row per split.  The arithmetic (split-order sum,
+    // meta fma chain, + b1, ReLU, fma with w2 over the lane's four units, xor-shuffle sum) is, operation for operation,
+    // the fused tail of the bf16 value-FC GEMM (tower_bf16.cu, EPI_RAW): small batches use that one, large batches
+    // this kernel, and a leaf's value must not depend on which.
     const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (b >= n) return;
     const float *mt = meta + b * 8;
+    float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int sp = 0; sp < n_split; sp++) {
+        const float4 p = __ldcg(reinterpret_cast<const float4 *>(pre + ((size_t)sp * n + b) * N_VALUE_HIDDEN) + lane);
+        h.x += p.x;
+        h.y += p.y;
+        h.z += p.z;
+        h.w += p.w;
+    }
+    float hv[4] = {h.x, h.y, h.z, h.w};
     float acc = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        int j = lane + 32 * i;
-        float hsum = 0.f;
-        for (int sp = 0; sp < n_split; sp++) hsum += pre[((size_t)sp * n + b) * N_VALUE_HIDDEN + j];
+        const int j = 4 * lane + i;
 #pragma unroll
-        for (int k = 0; k < SC_N_META; k++) hsum = fmaf(w_meta[k * N_VALUE_HIDDEN + j], mt[k], hsum);
-        hsum += b1[j];
-        acc = fmaf(w2[j], fmaxf(hsum, 0.f), acc);
+        for (int k = 0; k < SC_N_META; k++) hv[i] = fmaf(w_meta[k * N_VALUE_HIDDEN + j], mt[k], hv[i]);
+        acc = fmaf(w2[j], fmaxf(hv[i] + b1[j], 0.f), acc);
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);

@@ -516,3 +516,33 @@ def test_bf16_mode_deviation_is_operand_rounding(co, nets, positions):
         assert d_f32 < BF16_TOL
         assert d_emu < 1e-2
         assert d_f32 < 4 * d_ref + 1e-4          # same order as the rounding the reference's bf16 path has
+
+
+def test_fused_value_tail_matches_standalone_kernel(co, nets, positions, monkeypatch):
+    """bf16 mode, single-tile batches (n <= 128): the value head is finished inside the split-K value-FC GEMM (the CTA
+    delivering the last split of the row tile sums the partials in split order, adds meta columns + bias, ReLU,
+    FC 128 -> 1, tanh) and a launch is saved.  Larger batches use the stand-alone value_finish kernel.  Both must produce
+    the same bits (a leaf's value must not depend on the batch it travels in), also repeatedly (the arrival counters
+    reset themselves)."""
+    import scb200
+
+    out = {}
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("SCB200_FUSE_VALUE", fuse)
+        e = scb200.Engine(nets["n2"][1], 0, scb200.SC_MODE_BF16, 512)
+        try:
+            res = []
+            for n in (1, 127, 128, 129, 333, 129):
+                games = positions[2::3][:n]
+                pos, moves, off, _ = games_to_batch(games)
+                l0 = e.launch_count()
+                pri, val = e.eval(pos, moves, off)
+                res.append((pri.copy(), val.copy(), e.launch_count() - l0))
+            out[fuse] = res
+        finally:
+            e.close()
+    for a, b, n in zip(out["1"], out["0"], (1, 127, 128, 129, 333, 129)):
+        assert a[2] == b[2] - (1 if n <= 128 else 0)      # the fused tail serves single-tile batches
+        assert np.array_equal(a[0], b[0])
+        assert np.array_equal(a[1], b[1]) and np.isfinite(a[1]).all()   # operation for operation the same arithmetic
+    assert np.array_equal(out["1"][3][1], out["1"][5][1])        # same batch again: identical

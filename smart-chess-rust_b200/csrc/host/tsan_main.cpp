@@ -59,9 +59,14 @@ static int run(bool arena, int threads, int leaves_per_tree)
     return ok ? 0 : 1;
 }
 
-int main()
+int main(int argc, char **argv)
 {
     int bad = 0;
+    if (argc > 1) {  // `prof`: one single-threaded self-play run (the gprof target of `make hostprof`)
+        bad = run(false, 1, 1);
+        printf(bad ? "FAILED\n" : "host profile run ok\n");
+        return bad;
+    }
     bad += run(false, 8, 1);
     bad += run(false, 8, 4);
     bad += run(true, 8, 1);

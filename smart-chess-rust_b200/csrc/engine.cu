@@ -193,6 +193,9 @@ struct sc_engine {
         cudaEvent_t in_done = nullptr, compute_done = nullptr, out_done = nullptr;
     } io[2];
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    // small batches: the value head runs on its own stream next to the policy head (both are a few CTAs wide)
+    cudaStream_t head_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int64_t n_submits = 0;
     // small batches (sc_eval with n <= SC_SMALL_N): inputs are packed into ONE pinned staging buffer and travel in one
     // copy, values + priors come back in one copy (a caller's Vec / numpy array is pageable memory, which would
@@ -452,7 +455,7 @@ static int alloc_buffers(sc_engine *e)
         SCB_CHECK(dev_alloc(e, &e->f_t, act));
         SCB_CHECK(dev_alloc(e, &e->f_y, act));
     } else {
-        e->vsplit = 8;
+        e->vsplit = 16;  // 16 k-blocks per work item: 16 CTAs share the 4 MB of value-FC weights even for one leaf
         SCB_CHECK(dev_alloc(e, &e->h_planes, (size_t)B * 64 * C_IN_PAD));
         SCB_CHECK(dev_alloc(e, &e->h_x, act));
         SCB_CHECK(dev_alloc(e, &e->h_t, act));
@@ -613,15 +616,26 @@ static int run_network(sc_engine *e, int n, cudaStream_t st, const TcGather *gat
             SCB_CHECK(tc_conv_launch(e->val1.tc, e->h_x, nb, n, e->h_y, nullptr, 1, 1, e->num_sms, st));
             e->launches += 2;
         }
-        SCB_CHECK(tc_conv_launch(e->pol2.tc, e->h_t, nb, n, e->logits, nullptr, 0, 1, e->num_sms, st, gather));
-        // one row tile (n <= 128): the GEMM finishes the value head itself and a launch is saved; with more tiles the
-        // stand-alone kernel spreads the tail over the whole chip and is faster (28 vs 53 us at 2048).  Same bits either way.
+        // one row tile (n <= 128): the value-FC GEMM finishes the value head itself (a launch is saved) and runs on its own
+        // stream NEXT TO the policy head -- both are a few CTAs wide.  With more tiles the stand-alone tail kernel spreads
+        // over the whole chip and is faster (28 vs 53 us at 2048), and the two heads each fill the chip.  Same bits either way.
         if (e->fuse_value && n <= 128) {
             const TcValueFinish vf{e->d_meta, e->v_wmeta, e->v_b1, e->v_w2, e->v_b2, e->d_value, e->d_vcount};
-            SCB_CHECK(tc_conv_launch(e->vfc_tc, e->h_y, nb, n, e->vpre, nullptr, 0, e->vsplit, e->num_sms, st, nullptr, &vf));
+            if (!e->head_stream) {
+                SCB_CUDA(cudaStreamCreateWithFlags(&e->head_stream, cudaStreamNonBlocking));
+                SCB_CUDA(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+                SCB_CUDA(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+            }
+            SCB_CUDA(cudaEventRecord(e->ev_fork, st));
+            SCB_CUDA(cudaStreamWaitEvent(e->head_stream, e->ev_fork, 0));
+            SCB_CHECK(tc_conv_launch(e->vfc_tc, e->h_y, nb, n, e->vpre, nullptr, 0, e->vsplit, e->num_sms, e->head_stream, nullptr, &vf));
+            SCB_CUDA(cudaEventRecord(e->ev_join, e->head_stream));
+            SCB_CHECK(tc_conv_launch(e->pol2.tc, e->h_t, nb, n, e->logits, nullptr, 0, 1, e->num_sms, st, gather));
+            SCB_CUDA(cudaStreamWaitEvent(st, e->ev_join, 0));
             e->launches += 2;
             return SC_OK;
         }
+        SCB_CHECK(tc_conv_launch(e->pol2.tc, e->h_t, nb, n, e->logits, nullptr, 0, 1, e->num_sms, st, gather));
         SCB_CHECK(tc_conv_launch(e->vfc_tc, e->h_y, nb, n, e->vpre, nullptr, 0, e->vsplit, e->num_sms, st));
         e->launches += 2;
     }
@@ -786,6 +800,9 @@ int sc_destroy(sc_engine *e)
         if (s.compute_done) cudaEventDestroy(s.compute_done);
         if (s.out_done) cudaEventDestroy(s.out_done);
     }
+    if (e->head_stream) cudaStreamDestroy(e->head_stream);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
     if (e->copy_in) cudaStreamDestroy(e->copy_in);
     if (e->copy_out) cudaStreamDestroy(e->copy_out);
     if (e->stream) cudaStreamDestroy(e->stream);

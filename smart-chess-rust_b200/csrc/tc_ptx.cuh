@@ -303,20 +303,35 @@ __device__ __forceinline__ float2 warp_transpose_reduce_2boards(float (&v)[32], 
 // ---- LayerNorm arithmetic shared by both kernels -------------------------------------------------------------
 // Written with explicit round-to-nearest intrinsics so that the compiler cannot contract / reassociate it
 // differently in different kernels: the latency kernel must produce the bits of the throughput kernel.
-// Statistics: per 32-channel chunk k the sums (s_k, q_k) of a = acc + bias and a * a (ln_chunk_stats); combined as
+// Statistics: per 32-channel chunk k the sums (s_k, q_k) of a = acc + bias and a * a (ln_chunk_stats: two 16-channel
+// halves, each four interleaved chains and a tree); combined as
 //   half0 = (p0 + p1) + (p2 + p3), half1 = (p4 + p5) + (p6 + p7), total = half0 + half1
 // -- a fixed tree, so the chunks may be computed by different threads / CTAs.
-__device__ __forceinline__ void ln_chunk_stats(const float (&a)[32], float &s, float &q)
+// half a chunk: 16 channels as four interleaved sequential chains (j mod 4) and a fixed tree
+__device__ __forceinline__ void ln_half_chunk_stats(const float *a /*[16]*/, float &s, float &q)
 {
-    // four interleaved sequential chains (j mod 4) and a fixed tree: a quarter of the dependent-add latency of one chain
     float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int j = 0; j < 32; j++) {
+    for (int j = 0; j < 16; j++) {
         s4[j & 3] = __fadd_rn(s4[j & 3], a[j]);
         q4[j & 3] = __fmaf_rn(a[j], a[j], q4[j & 3]);
     }
     s = __fadd_rn(__fadd_rn(s4[0], s4[1]), __fadd_rn(s4[2], s4[3]));
     q = __fadd_rn(__fadd_rn(q4[0], q4[1]), __fadd_rn(q4[2], q4[3]));
+}
+// a 32-channel chunk = its two halves added (the latency kernel computes the halves in two threads)
+__device__ __forceinline__ float2 ln_join_halves(const float2 h0, const float2 h1)
+{
+    return make_float2(__fadd_rn(h0.x, h1.x), __fadd_rn(h0.y, h1.y));
+}
+__device__ __forceinline__ void ln_chunk_stats(const float (&a)[32], float &s, float &q)
+{
+    float2 h0, h1;
+    ln_half_chunk_stats(a, h0.x, h0.y);
+    ln_half_chunk_stats(a + 16, h1.x, h1.y);
+    const float2 c = ln_join_halves(h0, h1);
+    s = c.x;
+    q = c.y;
 }
 __device__ __forceinline__ float2 ln_half(const float2 p0, const float2 p1, const float2 p2, const float2 p3)
 {

@@ -20,6 +20,8 @@
 //     activations: their producer warp runs ahead through the layers as far as its ring allows.
 // A tile of ONE board (NB = 1: 64 rows, tcgen05.mma M64) halves the shared-memory operand traffic that bounds the MMA
 // phase at these narrow N; it is used while there are enough clusters for one board each.
+// (An epilogue of eight warps -- two per TMEM quadrant, half of the CTA's channels each -- was built and measured: the
+// per-thread work halves, but twice as many threads fence and push statistics; 541 k cycles per call against 524 k.)
 // Warp roles (256 threads): 0 = activation TMA, 1 = weight TMA, 2 = TMEM allocator + MMA issuer, 3 = SE weight
 // staging, 4..7 = epilogue (one thread per row of the tile).
 #include <cstdio>
@@ -226,6 +228,7 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
+        if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(NB == 2 ? &args.layers[0].map_a : &args.layers[0].map_a1) : "memory");
         // ---- activation boxes: wait until the whole cluster has written the previous layer ----
         int st = 0;
         uint32_t ph = 0;
@@ -256,6 +259,11 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs
                         ph ^= 1u;
                     }
                 }
+            // the next layer's tensor map (a different 128-byte descriptor per layer) would otherwise be fetched from
+            // L2 on the critical path right after the hand-over
+            if (l + 1 < n_layers && lane == 0)
+                asm volatile("prefetch.tensormap [%0];" ::"l"(NB == 2 ? &args.layers[l + 1].map_a : &args.layers[l + 1].map_a1)
+                             : "memory");
         }
         if (args.prof && lane == 0) {
             args.prof[blockIdx.x * 16 + 0] = pa_ready;
@@ -268,6 +276,7 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs
         for (int l = 0; l < n_layers; l++) {
             const LatLayer &L = args.layers[l];
             const int nd = L.taps == 9 ? 3 : 1;
+            if (l + 1 < n_layers && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&args.layers[l + 1].map_w) : "memory");
             for (int kc = 0; kc < L.kchunks; kc++)
                 for (int dxi = 0; dxi < nd; dxi++) {
                     mbar_wait(empty(st), ph ^ 1u);
@@ -371,6 +380,12 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs
                 const uint4 *xg = reinterpret_cast<const uint4 *>(L.resid + grow * 256 + c0);
 #pragma unroll
                 for (int i = 0; i < NC / 8; i++) xres[i] = xg[i];
+            }
+            // SE biases of this thread's hidden unit / channel: global loads, requested a whole MMA phase before their use
+            float se_b1v = 0.f, se_b2v = 0.f;
+            if (L.se == 1) {
+                se_b1v = L.se_b1[tid];
+                se_b2v = L.se_b2[c0 + tid % NC];
             }
             if (tid == 0) {
                 // arm this layer's exchange barriers with the bytes the cluster will push into this CTA
@@ -494,7 +509,7 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs
 #pragma unroll
                         for (int b = 0; b < NB; b++) {
                             const float *p = s_hidp + b * 128 + j;  // chunk k at p[k * 256]
-                            s_hid[b * 128 + j] = se_hidden(L.se_b1[j], se_tree4(p[0], p[256], p[512], p[768]),
+                            s_hid[b * 128 + j] = se_hidden(se_b1v, se_tree4(p[0], p[256], p[512], p[768]),
                                                            se_tree4(p[1024], p[1280], p[1536], p[1792]));
                         }
                     }
@@ -520,7 +535,7 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs
                     lat_epi_sync();
                     if (tid < NB * NC) {
                         const float *c4 = s_fc2p + tid * 4;
-                        s_gate[tid] = se_sigmoid(se_fc2_sum(L.se_b2[c0 + tid % NC], c4[0], c4[1], c4[2], c4[3]));
+                        s_gate[tid] = se_sigmoid(se_fc2_sum(se_b2v, c4[0], c4[1], c4[2], c4[3]));
                     }
                     lat_epi_sync();
                     n_se++;

@@ -174,13 +174,14 @@ class Engine:
              stream: int = 0):
         """`predict` for n leaves: returns (priors CSR float32, values float32[n])."""
         n = len(positions)
-        positions = np.ascontiguousarray(positions, dtype=POSITION_DTYPE) if not hasattr(positions, "data_ptr") else positions
         # numpy inputs are coerced to the ABI's element types (an int64 move_off or a strided view would otherwise be
-        # reinterpreted); torch tensors (pinned host buffers of bench.py) are taken as they are
-        if not hasattr(moves, "data_ptr"):
-            moves = np.ascontiguousarray(moves, dtype=MOVE_DTYPE)
-        if not hasattr(move_off, "data_ptr"):
-            move_off = np.ascontiguousarray(move_off, dtype=np.int32)
+        # reinterpreted) unless they already have them; torch tensors (pinned host buffers of bench.py) are taken as they are
+        def _as(a, dt):
+            if hasattr(a, "data_ptr") or (a.dtype == dt and a.flags.c_contiguous):
+                return a
+            return np.ascontiguousarray(a, dtype=dt)
+
+        positions, moves, move_off = _as(positions, POSITION_DTYPE), _as(moves, MOVE_DTYPE), _as(move_off, np.int32)
         total = int(move_off[n]) if n else 0
         if priors_out is None:
             priors_out = np.zeros(max(total, 1), dtype=np.float32)

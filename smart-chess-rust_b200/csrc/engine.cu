@@ -875,7 +875,7 @@ int sc_eval(sc_engine *e, int n, const sc_position *pos, const sc_move *moves, c
     }
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
     SCB_CUDA(cudaSetDevice(e->device));
-    if (n <= SC_SMALL_N) {
+    if (n <= SC_SMALL_N && total <= n * SC_MAX_MOVES) {  // (the staging buffers hold SC_MAX_MOVES moves per leaf)
         // latency path: [positions | offsets | moves] in one copy, [values | priors] back in one copy
         const size_t pos_b = sizeof(sc_position) * (size_t)n, off_b = sizeof(int32_t) * (size_t)(n + 1);
         const size_t mv_b = sizeof(sc_move) * (size_t)total;

@@ -355,3 +355,35 @@ def test_rules_against_python_chess_goldens(co):
         gold = json.load(f)
     assert gold["n_plies"] >= 13000
     assert _check_games(co, gold["games"], check_oracle=True) == gold["n_plies"]
+
+
+def test_move_order_of_the_reference_notebook_trace(co):
+    """notebooks/verify_model.ipynb holds the first ten plies of a trace the reference produced on real python-chess:
+    per ply the root's children in `predict`'s order = python-chess' legal-move generation order.  Both rule engines must
+    reproduce all ten lists (19 - 36 moves; queen sorties, pawn captures) while replaying the moves, and the 40-ply game of
+    notebooks/visualize_mcts.ipynb must replay as legal moves (tests/golden/notebook_traces.json, made by
+    oracle/make_golden_notebooks.py).  These are the only python-chess-made move lists available offline."""
+    import json
+
+    import scb200
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "notebook_traces.json")) as f:
+        gold = json.load(f)
+    g = co.Game()
+    hist = []
+    assert len(gold["verify_model_trace"]) == 10
+    for ply, st in enumerate(gold["verify_model_trace"]):
+        assert g.legal_uci() == st["children"], ply
+        mv, pos, _ = scb200.rules_probe(hist)
+        assert [co.uci(m) for m in mv] == st["children"], ply
+        assert st["move"] in st["children"]
+        g.push(st["move"])
+        hist.append(tuple(int(v) for v in co.parse_uci(st["move"])))
+    g = co.Game()
+    hist = []
+    for u in gold["visualize_mcts_game"]:
+        assert u in g.legal_uci(), u
+        mv, _, _ = scb200.rules_probe(hist)
+        assert u in [co.uci(m) for m in mv]
+        g.push(u)
+        hist.append(tuple(int(v) for v in co.parse_uci(u)))

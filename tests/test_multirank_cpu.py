@@ -57,3 +57,27 @@ def test_two_ranks_gloo(tmp_path):
     assert d["tot"]["games_finished"] == 7
     assert d["tot"]["moves"] == 7 * 10
     assert d["tot"]["rollouts"] == 7 * 10 * 12
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the oracle port on the host cores) needs no GPU: one JSON line with the keys the
+    driver reads, `config` identical in shape to the GPU arm's, the real step size when it fits the time budget."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--leaves", "64"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "leaf_evals_per_s" and d["unit"] == "leaf evals/s"
+    assert d["higher_is_better"] is True and d["steps"] == 1 and d["value"] > 0 and d["vs_baseline"] is None
+    assert d["config"]["leaves_per_step"] == 64 and "workload" in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["leaves_per_step_run"] == 64
+    assert cb["batch1_value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": "leaf evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

@@ -770,11 +770,12 @@ template <int CL, int NB> static int lat_launch(const LatTower *t, int v, int n_
 int lat_tower_launch(LatTower *t, int n_boards, cudaStream_t st, int max_layers)
 {
     if (n_boards <= 0) return SC_OK;
-    // widest split first; one-board tiles (half the operand traffic per CTA) while every board can have a cluster
+    // one-board tiles (half the operand traffic per CTA) while every board can have a cluster -- 8 CTAs per board, then 4
+    // (measured, n = 16: 0.418 ms against 0.433 ms for two boards per 8-CTA cluster) -- then two-board tiles
     const int n_tiles = (n_boards + 1) / 2;
     if (t->one_board && n_boards <= t->max_tiles[0]) return lat_launch<8, 1>(t, 0, n_boards, st, max_layers);
-    if (n_tiles <= t->max_tiles[0]) return lat_launch<8, 2>(t, 0, n_tiles, st, max_layers);
     if (t->one_board && n_boards <= t->max_tiles[1]) return lat_launch<4, 1>(t, 1, n_boards, st, max_layers);
+    if (n_tiles <= t->max_tiles[0]) return lat_launch<8, 2>(t, 0, n_tiles, st, max_layers);
     if (n_tiles <= t->max_tiles[1]) return lat_launch<4, 2>(t, 1, n_tiles, st, max_layers);
     return SC_E_STATE;
 }

@@ -665,16 +665,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                 grow[u] = tile * TC_BM + r0 + 4 * u;
                                 h[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                             }
-                            for (int sp = 0; sp < nsp; sp++) {  // split order: a fixed fp32 sum
+                            // split order: a fixed fp32 sum; the loads of four splits are issued together (a split-at-a-time
+                            // loop exposes one L2 latency per split: 16 x 0.35 us on the one-leaf path)
+                            for (int sp0 = 0; sp0 < nsp; sp0 += 4) {
+                                float4 p[4][4];
 #pragma unroll
-                                for (int u = 0; u < 4; u++)
-                                    if (grow[u] < args.m_rows) {
-                                        const float4 p = __ldcg(reinterpret_cast<const float4 *>(pre + ((size_t)sp * args.m_rows + grow[u]) * BN) + lane);
-                                        h[u].x += p.x;
-                                        h[u].y += p.y;
-                                        h[u].z += p.z;
-                                        h[u].w += p.w;
-                                    }
+                                for (int d = 0; d < 4; d++)
+#pragma unroll
+                                    for (int u = 0; u < 4; u++)
+                                        p[d][u] = (sp0 + d < nsp && grow[u] < args.m_rows)
+                                                      ? __ldcg(reinterpret_cast<const float4 *>(pre + ((size_t)(sp0 + d) * args.m_rows + grow[u]) * BN) + lane)
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                                for (int d = 0; d < 4; d++)
+#pragma unroll
+                                    for (int u = 0; u < 4; u++)
+                                        if (sp0 + d < nsp) {  // (x + 0 is exact, but keep the operation count of the kernel form)
+                                            h[u].x += p[d][u].x;
+                                            h[u].y += p[d][u].y;
+                                            h[u].z += p[d][u].z;
+                                            h[u].w += p[d][u].w;
+                                        }
                             }
 #pragma unroll
                             for (int u = 0; u < 4; u++) {

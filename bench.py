@@ -543,6 +543,30 @@ def main():
                     "leaf_evals_per_s": sus["steps"] * B / sus["seconds"], "seconds": sus["seconds"], "steps": sus["steps"],
                     "avg_launch_ms": sus["conv_ms_total"] / sus["steps"] / conv_n}
             if args.mode == "fp32":
+                # the fp32 peaks are not in MEASURED_PEAKS.json -- measure them on this box, the way the
+                # driver measured the bf16 one (torch.matmul 8192^3, best of 5, CUDA events): FP32 on the CUDA cores (cuBLAS
+                # SGEMM, TF32 off) and TF32 on the tensor cores
+                def _matmul_peak(tf32):
+                    old = torch.backends.cuda.matmul.allow_tf32
+                    torch.backends.cuda.matmul.allow_tf32 = tf32
+                    a = torch.randn(8192, 8192, device=f"cuda:{local_rank}")
+                    b = torch.randn(8192, 8192, device=f"cuda:{local_rank}")
+                    best = 0.0
+                    for it in range(6):
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                        torch.matmul(a, b)
+                        e1.record()
+                        e1.synchronize()
+                        if it:
+                            best = max(best, 2 * 8192 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+                    torch.backends.cuda.matmul.allow_tf32 = old
+                    return best
+                ffma_peak, tf32_peak = _matmul_peak(False), _matmul_peak(True)
+                roof["fp32_peaks_measured_here"] = {
+                    "fp32_ffma_tflops": ffma_peak, "tf32_tflops": tf32_peak, "how": "torch.matmul fp32 8192^3, best of 5, TF32 off / on",
+                    "achieved_over_fp32_ffma_peak": ach / ffma_peak if ffma_peak else None,
+                    "achieved_over_tf32_peak_div_3": ach / (tf32_peak / 3) if tf32_peak else None}
                 roof["kernel"] = ("tc_gemm_kernel<256, EPI_F32, pair>: 3x3 256->256 conv as a bf16x3 split GEMM (6 tcgen05 bf16 products "
                                   "per fp32 product, fp32 accumulate in TMEM), one launch per layer; LayerNorm / SE in fp32 kernels")
                 roof["traffic"] = None

@@ -108,26 +108,30 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) encode_f32_kernel(const sc_pos
     if (lane < 8) meta_out[b * 8 + lane] = lane < SC_N_META ? (float)pos[b].meta[lane] : 0.f;
 }
 
+// bf16 form (the network's own input): FOUR warps per position, 16 squares each.  The kernel is short (34 MB at 2048
+// leaves) and ends in a store stream, so it is bound by how many bytes are in flight when it starts: with one warp per
+// position the 32 store instructions of a position were issued one after another by a single warp.
 __global__ void __launch_bounds__(ENC_WARPS * 32) encode_bf16_kernel(const sc_position *__restrict__ pos, int n,
                                                                      __nv_bfloat16 *__restrict__ out,
                                                                      float *__restrict__ meta_out)
 {
-    __shared__ uint64_t s_slots[ENC_WARPS][64];
-    __shared__ uint64_t s_masks[ENC_WARPS][128];
+    __shared__ uint64_t s_slots[64];
+    __shared__ uint64_t s_masks[128];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x * ENC_WARPS + warp;
+    const int b = blockIdx.x;
     if (b >= n) return;
-    build_masks(pos + b, s_slots[warp], s_masks[warp], lane);
-    const uint64_t *masks = s_masks[warp];
+    if (warp == 0) build_masks(pos + b, s_slots, s_masks, lane);
+    __syncthreads();
     uint4 *dst = reinterpret_cast<uint4 *>(out + (size_t)b * 64 * C_IN_PAD);
     const int c0 = (lane & 15) * 8;
     uint64_t m[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) m[j] = masks[c0 + j];
-    // two rows (2 x 256 B) per warp store instruction
-#pragma unroll 4
-    for (int it = 0; it < 32; it++) {
-        int s = it * 2 + (lane >> 4);
+    for (int j = 0; j < 8; j++) m[j] = s_masks[c0 + j];
+    // two rows (2 x 256 B) per warp store instruction; this warp: squares [16 warp, 16 warp + 16)
+#pragma unroll
+    for (int it8 = 0; it8 < 8; it8++) {
+        const int it = warp * 8 + it8;
+        const int s = it * 2 + (lane >> 4);
         uint32_t w[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -137,7 +141,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) encode_bf16_kernel(const sc_po
         }
         dst[it * 32 + lane] = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    if (lane < 8) meta_out[b * 8 + lane] = lane < SC_N_META ? (float)pos[b].meta[lane] : 0.f;
+    if (warp == 0 && lane < 8) meta_out[b * 8 + lane] = lane < SC_N_META ? (float)pos[b].meta[lane] : 0.f;
 }
 
 int launch_encode_i8(const sc_position *d_pos, int n, int8_t *out, int32_t *meta_out, cudaStream_t st)
@@ -159,7 +163,7 @@ int launch_encode_f32(const sc_position *d_pos, int n, float *out, float *meta_o
 int launch_encode_bf16(const sc_position *d_pos, int n, __nv_bfloat16 *out, float *meta_out, cudaStream_t st)
 {
     if (n <= 0) return SC_OK;
-    encode_bf16_kernel<<<(n + ENC_WARPS - 1) / ENC_WARPS, ENC_WARPS * 32, 0, st>>>(d_pos, n, out, meta_out);
+    encode_bf16_kernel<<<n, ENC_WARPS * 32, 0, st>>>(d_pos, n, out, meta_out);
     SCB_CUDA(cudaGetLastError());
     return SC_OK;
 }

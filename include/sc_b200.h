@@ -212,6 +212,10 @@ int sc_selfplay_run_many(sc_selfplay **sps, int n, int64_t max_games, int64_t ma
  * ({"steps": [[uci, q, [[uci, n, q, uct], ...]], ...], "outcome": {...} | null}); returns the number
  * of bytes needed (including the NUL); copies at most `cap`. */
 int64_t sc_selfplay_trace_json(sc_selfplay *sp, int64_t k, char *buf, int64_t cap);
+/* which game the k-th finished trace is: the game's start order within the run (0-based; the games sitting in the tree
+ * slots at the start are 0 .. n_trees-1, every later game takes the next number when its slot frees up); -1 if k is out
+ * of range.  Lets a caller name trace files by game instead of by finishing order (scripts/run_batch: trace{k}.json). */
+int64_t sc_selfplay_trace_game(sc_selfplay *sp, int64_t k);
 int sc_selfplay_destroy(sc_selfplay *sp);
 
 /* One self-play game through the one-leaf-at-a-time interface of the reference: the C++ mirror of

@@ -78,6 +78,7 @@ struct Tree {
     // current search / game
     int rollouts_done = 0;
     int rollout_target = 0;  // rollouts of the current move (--rollout-num, or --rollout-factor x legal moves at the root)
+    int64_t game_no = 0;     // start order of this slot's current game within the run (0-based)
     bool failed = false;     // the network returned a non-finite prior / value for one of this game's leaves
     int move_index = 0;      // `i` of the self-play loop (main.rs:168)
     int ply_offset = 0;      // arena: the (even) group ply at which this slot's current game started
@@ -141,6 +142,7 @@ struct sc_selfplay {
     int64_t max_games = 0, max_moves = 0;
     std::mutex trace_mu;
     std::vector<std::string> traces;
+    std::vector<int64_t> trace_games;  // start order of the game each kept trace belongs to
     // worker pool
     std::vector<std::thread> workers;
     std::mutex mu;
@@ -397,6 +399,7 @@ bool play_move(sc_selfplay *sp, Tree &t)
             std::string js = trace_to_json(t.trace);
             std::lock_guard<std::mutex> lk(sp->trace_mu);
             sp->traces.push_back(std::move(js));
+            sp->trace_games.push_back(t.game_no);
         }
         sp->games_finished++;
     }
@@ -482,6 +485,7 @@ void play_move_arena(sc_selfplay *sp, Tree &t)
             std::string js = trace_to_json(t.trace);
             std::lock_guard<std::mutex> lk(sp->trace_mu);
             sp->traces.push_back(std::move(js));
+            sp->trace_games.push_back(t.game_no);
         }
         sp->games_finished++;
     }
@@ -571,6 +575,7 @@ void finish_pending(sc_selfplay *sp, Tree &t, const float *priors, const float *
         } else {
             const int off = t.ply_offset, mi = t.move_index;
             t.new_game(0);
+            t.game_no = started - 1;
             // arena: the replacement game starts at the next even group ply after the one the slot was searching
             if (sp->arena) t.ply_offset = (off + mi + 2) & ~1;
         }
@@ -591,6 +596,7 @@ void advance_tree_arena(sc_selfplay *sp, Tree &t, int group_ply, const BatchOut 
             return;
         }
         t.new_game(0);
+        t.game_no = k - 1;
         t.ply_offset = (group_ply + 2) & ~1;  // > group_ply and even
     };
     for (;;) {
@@ -620,6 +626,7 @@ void advance_tree(sc_selfplay *sp, Tree &t, const BatchOut &out, const float *pr
                     return false;
                 }
                 t.new_game(0);
+                t.game_no = started - 1;
             }
             if (sp->max_moves > 0 && sp->moves.load(std::memory_order_relaxed) >= sp->max_moves) {
                 t.active = false;
@@ -749,6 +756,7 @@ int sc_selfplay_create(sc_engine *e, const sc_selfplay_config *cfg, sc_selfplay 
     for (int i = 0; i < cfg->n_trees; i++) {
         sp->trees[i].rng.seed(cfg->seed * 0x9E3779B97F4A7C15ULL + (uint64_t)i + 1);
         sp->trees[i].new_game(0);
+        sp->trees[i].game_no = i;
     }
     for (int g = 0; g < sp->n_groups; g++) {
         sc_selfplay::Group &G = sp->groups[g];
@@ -938,6 +946,14 @@ int64_t sc_selfplay_trace_json(sc_selfplay *sp, int64_t k, char *buf, int64_t ca
         buf[n] = 0;
     }
     return (int64_t)s.size() + 1;
+}
+
+int64_t sc_selfplay_trace_game(sc_selfplay *sp, int64_t k)
+{
+    if (!sp) return -1;
+    std::lock_guard<std::mutex> lk(sp->trace_mu);
+    if (k < 0 || k >= (int64_t)sp->trace_games.size()) return -1;
+    return sp->trace_games[(size_t)k];
 }
 
 int sc_random_positions(int n, uint64_t seed, int max_ply, sc_position *pos_out, sc_move *moves_out, int32_t *move_off,

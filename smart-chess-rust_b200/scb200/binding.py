@@ -25,7 +25,7 @@ DECLARED_SYMBOLS = [
     "sc_eval_submit", "sc_eval_wait", "sc_selfplay_create", "sc_selfplay_run", "sc_selfplay_trace_json",
     "sc_selfplay_destroy", "sc_rules_probe", "sc_arena_create", "sc_encode_steps", "sc_timed_flops_per_leaf",
     "sc_random_positions", "sc_test_dirichlet", "sc_game_selfplay", "sc_rules_perft", "sc_device_info",
-    "sc_selfplay_run_many", "sc_debug_tower", "sc_rules_probe_fen",
+    "sc_selfplay_run_many", "sc_debug_tower", "sc_rules_probe_fen", "sc_selfplay_trace_game",
 ]
 
 
@@ -98,6 +98,8 @@ def load_library():
         L.sc_game_selfplay.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int64]
         L.sc_selfplay_trace_json.restype = C.c_int64
         L.sc_selfplay_trace_json.argtypes = [C.c_void_p, C.c_int64, C.c_char_p, C.c_int64]
+        L.sc_selfplay_trace_game.restype = C.c_int64
+        L.sc_selfplay_trace_game.argtypes = [C.c_void_p, C.c_int64]
         L.sc_selfplay_destroy.argtypes = [C.c_void_p]
         L.sc_arena_create.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(SelfPlayConfig), C.POINTER(C.c_void_p)]
         L.sc_random_positions.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
@@ -340,6 +342,10 @@ class SelfPlay:
         buf = C.create_string_buffer(n)
         L.sc_selfplay_trace_json(self._h, k, buf, n)
         return self._json.loads(buf.value.decode())
+
+    def trace_game(self, k: int) -> int:
+        """start order (0-based) of the game the k-th finished trace belongs to; -1 if there is no such trace"""
+        return int(load_library().sc_selfplay_trace_game(self._h, k))
 
     def close(self):
         if getattr(self, "_h", None):

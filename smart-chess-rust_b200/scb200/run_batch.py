@@ -50,10 +50,11 @@ def main(argv=None):
                   pipeline_groups=2 if trees >= 2 else 1, keep_traces=True, leaves_per_tree=a.leaves_per_tree)
     st = sp.run(max_games=len(mine))
     os.makedirs(a.prefix, exist_ok=True)
-    for k, gid in enumerate(mine):
+    for k in range(len(mine)):
         tr = sp.trace(k)
         if tr is None:
             break
+        gid = mine[sp.trace_game(k)]          # the file is named after the GAME (its id in the run), not its finishing order
         with open(os.path.join(a.prefix, f"trace{gid + 1}.json"), "w") as f:
             json.dump(tr, f)
         print(f"{gid + 1:02d}, {json.dumps(tr['outcome'], separators=(',', ':'))}, num-steps: {len(tr['steps'])}")

@@ -403,3 +403,17 @@ def test_host_search_is_clean_under_thread_sanitizer():
         pytest.skip("toolchain without ThreadSanitizer")
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "tsan harness ok" in r.stdout and "WARNING: ThreadSanitizer" not in r.stderr
+
+
+def test_trace_game_numbers_are_a_permutation_of_the_started_games():
+    """sc_selfplay_trace_game: every kept trace knows which game of the run it is (start order), so files can be named
+    by game instead of by finishing order (scripts/run_batch writes trace{k}.json for game k)."""
+    import scb200
+
+    sp = scb200.SelfPlay(None, n_trees=4, rollout_num=8, num_steps=12, evaluator="hash", keep_traces=True,
+                         temperature_switch=12, temperature=1.0, seed=2, n_threads=2)
+    st = sp.run(max_games=10)
+    ids = [sp.trace_game(k) for k in range(st["games_finished"])]
+    assert st["games_finished"] == 10 and sorted(ids) == list(range(10))
+    assert sp.trace_game(10) == -1 and sp.trace_game(-1) == -1
+    sp.close()

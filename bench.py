@@ -587,6 +587,9 @@ def main():
                 if "sustained" in roof:
                     roof["sustained"]["peak"] = peaks["tflops"] / 6
                     roof["sustained"]["frac"] = roof["sustained"]["achieved"] / roof["sustained"]["peak"]
+                    if "frac_at_equal_clock" in roof["sustained"]:
+                        roof["sustained"]["frac_at_equal_clock"] = (roof["sustained"]["frac"] * roof["sustained"]["peak_measured_at_sm_mhz"]
+                                                                    / roof["sustained"]["this_run_sm_mhz"])
         cpu = None
         if world == 1 and args.cpu_budget > 0:
             b, b1, n, thr = cpu_reference_throughput(sd, oracle_sample(512, seed=1000), args.cpu_budget, 64)

@@ -85,3 +85,27 @@ def test_latency_kernel_vs_oracle(co, net19, leaves):
             print(f"sc_eval n={nb}: {(time.perf_counter() - t0) / 30 * 1e3:.3f} ms")
     finally:
         e.close()
+
+
+def test_latency_kernel_repeatable_under_random_batch_sizes(net19, leaves, monkeypatch):
+    """Race hunt: 300 calls with random batch sizes (every cluster shape, back to back on one engine, so the exchange
+    buffers, mbarrier phases and the SE weight staging are re-used across launches); each leaf's result must be the
+    bits the throughput kernel produced for it, every time."""
+    import scb200
+
+    games, (pos, moves, off, mv_all) = leaves
+    ref = _eval_sizes(net19[1], pos, moves, off, (96,), {"SCB200_LATENCY": "0"}, monkeypatch)[96]
+    for k in ("SCB200_LATENCY", "SCB200_LAT_CLUSTER", "SCB200_LAT_ONE_BOARD"):
+        monkeypatch.delenv(k, raising=False)
+    e = scb200.Engine(net19[1], 0, scb200.SC_MODE_BF16, 128)
+    rng = np.random.RandomState(5)
+    try:
+        for it in range(300):
+            n = int(rng.choice([1, 2, 3, 5, 8, 15, 16, 17, 31, 33, 34, 40, 63, 66]))
+            lo = int(rng.randint(0, 96 - n + 1))
+            sub_off = (off[lo:lo + n + 1] - off[lo]).astype(np.int32)
+            pri, val = e.eval(pos[lo:lo + n], moves[off[lo]:off[lo + n]], sub_off)
+            assert np.array_equal(val, ref[1][lo:lo + n]), (it, n, lo)
+            assert np.array_equal(pri, ref[0][off[lo]:off[lo + n]]), (it, n, lo)
+    finally:
+        e.close()

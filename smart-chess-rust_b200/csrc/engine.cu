@@ -882,13 +882,19 @@ int sc_eval(sc_engine *e, int n, const sc_position *pos, const sc_move *moves, c
         memcpy(e->h_small_in, pos, pos_b);
         memcpy(e->h_small_in + pos_b, move_off, off_b);
         memcpy(e->h_small_in + pos_b + off_b, moves, mv_b);
-        SCB_CUDA(cudaMemcpyAsync(e->d_small_in, e->h_small_in, pos_b + off_b + mv_b, cudaMemcpyHostToDevice, st));
+        // inputs: up to 16 leaves are read by the kernels straight from the pinned staging buffer (a few hundred bytes per
+        // leaf over PCIe inside the encode / gather kernels instead of a copy engine round trip before the first launch)
+        static const bool zero_copy_in = !(getenv("SCB200_ZERO_COPY_IN") && getenv("SCB200_ZERO_COPY_IN")[0] == '0');
+        const uint8_t *in_dev = e->d_small_in;
+        if (zero_copy_in && n <= 16)
+            in_dev = e->h_small_in;
+        else
+            SCB_CUDA(cudaMemcpyAsync(e->d_small_in, e->h_small_in, pos_b + off_b + mv_b, cudaMemcpyHostToDevice, st));
         // results: the kernels store priors and values straight into the pinned (device-mapped under UVA) staging buffer --
         // posted writes over PCIe instead of a device buffer + a copy; the stream sync makes them visible to the host
         static const bool zero_copy_out = !(getenv("SCB200_ZERO_COPY_OUT") && getenv("SCB200_ZERO_COPY_OUT")[0] == '0');
         float *out_dev = zero_copy_out ? e->h_small_out : e->d_small_out;
-        SCB_CHECK(sc_eval_device(e, n, e->d_small_in, e->d_small_in + pos_b + off_b, e->d_small_in + pos_b, total, out_dev + n,
-                                 out_dev, st));
+        SCB_CHECK(sc_eval_device(e, n, in_dev, in_dev + pos_b + off_b, in_dev + pos_b, total, out_dev + n, out_dev, st));
         if (!zero_copy_out)
             SCB_CUDA(cudaMemcpyAsync(e->h_small_out, e->d_small_out, sizeof(float) * (size_t)(n + total), cudaMemcpyDeviceToHost, st));
         SCB_CUDA(cudaStreamSynchronize(st));

@@ -1203,7 +1203,7 @@ struct TcConv {
 };
 
 int tc_encode_map(CUtensorMap *m, const void *ptr, int rank, const cuuint64_t *dims, const cuuint64_t *strides,
-                      const cuuint32_t *box, const char *what)
+                  const cuuint32_t *box, const char *what, bool swizzle128)
 {
     EncodeTiledFn enc = get_encode();
     if (!enc) {
@@ -1212,7 +1212,8 @@ int tc_encode_map(CUtensorMap *m, const void *ptr, int rank, const cuuint64_t *d
     }
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(ptr), dims, strides, box,
-                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error(std::string("cuTensorMapEncodeTiled(") + what + ") failed: " + std::to_string((int)r));

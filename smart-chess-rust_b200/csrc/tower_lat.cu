@@ -15,8 +15,11 @@
 //     (tc_ptx.cuh), so every CTA computes ITS chunks' partial sums for all 128 hidden units and pushes them to the
 //     cluster -- one exchange -- and everybody adds the eight partials in the fixed tree; FC2 and the gate are per
 //     channel, i.e. local;
-//   * layer l+1 reads layer l's output through L2: after its stores a CTA signals the `ready` mbarrier of every CTA of
-//     the cluster, whose TMA warp then starts the next layer's activation loads.  Weight loads never wait for
+//   * layer l+1 reads layer l's output through L2: the epilogue threads put the CTA's slice into a shared-memory tile
+//     laid out as the TMA box {NC channels, 8 files, boards, 8 ranks}, ONE thread stores it (cp.async.bulk.tensor) and
+//     waits for the write to complete, then the CTA signals the `ready` mbarrier of every CTA of the cluster, whose TMA
+//     warp starts the next layer's activation loads (128 threads storing to global memory and fencing generic -> async
+//     proxy at GPU scope cost 0.9 k cycles per layer more).  Weight loads never wait for
 //     activations: their producer warp runs ahead through the layers as far as its ring allows.
 // A tile of ONE board (NB = 1: 64 rows, tcgen05.mma M64) halves the shared-memory operand traffic that bounds the MMA
 // phase at these narrow N; it is used while there are enough clusters for one board each.
@@ -41,6 +44,7 @@ struct alignas(64) LatLayer {
     CUtensorMap map_a;   // input activations {C, file, board, rank}, box of two boards
     CUtensorMap map_a1;  // the same tensor, box of one board
     CUtensorMap map_w;  // weights {cin, cout, dx, dy}, box {64, NC, 1, 3 | 1}
+    CUtensorMap map_o, map_o1;  // output {C, file, board, rank}, box {NC, 8, 2 | 1, 8}, no swizzle (TMA store hand-over)
     void *out;
     const __nv_bfloat16 *resid;
     const float *bias, *gamma, *beta;
@@ -54,6 +58,7 @@ struct LatArgs {
     int n_layers;
     int n_tiles;
     long long *prof;  // optional [grid][16] cycle counters (SCB200_PHASE_PROFILE=1)
+    int tma_store;    // hand-over: stage the CTA's output slice in shared memory, ONE thread stores it with the TMA
 };
 
 template <int CL, int NB = 2> struct LatCfg {
@@ -77,7 +82,8 @@ template <int CL, int NB = 2> struct LatCfg {
     static constexpr int OFF_HID = OFF_HIDP + 8 * 2 * 128 * 4;  // [2][128]
     static constexpr int OFF_FC2P = OFF_HID + 2 * 128 * 4;      // [2 * NC outputs][4 chunk sums]
     static constexpr int OFF_GATE = OFF_FC2P + 2 * NC * 4 * 4;  // [2][NC]
-    static constexpr int OFF_BARS = (OFF_GATE + 2 * NC * 4 + 7) & ~7;
+    static constexpr int OFF_OUT = (OFF_GATE + 2 * NC * 4 + 127) & ~127;  // [64 NB rows][NC] bf16 output staging (TMA store)
+    static constexpr int OFF_BARS = OFF_OUT + 128 * NC * 2;
     static constexpr int N_BARS = 2 * 8 + 7;  // up to 8 stages (full, empty) + 7 single barriers, the same in every variant
     static constexpr int SMEM_BYTES = OFF_BARS + N_BARS * 8 + 16;
 };
@@ -435,6 +441,10 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs
 #pragma unroll
             for (int j = 0; j < NC; j++) a[j] = ln_apply(a[j], mean, rstd, s_gamma[j], s_beta[j]);
             __nv_bfloat16 *og = static_cast<__nv_bfloat16 *>(L.out) + grow * 256 + c0;
+            // TMA-store hand-over: the row goes to the staging tile [row][NC] instead (row = accumulator row = the box's
+            // (rank, board, file) order, so the tile is exactly the store box)
+            uint4 *so = reinterpret_cast<uint4 *>(smem + Cfg::OFF_OUT + row * NC * 2);
+            uint4 *odst = args.tma_store ? so : reinterpret_cast<uint4 *>(og);
             if (!L.se) {
                 // ---- bias + LayerNorm (+ReLU) -> bf16 ----
                 if (active) {
@@ -451,7 +461,7 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs
                             __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);
                             pw[k] = *reinterpret_cast<uint32_t *>(&h);
                         }
-                        reinterpret_cast<uint4 *>(og)[i] = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+                        odst[i] = make_uint4(pw[0], pw[1], pw[2], pw[3]);
                     }
                 }
             } else {
@@ -559,7 +569,7 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs
                             __nv_bfloat162 h = __floats2bfloat162_rn(o0, o1);
                             pw[k] = *reinterpret_cast<uint32_t *>(&h);
                         }
-                        reinterpret_cast<uint4 *>(og)[i] = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+                        odst[i] = make_uint4(pw[0], pw[1], pw[2], pw[3]);
                     }
                 }
             }
@@ -567,10 +577,25 @@ __global__ void __launch_bounds__(LAT_THREADS, 1) lat_tower_kernel(const LatArgs
             //      to the async proxy (this fence waits for them at GPU scope), block barrier, then ONE warp signals the
             //      `ready` barrier of every CTA (release is cumulative over the barrier) ----
             const long long tf0 = prof ? clock64() : 0;
-            asm volatile("fence.proxy.async;" ::: "memory");
+            if (args.tma_store)
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // staging tile -> visible to the TMA
+            else
+                asm volatile("fence.proxy.async;" ::: "memory");
             const long long tf1 = prof ? clock64() : 0;
             lat_epi_sync();
             const long long tf2 = prof ? clock64() : 0;
+            if (args.tma_store && quad == 0) {
+                // one thread stores the CTA's slice and waits until the write is complete, then the warp signals
+                if (elect_one()) {
+                    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                                     NB == 2 ? &L.map_o : &L.map_o1),
+                                 "r"(smem_base + (uint32_t)Cfg::OFF_OUT), "r"(c0), "r"(0), "r"(tile * NB), "r"(0)
+                                 : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                }
+                __syncwarp();
+            }
             if (quad == 0 && lane < CL) mbar_arrive_cluster(map_to_cta(bar_ready, (uint32_t)lane));
             if (prof) {
                 pe_pfence += tf1 - tf0;
@@ -656,6 +681,14 @@ int lat_tower_create(LatTower **out, const LatLayerDesc *descs, int n, int board
                 rc = tc_encode_map(&L.map_a1, d.in, 4, dims, strides, box, "activations (rank, file), one board");
             }
             if (rc == SC_OK) {
+                // output {C, file, board, rank}: box of this CTA's NC channels of the tile's boards, unswizzled
+                cuuint64_t dims[4] = {256, 8, (cuuint64_t)boards_alloc, 8};
+                cuuint64_t strides[3] = {256 * 2, 256 * 128, 256 * 16};
+                cuuint32_t box2[4] = {(cuuint32_t)NC, 8, 2, 8}, box1[4] = {(cuuint32_t)NC, 8, 1, 8};
+                rc = tc_encode_map(&L.map_o, d.out, 4, dims, strides, box2, "output slice, two boards", false);
+                if (rc == SC_OK) rc = tc_encode_map(&L.map_o1, d.out, 4, dims, strides, box1, "output slice, one board", false);
+            }
+            if (rc == SC_OK) {
                 // weights [tap = dy * 3 + dx][256][cin_pad] as {cin, cout, dx, dy}
                 const int nd = d.taps == 9 ? 3 : 1;
                 cuuint64_t dims[4] = {(cuuint64_t)d.cin_pad, 256, (cuuint64_t)nd, (cuuint64_t)nd};
@@ -728,6 +761,9 @@ template <int CL, int NB> static int lat_launch(const LatTower *t, int v, int n_
     a.n_layers = max_layers > 0 && max_layers < t->n_layers ? max_layers : t->n_layers;
     a.n_tiles = n_tiles;
     a.prof = nullptr;
+    // SCB200_LAT_TMA_STORE=0: per-thread global stores + async-proxy fence instead (A/B: 519 k vs 503 k cycles at n = 1)
+    static const bool tma_store = !(getenv("SCB200_LAT_TMA_STORE") && getenv("SCB200_LAT_TMA_STORE")[0] == '0');
+    a.tma_store = tma_store ? 1 : 0;
     static const bool want_prof = getenv("SCB200_PHASE_PROFILE") != nullptr;
     if (want_prof) {
         SCB_CUDA(cudaMalloc(&a.prof, (size_t)n_tiles * CL * 16 * sizeof(long long)));
